@@ -1,0 +1,210 @@
+/*
+ * jafpro_b200 — C ABI of the B200-native appearance warp-and-fuse path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every
+ * entry point names the reference interface it replaces (paths relative to the
+ * Larry-u/JAFPro tree; "NR" = third_party/neural_renderer/neural_renderer).
+ * INTEGRATION.md shows the reference-side binding for each one.
+ *
+ * Conventions (kept from the reference's extension, NR/cuda/rasterize_cuda.cpp:70-95):
+ *   - the CALLER allocates every output and workspace; functions fill them in place;
+ *   - all pointers are DEVICE pointers of the current CUDA device unless the
+ *     function name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which
+ *     is what the reference launches on, rasterize_cuda_kernel.cu:616);
+ *   - tensors are dense, row-major, in the shapes written next to each argument.
+ * Unlike the reference (which only printf()s launch failures,
+ * rasterize_cuda_kernel.cu:624-626,647-649) every function returns a status:
+ *   0 success, <0 failure; jaf_last_error() gives a thread-local message.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef JAFPRO_B200_H_
+#define JAFPRO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JAF_OK 0
+#define JAF_ERR_INVALID (-1)     /* bad argument (NULL pointer, unsupported shape ...) */
+#define JAF_ERR_CUDA (-2)        /* a CUDA call or kernel launch failed                */
+#define JAF_ERR_UNSUPPORTED (-3) /* valid request this build cannot serve              */
+
+#define JAF_LAYOUT_PLANAR 0 /* [.., C, H, W]  (the reference's NCHW)          */
+#define JAF_LAYOUT_NHWC 1   /* [.., H, W, C]  (channels-last)                 */
+#define JAF_DTYPE_F32 0
+#define JAF_DTYPE_BF16 1
+
+int jaf_version(void);
+const char* jaf_last_error(void);
+/* Number of kernels this library has launched in the calling process (monotonic). */
+uint64_t jaf_launch_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * a1-a3  projection + y flip + look_at + face gather
+ * replaces: orthographic_proj_withz_idrot (src/nmr.py:10-28), `proj_verts[:,:,1] *= -1`
+ *           (src/nmr.py:271), nr.look_at(proj, eye) (NR/look_at.py:6-62; identity rotation
+ *           for SMPLRenderer's eye, src/nmr.py:177), nr.vertices_to_faces
+ *           (NR/vertices_to_faces.py:4-22).
+ * cam [B,3] (s,tx,ty); verts [B,V,3]; faces_idx [F,3] int32 (shared by the batch,
+ * src/nmr.py:266); eye_z = float32(-(1/tan(30deg)+1)); faces_xyz out [B,F,3,3].
+ * --------------------------------------------------------------------------------- */
+int jaf_project_gather(const float* cam, const float* verts, const int32_t* faces_idx, int B, int V,
+                       int F, float eye_z, float* faces_xyz, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * a4-a6  face-index + barycentric-weight rasteriser
+ * replaces: rasterize_cuda.forward_face_index_map (NR/cuda/rasterize_cuda.cpp:70-95 ->
+ *           rasterize_cuda_kernel.cu:24-169,596-651) together with the Python around it:
+ *           the output fills of NR/rasterize.py:50-52 and the row flips of :334-338
+ *           (flip_rows=1), i.e. nr.rasterize_face_index_map_and_weight_map
+ *           (NR/rasterize.py:543-571) with anti_aliasing=False.
+ * faces_xyz [B,F,3,3]; fim out [B,S,S] int32 (-1 = background); wim out [B,S,S,3];
+ * depth out [B,S,S] or NULL (background = far); workspace: jaf_raster_workspace_bytes().
+ * fim is bit-exact with the reference kernels; wim/depth reproduce their fp32 operation
+ * order (including nvcc's FMA contraction) and are bit-exact as well.
+ * --------------------------------------------------------------------------------- */
+size_t jaf_raster_workspace_bytes(int B, int image_size);
+int jaf_raster_fim_wim(const float* faces_xyz, int B, int F, int image_size, float near_, float far_,
+                       int flip_rows, int32_t* fim, float* wim, float* depth, void* workspace,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * a7  SMPLRenderer.render_fim_wim (src/nmr.py:263-278) in one call: a1-a3 + a4-a6.
+ * faces_xyz out [B,F,3,3] may be NULL when the caller does not need `faces`
+ * (then the [B,13776,3,3] tensor never touches HBM).
+ * --------------------------------------------------------------------------------- */
+int jaf_render_fim_wim(const float* cam, const float* verts, const int32_t* faces_idx, int B, int V,
+                       int F, int image_size, float eye_z, float near_, float far_, float* faces_xyz,
+                       int32_t* fim, float* wim, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * a9  barycentric flow compose
+ * replaces: SMPLRenderer.cal_bc_transform (src/nmr.py:617-659).
+ * src_pts: per-face source coordinates, `stride` floats per vertex: 2 for the
+ * [B,F,3,2] tensor of the reference signature, 3 to read x,y straight from a
+ * faces_xyz [B,F,3,3] tensor.  negate_y=1 applies `src_f2verts[:,:,:,1] *= -1`
+ * (src/cal_flow.py:31) on the fly.  fim [B,H,W] int32; wim [B,H,W,3]; T out [B,H,W,2],
+ * -2 where fim == -1 (src/nmr.py:627).
+ * --------------------------------------------------------------------------------- */
+int jaf_flow_compose(const float* src_pts, int stride, int negate_y, const int32_t* fim,
+                     const float* wim, int B, int F, int H, int W, float* T, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * a8  float_estimate.cal_flow (src/cal_flow.py:28-35) in one call.  The source pose is
+ * projected but NOT rasterised (its fim/wim are dead in the reference, cal_flow.py:29).
+ * T out [B,S,S,2]; fim/wim out may be NULL (then they never touch HBM).
+ * workspace: jaf_raster_workspace_bytes(B, S).
+ * --------------------------------------------------------------------------------- */
+int jaf_cal_flow(const float* src_cam, const float* src_verts, const float* tgt_cam,
+                 const float* tgt_verts, const int32_t* faces_idx, int B, int V, int F,
+                 int image_size, float eye_z, float near_, float far_, float* T, int32_t* fim,
+                 float* wim, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * row F  fused bilinear backward warp of K references + visibility/softmax fusion
+ * replaces, in ONE pass over every input byte:
+ *   float_estimate.warp_image = F.grid_sample(src, flow, padding_mode='border')
+ *       (src/cal_flow.py:37-39; feature-map warps src/crn_model.py:463-566),
+ *   tsf * tgt_smpl_mask and the confidence blend (src/flow_net.py:91,98),
+ *   softmax-over-K weighting and the sum over K (src/networks.py:1230-1244,1264-1286).
+ * Per target pixel p of frame b (fp32 arithmetic, bf16 only as storage):
+ *   alpha = softmax_k(logits[b,k,p])            (uniform 1/K when logits == NULL)
+ *   v_k   = vis[b,k,p]  |  (fim[b,p] != -1)     (1 when both NULL)
+ *   fused = sum_k (alpha_k * v_k) * bilinear_border(ref[r,k], grid[b,k,p]);  r = ref_index[b] | b
+ *   fused *= tgt_mask[b,c|0,p]                  (when tgt_mask != NULL)
+ *   out_rgb = fake*conf + fused*(1-conf)        (RGB only, when fake and conf != NULL)
+ * K == 1 without logits/vis/fim reduces exactly to warp_image(src, T) * mask.
+ * --------------------------------------------------------------------------------- */
+typedef struct JafWarpFuseParams {
+  int32_t B, K, H, W;    /* target frames, references per frame, output size        */
+  int32_t Hs, Ws;        /* reference (source) size                                 */
+  int32_t C;             /* feature channels (0 = no feature tensor)                */
+  int32_t align_corners; /* torch 1.2 (pinned by the reference) == 1, torch >= 1.3 default == 0 */
+  int32_t feat_layout;   /* JAF_LAYOUT_*                                            */
+  int32_t feat_dtype;    /* JAF_DTYPE_*                                             */
+  int32_t mask_c;        /* channels of tgt_mask: 1 or 3                            */
+  int32_t reserved;
+  const float* rgb;         /* [R,K,3,Hs,Ws] f32 planar, or NULL                    */
+  const void* feat;         /* [R,K,C,Hs,Ws] | [R,K,Hs,Ws,C], or NULL               */
+  const int32_t* ref_index; /* [B] reference-set index per target frame, or NULL    */
+  const float* grid;        /* [B,K,H,W,2] transfer flows, (x,y) in NDC             */
+  const float* logits;      /* [B,K,H,W] or NULL                                    */
+  const float* vis;         /* [B,K,H,W] or NULL                                    */
+  const int32_t* fim;       /* [B,H,W] or NULL (default visibility)                 */
+  const float* tgt_mask;    /* [B,mask_c,H,W] or NULL                               */
+  const float* fake;        /* [B,3,H,W] or NULL                                    */
+  const float* conf;        /* [B,1,H,W] or NULL                                    */
+  float* out_rgb;           /* [B,3,H,W] or NULL                                    */
+  void* out_feat;           /* [B,C,H,W] | [B,H,W,C] (layout/dtype of feat) or NULL */
+  float* warped_rgb;        /* [B,K,3,H,W] per-reference warps, or NULL             */
+  void* stream;
+} JafWarpFuseParams;
+
+int jaf_warp_fuse(const JafWarpFuseParams* p);
+
+/* Same operation with every pointer in `p` a HOST pointer (pinned or pageable): the
+ * library stages frames through device buffers it owns, overlapping H2D copies, the
+ * kernel and D2H copies on its own streams, `frames_per_chunk` target frames at a time
+ * (0 = pick).  Reference sets are uploaded once per distinct ref_index run.  Blocking. */
+int jaf_warp_fuse_host(const JafWarpFuseParams* p, int frames_per_chunk);
+
+/* ---------------------------------------------------------------------------------
+ * a10  float_estimate.warp_image (src/cal_flow.py:37-39): jaf_warp_fuse with K = 1.
+ * src [N,C,Hs,Ws] f32 planar; grid [N,H,W,2]; out [N,C,H,W].
+ * --------------------------------------------------------------------------------- */
+int jaf_warp_image(const float* src, const float* grid, int N, int C, int Hs, int Ws, int H, int W,
+                   int align_corners, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * a11  Propagation3DFlowNet.forward lines 91 and 98 (src/flow_net.py:87-99)
+ * tsf, fake, pred, masked_out: [B,C,H,W]; mask [B,mask_c,H,W] (mask_c 1 or C) or NULL;
+ * conf [B,1,H,W].  masked_out (nullable) = tsf*mask; pred (nullable) =
+ * fake*conf + (tsf*mask)*(1-conf).
+ * --------------------------------------------------------------------------------- */
+int jaf_mask_blend(const float* fake, const float* tsf, const float* mask, int mask_c,
+                   const float* conf, int B, int C, int H, int W, float* masked_out, float* pred,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * a12  softmax-over-K reduction of Downsampler_mask.forward (src/networks.py:1264-1286)
+ * feat [B,K*C,H,W] (channel-concatenated references); logits [B,K,H,W] = the mask conv
+ * output BEFORE nn.Softmax(dim=1); out [B,C,H,W].
+ * --------------------------------------------------------------------------------- */
+int jaf_softmax_fuse(const float* feat, const float* logits, int B, int K, int C, int H, int W,
+                     float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * a13  ConvLSTMCell.forward (src/convLSTM.py:41-56), fp32 reference layout
+ * x [B,Cin,H,W]; h,c [B,Ch,H,W]; weight [4Ch,Cin+Ch,kh,kw]; bias [4Ch] or NULL;
+ * h_out,c_out [B,Ch,H,W].  Gate order in the 4Ch rows is i,f,o,g (:46).
+ * CUDA-core direct convolution with the gate epilogue fused — the right tool for the
+ * reference's own channel counts (12..96, src/networks.py:1304-1313).
+ * --------------------------------------------------------------------------------- */
+int jaf_convlstm_step_f32(const float* x, const float* h, const float* c, const float* weight,
+                          const float* bias, int B, int Cin, int Ch, int H, int W, int kh, int kw,
+                          float* h_out, float* c_out, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * a13  the same cell as a tensor-core implicit GEMM (tcgen05 + TMEM + TMA), for wide
+ * cells (BASELINE config 4: Cin = Ch = 256, 64x64, B = 16).  3x3 kernel, pad 1.
+ * Activations are channels-last bf16: x [B,H,W,Cin], h [B,H,W,Ch]; the cell state stays
+ * fp32: c, c_out [B,H,W,Ch]; h_out [B,H,W,Ch] bf16.  `wpack` is the weight repacked once
+ * by jaf_convlstm_pack_weight (bf16, tap-major, gate-interleaved per 64 hidden channels);
+ * bias [4Ch] f32 or NULL.  Requirements: Cin % 64 == 0, Ch % 64 == 0, W % 64 == 0 or
+ * 128 % W == 0 (whole rows per 128-pixel tile).
+ * --------------------------------------------------------------------------------- */
+size_t jaf_convlstm_wpack_bytes(int Cin, int Ch);
+int jaf_convlstm_pack_weight(const float* weight /* [4Ch,Cin+Ch,3,3] f32 */, int Cin, int Ch,
+                             void* wpack, void* stream);
+int jaf_convlstm_step_tc(const void* x, const void* h, const float* c, const void* wpack,
+                         const float* bias, int B, int Cin, int Ch, int H, int W, void* h_out,
+                         float* c_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAFPRO_B200_H_ */

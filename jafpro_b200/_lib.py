@@ -1,0 +1,96 @@
+"""ctypes binding of ``libjafpro_b200.so`` (the C ABI in include/jafpro_b200.h).
+
+There is no fallback: if the library is missing the import fails loudly, and every
+non-zero status becomes a ``RuntimeError`` carrying ``jaf_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjafpro_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+_vp, _i, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_uint64
+
+
+class WarpFuseParams(C.Structure):
+    """``JafWarpFuseParams`` (include/jafpro_b200.h)."""
+    _fields_ = [
+        ("B", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("Hs", C.c_int32), ("Ws", C.c_int32), ("C", C.c_int32),
+        ("align_corners", C.c_int32), ("feat_layout", C.c_int32), ("feat_dtype", C.c_int32),
+        ("mask_c", C.c_int32), ("reserved", C.c_int32),
+        ("rgb", _vp), ("feat", _vp), ("ref_index", _vp), ("grid", _vp), ("logits", _vp),
+        ("vis", _vp), ("fim", _vp), ("tgt_mask", _vp), ("fake", _vp), ("conf", _vp),
+        ("out_rgb", _vp), ("out_feat", _vp), ("warped_rgb", _vp), ("stream", _vp),
+    ]
+
+
+# name -> (restype, argtypes); kept in the order of include/jafpro_b200.h
+SIGNATURES = {
+    "jaf_version": (_i, []),
+    "jaf_last_error": (C.c_char_p, []),
+    "jaf_launch_count": (_u64, []),
+    "jaf_project_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "jaf_raster_workspace_bytes": (_sz, [_i, _i]),
+    "jaf_raster_fim_wim": (_i, [_vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "jaf_render_fim_wim": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "jaf_flow_compose": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "jaf_cal_flow": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "jaf_warp_fuse": (_i, [C.POINTER(WarpFuseParams)]),
+    "jaf_warp_fuse_host": (_i, [C.POINTER(WarpFuseParams), _i]),
+    "jaf_warp_image": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "jaf_mask_blend": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "jaf_softmax_fuse": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "jaf_convlstm_step_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "jaf_convlstm_wpack_bytes": (_sz, [_i, _i]),
+    "jaf_convlstm_pack_weight": (_i, [_vp, _i, _i, _vp, _vp]),
+    "jaf_convlstm_step_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``libjafpro_b200.so`` (nvcc cross-compiles
+    without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libjafpro_b200.so failed")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C jafpro_b200/csrc`). "
+                "jafpro_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().jaf_last_error().decode("utf-8", "replace")
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        raise RuntimeError(f"jafpro_b200 {what} failed ({status}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib().jaf_launch_count())

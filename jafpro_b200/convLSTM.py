@@ -1,0 +1,112 @@
+"""Drop-in for ``src/convLSTM.py``: ``ConvLSTMCell`` (:7-63) and ``ConvLSTM`` (:66-165) with the
+whole cell step (cat, conv, split, gates, state update) in one fused kernel."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class ConvLSTMCell(nn.Module):
+    """Same constructor, parameters (``conv.weight`` [4Ch,Cin+Ch,kh,kw], ``conv.bias``) and forward
+    signature as the reference cell, so its state_dict loads unchanged."""
+
+    def __init__(self, input_size, input_dim, hidden_dim, kernel_size, bias):
+        super().__init__()
+        self.height, self.width = input_size
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.kernel_size = kernel_size
+        self.padding = kernel_size[0] // 2, kernel_size[1] // 2
+        self.bias = bias
+        # parameter holder only (same init as the reference); the convolution runs in the fused kernel
+        self.conv = nn.Conv2d(in_channels=input_dim + hidden_dim, out_channels=4 * hidden_dim,
+                              kernel_size=kernel_size, padding=self.padding, bias=bias)
+
+    def forward(self, input, prev_state):
+        h_prev, c_prev = prev_state
+        return ops.convlstm_step(input.contiguous(), h_prev.contiguous(), c_prev.contiguous(),
+                                 self.conv.weight.contiguous(), self.conv.bias)
+
+    def init_hidden(self, batch_size, cuda=True):
+        dev = self.conv.weight.device  # the reference hard-codes .cuda() (:58-63)
+        z = torch.zeros(batch_size, self.hidden_dim, self.height, self.width, device=dev)
+        return z, z.clone()
+
+
+class ConvLSTM(nn.Module):
+    def __init__(self, input_size, input_dim, hidden_dim, kernel_size, num_layers, batch_first=False, bias=True,
+                 return_all_layers=False):
+        super().__init__()
+        self._check_kernel_size_consistency(kernel_size)
+        kernel_size = self._extend_for_multilayer(kernel_size, num_layers)
+        hidden_dim = self._extend_for_multilayer(hidden_dim, num_layers)
+        if not len(kernel_size) == len(hidden_dim) == num_layers:
+            raise ValueError('Inconsistent list length.')
+        self.height, self.width = input_size
+        self.input_dim, self.hidden_dim, self.kernel_size = input_dim, hidden_dim, kernel_size
+        self.num_layers, self.batch_first, self.bias = num_layers, batch_first, bias
+        self.return_all_layers = return_all_layers
+        self.cell_list = nn.ModuleList([
+            ConvLSTMCell((self.height, self.width), input_dim if i == 0 else hidden_dim[i - 1], hidden_dim[i],
+                         kernel_size[i], bias) for i in range(num_layers)])
+
+    def forward(self, input, hidden_state=None):
+        """(t,b,c,h,w) or, with batch_first, (b,t,c,h,w) -> (layer_output of the last layer, [(h, c)] per layer),
+        src/convLSTM.py:102-147."""
+        if not self.batch_first:
+            input = input.permute(1, 0, 2, 3, 4)
+        if hidden_state is None:
+            hidden_state = self.get_init_states(batch_size=input.size(0))
+        layer_output_list, last_state_list = [], []
+        cur = input
+        for layer_idx in range(self.num_layers):
+            h, c = hidden_state[layer_idx]
+            outs = []
+            for t in range(cur.size(1)):
+                h, c = self.cell_list[layer_idx](input=cur[:, t], prev_state=[h, c])
+                outs.append(h)
+            cur = torch.stack(outs, dim=1)
+            layer_output_list.append(cur)
+            last_state_list.append((h, c))
+        layer_output = layer_output_list[-1]
+        if not self.batch_first:
+            layer_output = layer_output.permute(1, 0, 2, 3, 4)
+        return layer_output, last_state_list
+
+    def get_init_states(self, batch_size, cuda=True):
+        return [cell.init_hidden(batch_size, cuda) for cell in self.cell_list]
+
+    @staticmethod
+    def _check_kernel_size_consistency(kernel_size):
+        if not (isinstance(kernel_size, tuple) or
+                (isinstance(kernel_size, list) and all(isinstance(e, tuple) for e in kernel_size))):
+            raise ValueError('`kernel_size` must be tuple or list of tuples')
+
+    @staticmethod
+    def _extend_for_multilayer(param, num_layers):
+        if not isinstance(param, list):
+            param = [param] * num_layers
+        return param
+
+
+class ConvLSTMCellTC(nn.Module):
+    """The wide cell (BASELINE config 4: Cin = Ch = 256 @ 64x64) on tcgen05 tensor cores.
+    Activations are channels-last bf16 ([B,H,W,C]); the cell state stays fp32.  Build it from a
+    (reference or drop-in) ConvLSTMCell with ``from_cell``; weights are repacked once."""
+
+    def __init__(self, input_dim, hidden_dim, weight, bias):
+        super().__init__()
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
+        self.register_buffer('wpack', ops.convlstm_pack_weight(weight.detach().float().contiguous(), input_dim,
+                                                               hidden_dim))
+        self.register_buffer('bias', None if bias is None else bias.detach().float().contiguous())
+
+    @classmethod
+    def from_cell(cls, cell):
+        return cls(cell.input_dim, cell.hidden_dim, cell.conv.weight, cell.conv.bias)
+
+    def forward(self, x_nhwc, prev_state):
+        h, c = prev_state
+        return ops.convlstm_step_tc(x_nhwc, h, c, self.wpack, self.bias, self.input_dim, self.hidden_dim)

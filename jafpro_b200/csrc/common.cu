@@ -1,0 +1,41 @@
+// Error reporting, launch accounting and version for the jafpro_b200 C ABI.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+namespace jaf {
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_status(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return JAF_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return JAF_ERR_CUDA;
+}
+
+int finish_launch(const char* what, int launches) {
+  g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
+  return cuda_status(cudaGetLastError(), what);
+}
+
+}  // namespace jaf
+
+extern "C" {
+
+int jaf_version(void) { return 100; }
+const char* jaf_last_error(void) { return g_err; }
+uint64_t jaf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

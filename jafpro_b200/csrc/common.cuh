@@ -1,0 +1,69 @@
+// Shared host/device helpers for the jafpro_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jafpro_b200.h"
+
+namespace jaf {
+
+// Thread-local error message behind jaf_last_error().
+void set_error(const char* fmt, ...);
+// cudaGetLastError() -> status; bumps the process-wide launch counter by `launches`.
+int finish_launch(const char* what, int launches = 1);
+int cuda_status(cudaError_t e, const char* what);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace jaf
+
+#define JAF_REQUIRE(cond, msg)                                   \
+  do {                                                           \
+    if (!(cond)) {                                               \
+      jaf::set_error("%s: %s (%s)", __func__, msg, #cond);       \
+      return JAF_ERR_INVALID;                                    \
+    }                                                            \
+  } while (0)
+
+#define JAF_CUDA(call)                                           \
+  do {                                                           \
+    int st_ = jaf::cuda_status((call), #call);                   \
+    if (st_ != JAF_OK) return st_;                               \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// Device-side load/store flavours.
+//   ld_stream*: read-once data (flows, logits, masks): bypass L1 so the gather
+//               footprint of the reference images keeps the cache.
+//   st_stream*: write-once outputs: evict-first in L2.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ld_stream_f32x2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_gather_u128(const uint4* p) {
+  // read-only path, L1-allocating: neighbouring output pixels re-use the same taps
+  return __ldg(p);
+}
+__device__ __forceinline__ void st_stream_u128(uint4* p, uint4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream_f32(float* p, float v) { __stcs(p, v); }
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}

@@ -1,0 +1,204 @@
+// jaf_warp_fuse_host: the row-F operation for callers whose tensors live in HOST memory (the
+// reference's per-frame loop hands frames over from DataLoader workers, test/conv_pro_test.py:168-195,
+// and reads every result back, :282-302).  Target frames are streamed through two device-side
+// slots: while slot s computes, slot s^1 uploads the next chunk and downloads the previous
+// result, on three streams tied together with events.  Reference sets addressed through
+// ref_index are uploaded once and stay resident for the whole call.
+//
+// Device staging buffers are cached per process (grow-only) so steady-state calls do no
+// cudaMalloc.  Blocking: returns after the last D2H copy has landed.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return JAF_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return jaf::cuda_status(e, "cudaMalloc(staging)");
+    cap = bytes;
+    return JAF_OK;
+  }
+};
+
+struct Slot {
+  DevBuf grid, logits, vis, fim, mask, fake, conf, rgb, feat, out_rgb, out_feat, warped;
+  cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
+};
+
+struct Pipeline {
+  std::mutex mu;
+  Slot slot[2];
+  DevBuf ref_rgb, ref_feat, ref_index;
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  int device = -1;
+  int init() {
+    int dev = 0;
+    JAF_CUDA(cudaGetDevice(&dev));
+    if (s_in && dev == device) return JAF_OK;
+    JAF_REQUIRE(s_in == nullptr, "jaf_warp_fuse_host was initialised on another device");
+    device = dev;
+    JAF_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    JAF_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    JAF_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (auto& s : slot) {
+      JAF_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+      JAF_CUDA(cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
+      JAF_CUDA(cudaEventCreateWithFlags(&s.downloaded, cudaEventDisableTiming));
+    }
+    return JAF_OK;
+  }
+};
+
+Pipeline g_pipe;
+
+inline size_t esz(int dtype) { return dtype == JAF_DTYPE_BF16 ? 2 : 4; }
+
+#define JAF_TRY(expr)              \
+  do {                             \
+    int st__ = (expr);             \
+    if (st__ != JAF_OK) return st__; \
+  } while (0)
+
+int h2d(DevBuf& d, const void* src, size_t bytes, cudaStream_t st) {
+  JAF_TRY(d.ensure(bytes));
+  JAF_CUDA(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st));
+  return JAF_OK;
+}
+
+}  // namespace
+
+extern "C" int jaf_warp_fuse_host(const JafWarpFuseParams* hp, int frames_per_chunk) {
+  JAF_REQUIRE(hp != nullptr, "null params");
+  JAF_REQUIRE(hp->B >= 0 && hp->K >= 1 && hp->H > 0 && hp->W > 0 && hp->Hs > 0 && hp->Ws > 0, "bad sizes");
+  JAF_REQUIRE(hp->grid != nullptr, "grid is required");
+  const bool want_rgb = hp->rgb && (hp->out_rgb || hp->warped_rgb);
+  const bool want_feat = hp->feat && hp->out_feat && hp->C > 0;
+  JAF_REQUIRE(want_rgb || want_feat, "nothing to do");
+  if (hp->B == 0) return JAF_OK;
+
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  JAF_TRY(g_pipe.init());
+  Pipeline& P = g_pipe;
+
+  const int B = hp->B, K = hp->K;
+  const size_t HW = (size_t)hp->H * hp->W, HWs = (size_t)hp->Hs * hp->Ws;
+  const size_t fe = esz(hp->feat_dtype);
+  const size_t rgb_set = (size_t)K * 3 * HWs * 4;          // one reference set, RGB
+  const size_t feat_set = (size_t)K * hp->C * HWs * fe;    // one reference set, features
+  const size_t per_frame = K * HW * 16 + (want_rgb ? rgb_set : 0) + (want_feat ? feat_set : 0) + HW * 64;
+  int n = frames_per_chunk;
+  if (n <= 0) {
+    const size_t fit = ((size_t)256 << 20) / (per_frame > 0 ? per_frame : 1);  // ~256 MB per slot
+    n = fit < 1 ? 1 : (fit > 64 ? 64 : (int)fit);
+  }
+  if (n > B) n = B;
+
+  // resident reference sets (ref_index given): upload once
+  const float* d_ref_rgb = nullptr;
+  const void* d_ref_feat = nullptr;
+  if (hp->ref_index) {
+    int R = 0;
+    for (int b = 0; b < B; ++b) {
+      JAF_REQUIRE(hp->ref_index[b] >= 0, "negative ref_index");
+      if (hp->ref_index[b] + 1 > R) R = hp->ref_index[b] + 1;
+    }
+    if (want_rgb) {
+      JAF_TRY(h2d(P.ref_rgb, hp->rgb, rgb_set * R, P.s_in));
+      d_ref_rgb = static_cast<const float*>(P.ref_rgb.p);
+    }
+    if (want_feat) {
+      JAF_TRY(h2d(P.ref_feat, hp->feat, feat_set * R, P.s_in));
+      d_ref_feat = P.ref_feat.p;
+    }
+    JAF_TRY(h2d(P.ref_index, hp->ref_index, sizeof(int32_t) * B, P.s_in));
+  }
+
+  const int nchunks = (B + n - 1) / n;
+  for (int ci = 0; ci < nchunks; ++ci) {
+    Slot& S = P.slot[ci & 1];
+    const int b0 = ci * n;
+    const int nb = (b0 + n <= B) ? n : (B - b0);
+    // the slot's previous result must have left before its inputs/outputs are overwritten
+    if (ci >= 2) JAF_CUDA(cudaStreamWaitEvent(P.s_in, S.downloaded, 0));
+    // ---- upload
+    JAF_TRY(h2d(S.grid, hp->grid + (size_t)b0 * K * HW * 2, (size_t)nb * K * HW * 8, P.s_in));
+    if (hp->logits) JAF_TRY(h2d(S.logits, hp->logits + (size_t)b0 * K * HW, (size_t)nb * K * HW * 4, P.s_in));
+    if (hp->vis) JAF_TRY(h2d(S.vis, hp->vis + (size_t)b0 * K * HW, (size_t)nb * K * HW * 4, P.s_in));
+    if (hp->fim) JAF_TRY(h2d(S.fim, hp->fim + (size_t)b0 * HW, (size_t)nb * HW * 4, P.s_in));
+    if (hp->tgt_mask)
+      JAF_TRY(h2d(S.mask, hp->tgt_mask + (size_t)b0 * hp->mask_c * HW, (size_t)nb * hp->mask_c * HW * 4, P.s_in));
+    if (hp->fake && hp->conf) {
+      JAF_TRY(h2d(S.fake, hp->fake + (size_t)b0 * 3 * HW, (size_t)nb * 3 * HW * 4, P.s_in));
+      JAF_TRY(h2d(S.conf, hp->conf + (size_t)b0 * HW, (size_t)nb * HW * 4, P.s_in));
+    }
+    if (!hp->ref_index) {
+      if (want_rgb) JAF_TRY(h2d(S.rgb, hp->rgb + (size_t)b0 * K * 3 * HWs, rgb_set * nb, P.s_in));
+      if (want_feat)
+        JAF_TRY(h2d(S.feat, static_cast<const char*>(hp->feat) + feat_set * b0, feat_set * nb, P.s_in));
+    }
+    JAF_CUDA(cudaEventRecord(S.uploaded, P.s_in));
+    // ---- compute
+    JAF_CUDA(cudaStreamWaitEvent(P.s_k, S.uploaded, 0));
+    JafWarpFuseParams d = *hp;
+    d.B = nb;
+    d.grid = static_cast<const float*>(S.grid.p);
+    d.logits = hp->logits ? static_cast<const float*>(S.logits.p) : nullptr;
+    d.vis = hp->vis ? static_cast<const float*>(S.vis.p) : nullptr;
+    d.fim = hp->fim ? static_cast<const int32_t*>(S.fim.p) : nullptr;
+    d.tgt_mask = hp->tgt_mask ? static_cast<const float*>(S.mask.p) : nullptr;
+    d.fake = (hp->fake && hp->conf) ? static_cast<const float*>(S.fake.p) : nullptr;
+    d.conf = (hp->fake && hp->conf) ? static_cast<const float*>(S.conf.p) : nullptr;
+    if (hp->ref_index) {
+      d.rgb = want_rgb ? d_ref_rgb : nullptr;
+      d.feat = want_feat ? d_ref_feat : nullptr;
+      d.ref_index = static_cast<const int32_t*>(P.ref_index.p) + b0;
+    } else {
+      d.rgb = want_rgb ? static_cast<const float*>(S.rgb.p) : nullptr;
+      d.feat = want_feat ? S.feat.p : nullptr;
+      d.ref_index = nullptr;
+    }
+    d.out_rgb = nullptr;
+    d.out_feat = nullptr;
+    d.warped_rgb = nullptr;
+    if (want_rgb && hp->out_rgb) {
+      JAF_TRY(S.out_rgb.ensure((size_t)nb * 3 * HW * 4));
+      d.out_rgb = static_cast<float*>(S.out_rgb.p);
+    }
+    if (want_rgb && hp->warped_rgb) {
+      JAF_TRY(S.warped.ensure((size_t)nb * K * 3 * HW * 4));
+      d.warped_rgb = static_cast<float*>(S.warped.p);
+    }
+    if (want_feat) {
+      JAF_TRY(S.out_feat.ensure((size_t)nb * hp->C * HW * fe));
+      d.out_feat = S.out_feat.p;
+    }
+    d.stream = P.s_k;
+    JAF_TRY(jaf_warp_fuse(&d));
+    JAF_CUDA(cudaEventRecord(S.computed, P.s_k));
+    // ---- download
+    JAF_CUDA(cudaStreamWaitEvent(P.s_out, S.computed, 0));
+    if (d.out_rgb)
+      JAF_CUDA(cudaMemcpyAsync(hp->out_rgb + (size_t)b0 * 3 * HW, d.out_rgb, (size_t)nb * 3 * HW * 4,
+                               cudaMemcpyDeviceToHost, P.s_out));
+    if (d.warped_rgb)
+      JAF_CUDA(cudaMemcpyAsync(hp->warped_rgb + (size_t)b0 * K * 3 * HW, d.warped_rgb, (size_t)nb * K * 3 * HW * 4,
+                               cudaMemcpyDeviceToHost, P.s_out));
+    if (d.out_feat)
+      JAF_CUDA(cudaMemcpyAsync(static_cast<char*>(hp->out_feat) + (size_t)b0 * hp->C * HW * fe, d.out_feat,
+                               (size_t)nb * hp->C * HW * fe, cudaMemcpyDeviceToHost, P.s_out));
+    JAF_CUDA(cudaEventRecord(S.downloaded, P.s_out));
+  }
+  JAF_CUDA(cudaStreamSynchronize(P.s_out));
+  JAF_CUDA(cudaStreamSynchronize(P.s_k));
+  JAF_CUDA(cudaStreamSynchronize(P.s_in));
+  return JAF_OK;
+}

@@ -1,0 +1,405 @@
+// Face-index / barycentric-weight rasteriser and transfer-flow construction (rows a1-a9).
+//
+// The reference tests every pixel against every face
+// (NR/cuda/rasterize_cuda_kernel.cu:70-169: 65,536 px x 13,776 faces per frame).  SMPL
+// faces project to ~1 px^2, so this file inverts the loop: one thread per FACE walks a
+// conservative pixel bounding box (~10^4 x fewer tests) and resolves visibility with a
+// 64-bit atomicMin on (depth_bits << 32 | face_index), which reproduces the reference's
+// "strict '<' while scanning faces in ascending order" rule (lowest index wins a tie).
+// A second per-pixel pass decodes the winner and writes fim / wim (rows already flipped,
+// NR/rasterize.py:334-338), or composes the transfer flow directly (src/nmr.py:617-659).
+//
+// Bit-exactness: every float operation below is pinned with round-to-nearest intrinsics
+// in the exact order — including the FMA contractions — that nvcc emits for the
+// reference source on sm_100 (read from its SASS; DESIGN.md "Raster arithmetic").
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kBigBox = 64;  // boxes above this many pixels are walked by the whole warp
+
+// ---- a1-a3: src/nmr.py:10-28 (s*(X+t)), :271 (y *= -1), NR/look_at.py:59 (v - eye; the rotation
+// is exactly the identity for SMPLRenderer's eye), NR/vertices_to_faces.py:19-22 (gather).
+__device__ __forceinline__ void project_vertex(const float* __restrict__ p, float s, float tx, float ty,
+                                               float eye_z, float* o) {
+  o[0] = __fmul_rn(s, __fadd_rn(p[0], tx));
+  o[1] = -__fmul_rn(s, __fadd_rn(p[1], ty));
+  o[2] = __fsub_rn(p[2], eye_z);
+}
+
+__device__ __forceinline__ void load_face_projected(const float* __restrict__ cam, const float* __restrict__ verts,
+                                                    const int* __restrict__ fidx, int b, int fn, int V,
+                                                    float eye_z, float* f) {
+  const float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int v = fidx[fn * 3 + k];
+    project_vertex(verts + ((size_t)b * V + v) * 3, s, tx, ty, eye_z, f + 3 * k);
+  }
+}
+
+// ---- rasterize_cuda_kernel.cu:40 / :111
+__device__ __forceinline__ bool face_is_back(const float* f) {
+  return __fmul_rn(__fsub_rn(f[7], f[1]), __fsub_rn(f[3], f[0])) <
+         __fmul_rn(__fsub_rn(f[4], f[1]), __fsub_rn(f[6], f[0]));
+}
+
+// ---- rasterize_cuda_kernel.cu:44-62.  Returns the (pixel-space) denominator; also reports the
+// pixel-space vertex positions for the bounding box.
+__device__ __forceinline__ float face_setup(const float* f, int is, float* inv, float* px, float* py) {
+  const float isf = (float)is;
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    px[n] = __fmul_rn(__fadd_rn(__fmaf_rn(f[3 * n + 0], isf, isf), -1.0f), 0.5f);
+    py[n] = __fmul_rn(__fadd_rn(__fmaf_rn(f[3 * n + 1], isf, isf), -1.0f), 0.5f);
+  }
+  inv[0] = __fsub_rn(py[1], py[2]);
+  inv[1] = __fsub_rn(px[2], px[1]);
+  inv[2] = __fmaf_rn(px[1], py[2], -__fmul_rn(px[2], py[1]));
+  inv[3] = __fsub_rn(py[2], py[0]);
+  inv[4] = __fsub_rn(px[0], px[2]);
+  inv[5] = __fmaf_rn(px[2], py[0], -__fmul_rn(px[0], py[2]));
+  inv[6] = __fsub_rn(py[0], py[1]);
+  inv[7] = __fsub_rn(px[1], px[0]);
+  inv[8] = __fmaf_rn(px[0], py[1], -__fmul_rn(px[1], py[0]));
+  const float den = __fmaf_rn(px[1], inv[3], __fmaf_rn(px[2], inv[6], __fmul_rn(px[0], inv[0])));
+#pragma unroll
+  for (int k = 0; k < 9; ++k) inv[k] = __fdiv_rn(inv[k], den);
+  return den;
+}
+
+// ---- rasterize_cuda_kernel.cu:96-97, :115-137.  true => the face is a z-buffer candidate at (xi, yi).
+__device__ __forceinline__ bool pixel_test(const float* f, const float* inv, int xi, int yi, int is,
+                                           float near_, float far_, float* w, float* zp_out) {
+  const float yp = (float)((2. * yi + 1 - is) / is);
+  const float xp = (float)((2. * xi + 1 - is) / is);
+  if (__fmul_rn(__fsub_rn(yp, f[1]), __fsub_rn(f[3], f[0])) < __fmul_rn(__fsub_rn(xp, f[0]), __fsub_rn(f[4], f[1])))
+    return false;
+  if (__fmul_rn(__fsub_rn(yp, f[4]), __fsub_rn(f[6], f[3])) < __fmul_rn(__fsub_rn(xp, f[3]), __fsub_rn(f[7], f[4])))
+    return false;
+  if (__fmul_rn(__fsub_rn(yp, f[7]), __fsub_rn(f[0], f[6])) < __fmul_rn(__fsub_rn(xp, f[6]), __fsub_rn(f[1], f[7])))
+    return false;
+  const float xif = (float)xi, yif = (float)yi;
+  float w_sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float wk = __fadd_rn(__fmaf_rn(xif, inv[3 * k + 0], __fmul_rn(yif, inv[3 * k + 1])), inv[3 * k + 2]);
+    wk = (float)fmin(fmax((double)wk, 0.), 1.);  // :129, double min/max (NaN -> 0)
+    w[k] = wk;
+    w_sum = __fadd_rn(w_sum, wk);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[k] = __fdiv_rn(w[k], w_sum);
+  const float s = __fadd_rn(__fadd_rn(__fdiv_rn(w[0], f[2]), __fdiv_rn(w[1], f[5])), __fdiv_rn(w[2], f[8]));
+  const float zp = __frcp_rn(s);  // :136 `1. / s`: double reciprocal of a float == correctly rounded fp32
+  *zp_out = zp;
+  // :137 skip if zp <= near || far <= zp; :142 accept only if zp < depth_min (<= far).  NaN fails.
+  return (zp > near_) && (zp < far_);
+}
+
+// Order-preserving float -> uint map so atomicMin on the packed key orders by depth first.
+__device__ __forceinline__ unsigned int float_order_bits(float z) {
+  const unsigned int u = __float_as_uint(z);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct Box {
+  int x_lo, x_hi, y_lo, y_hi;
+};
+
+// Conservative pixel box of a front-facing face.  The reference accepts a pixel when three fp32
+// edge comparisons do not fail, so a pixel can pass while lying marginally outside the exact
+// triangle; the margin grows with the sliver-ness of the face, and degenerate faces (zero or
+// non-finite determinant — where the reference's tests hold on a whole line or everywhere)
+// are tested against the full image exactly like the reference does.
+__device__ __forceinline__ Box face_box(const float* px, const float* py, float den, int is) {
+  Box bx;
+  const float xmin = fminf(px[0], fminf(px[1], px[2])), xmax = fmaxf(px[0], fmaxf(px[1], px[2]));
+  const float ymin = fminf(py[0], fminf(py[1], py[2])), ymax = fmaxf(py[0], fmaxf(py[1], py[2]));
+  const float ex0 = px[1] - px[0], ey0 = py[1] - py[0], ex1 = px[2] - px[1], ey1 = py[2] - py[1];
+  const float ex2 = px[0] - px[2], ey2 = py[0] - py[2];
+  const float l2 = fmaxf(ex0 * ex0 + ey0 * ey0, fmaxf(ex1 * ex1 + ey1 * ey1, ex2 * ex2 + ey2 * ey2));
+  const float aden = fabsf(den);
+  const bool finite = isfinite(xmin) && isfinite(xmax) && isfinite(ymin) && isfinite(ymax) && isfinite(l2);
+  if (!finite || !(aden > 0.0f)) {
+    bx.x_lo = 0; bx.y_lo = 0; bx.x_hi = is - 1; bx.y_hi = is - 1;
+    return bx;
+  }
+  const float sliver = l2 / aden;  // ~2.3 for an equilateral face, large for slivers
+  const float mf = fminf((float)is, 1.0f + floorf(1.6e-5f * (float)is * sliver));
+  const float lim = 2.0f * (float)is + 4.0f;
+  bx.x_lo = max(0, (int)fmaxf(floorf(xmin) - mf, -lim));
+  bx.y_lo = max(0, (int)fmaxf(floorf(ymin) - mf, -lim));
+  bx.x_hi = min(is - 1, (int)fminf(ceilf(xmax) + mf, lim));
+  bx.y_hi = min(is - 1, (int)fminf(ceilf(ymax) + mf, lim));
+  return bx;
+}
+
+__device__ __forceinline__ void zbuf_try(unsigned long long* __restrict__ zb, const float* f, const float* inv,
+                                         int b, int fn, int xi, int yi, int is, float near_, float far_) {
+  float w[3], zp;
+  if (pixel_test(f, inv, xi, yi, is, near_, far_, w, &zp)) {
+    const unsigned long long key = ((unsigned long long)float_order_bits(zp) << 32) | (unsigned int)fn;
+    atomicMin(zb + ((size_t)b * is + yi) * is + xi, key);
+  }
+}
+
+// ---- pass 1: one thread per (batch, face)
+template <bool PROJECT>
+__global__ void __launch_bounds__(256)
+k_raster_scatter(const float* __restrict__ faces_xyz, const float* __restrict__ cam,
+                 const float* __restrict__ verts, const int* __restrict__ fidx, int B, int V, int F, int is,
+                 float eye_z, float near_, float far_, unsigned long long* __restrict__ zbuf,
+                 float* __restrict__ faces_out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  float f[9], inv[9];
+  Box bx = {0, -1, 0, -1};
+  int b = 0, fn = 0;
+  if (i < (long)B * F) {
+    b = (int)(i / F);
+    fn = (int)(i % F);
+    if (PROJECT) {
+      load_face_projected(cam, verts, fidx, b, fn, V, eye_z, f);
+      if (faces_out) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) faces_out[i * 9 + k] = f[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[k] = faces_xyz[i * 9 + k];
+    }
+    if (!face_is_back(f)) {
+      float px[3], py[3];
+      const float den = face_setup(f, is, inv, px, py);
+      bx = face_box(px, py, den, is);
+    }
+  }
+  const int bw = bx.x_hi - bx.x_lo + 1, bh = bx.y_hi - bx.y_lo + 1;
+  const int npx = (bw > 0 && bh > 0) ? bw * bh : 0;
+  const bool big = npx > kBigBox;
+  if (!big) {
+    for (int yi = bx.y_lo; yi <= bx.y_hi; ++yi)
+      for (int xi = bx.x_lo; xi <= bx.x_hi; ++xi) zbuf_try(zbuf, f, inv, b, fn, xi, yi, is, near_, far_);
+  }
+  // faces with large boxes: the whole warp walks each of them in turn
+  unsigned m = __ballot_sync(0xffffffffu, big);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    float ff[9], fi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      ff[k] = __shfl_sync(0xffffffffu, f[k], src);
+      fi[k] = __shfl_sync(0xffffffffu, inv[k], src);
+    }
+    const int sx = __shfl_sync(0xffffffffu, bx.x_lo, src), sy = __shfl_sync(0xffffffffu, bx.y_lo, src);
+    const int sw = __shfl_sync(0xffffffffu, bw, src), sn = __shfl_sync(0xffffffffu, npx, src);
+    const int sb = __shfl_sync(0xffffffffu, b, src), sf = __shfl_sync(0xffffffffu, fn, src);
+    for (int t = (int)lane; t < sn; t += 32)
+      zbuf_try(zbuf, ff, fi, sb, sf, sx + t % sw, sy + t / sw, is, near_, far_);
+  }
+}
+
+// ---- pass 2: one thread per pixel; decode the winner, recompute its weights with the same pinned
+// arithmetic (deterministic => identical bits), write outputs with rows flipped, and/or compose the
+// transfer flow (src/nmr.py:644-653; src/cal_flow.py:30-31 for the source x, -y_raster).
+template <bool PROJECT, bool COMPOSE>
+__global__ void __launch_bounds__(256)
+k_raster_resolve(const unsigned long long* __restrict__ zbuf, const float* __restrict__ faces_xyz,
+                 const float* __restrict__ cam, const float* __restrict__ verts, const int* __restrict__ fidx,
+                 const float* __restrict__ src_cam, const float* __restrict__ src_verts, int B, int V, int F,
+                 int is, float eye_z, float near_, float far_, int flip_rows, int* __restrict__ fim,
+                 float* __restrict__ wim, float* __restrict__ depth, float* __restrict__ T) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * is * is) return;
+  const int b = (int)(i / ((long)is * is));
+  const int pn = (int)(i % ((long)is * is));
+  const int yi = pn / is, xi = pn % is;
+  const int yo = flip_rows ? (is - 1 - yi) : yi;
+  const size_t o = ((size_t)b * is + yo) * is + xi;
+  const unsigned long long key = zbuf[i];
+  int fn = -1;
+  float w[3] = {0.f, 0.f, 0.f};
+  float zp = far_;
+  if (key != kEmptyKey) {
+    fn = (int)(unsigned int)(key & 0xffffffffull);
+    float f[9], inv[9], px[3], py[3];
+    if (PROJECT) {
+      load_face_projected(cam, verts, fidx, b, fn, V, eye_z, f);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[k] = faces_xyz[((size_t)b * F + fn) * 9 + k];
+    }
+    face_setup(f, is, inv, px, py);
+    pixel_test(f, inv, xi, yi, is, near_, far_, w, &zp);
+  }
+  if (fim) fim[o] = fn;
+  if (wim) {
+    wim[o * 3 + 0] = w[0];
+    wim[o * 3 + 1] = w[1];
+    wim[o * 3 + 2] = w[2];
+  }
+  if (depth) depth[o] = zp;
+  if (COMPOSE) {
+    float tx = -2.0f, ty = -2.0f;  // src/nmr.py:627
+    if (fn >= 0) {
+      const float s = src_cam[b * 3 + 0], ctx = src_cam[b * 3 + 1], cty = src_cam[b * 3 + 2];
+      float ax[3], ay[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float* p = src_verts + ((size_t)b * V + fidx[fn * 3 + k]) * 3;
+        ax[k] = __fmul_rn(s, __fadd_rn(p[0], ctx));
+        ay[k] = __fmul_rn(s, __fadd_rn(p[1], cty));  // -(-(s*(Y+ty))): raster flip then cal_flow.py:31
+      }
+      tx = __fadd_rn(__fadd_rn(__fmul_rn(ax[0], w[0]), __fmul_rn(ax[1], w[1])), __fmul_rn(ax[2], w[2]));
+      ty = __fadd_rn(__fadd_rn(__fmul_rn(ay[0], w[0]), __fmul_rn(ay[1], w[1])), __fmul_rn(ay[2], w[2]));
+    }
+    reinterpret_cast<float2*>(T)[o] = make_float2(tx, ty);
+  }
+}
+
+// ---- a1-a3 standalone (when the caller wants the [B,F,3,3] tensor)
+__global__ void __launch_bounds__(256)
+k_project_gather(const float* __restrict__ cam, const float* __restrict__ verts, const int* __restrict__ fidx,
+                 int B, int V, int F, float eye_z, float* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * F) return;
+  float f[9];
+  load_face_projected(cam, verts, fidx, (int)(i / F), (int)(i % F), V, eye_z, f);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[i * 9 + k] = f[k];
+}
+
+// ---- a9 standalone: src/nmr.py:617-659 on explicit fim / wim tensors
+__global__ void __launch_bounds__(256)
+k_flow_compose(const float* __restrict__ src_pts, int stride, int negate_y, const int* __restrict__ fim,
+               const float* __restrict__ wim, int B, int F, long HW, float* __restrict__ T) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * HW) return;
+  const int b = (int)(i / HW);
+  const int fn = ld_stream_s32(fim + i);
+  float tx = -2.0f, ty = -2.0f;
+  if (fn != -1) {
+    const float* p = src_pts + ((size_t)b * F + fn) * 3 * stride;
+    const float w0 = ld_stream_f32(wim + i * 3 + 0), w1 = ld_stream_f32(wim + i * 3 + 1),
+                w2 = ld_stream_f32(wim + i * 3 + 2);
+    float ax0 = p[0], ax1 = p[stride], ax2 = p[2 * stride];
+    float ay0 = p[1], ay1 = p[stride + 1], ay2 = p[2 * stride + 1];
+    if (negate_y) {
+      ay0 = -ay0;
+      ay1 = -ay1;
+      ay2 = -ay2;
+    }
+    tx = __fadd_rn(__fadd_rn(__fmul_rn(ax0, w0), __fmul_rn(ax1, w1)), __fmul_rn(ax2, w2));
+    ty = __fadd_rn(__fadd_rn(__fmul_rn(ay0, w0), __fmul_rn(ay1, w1)), __fmul_rn(ay2, w2));
+  }
+  reinterpret_cast<float2*>(T)[i] = make_float2(tx, ty);
+}
+
+int check_raster_args(int B, int F, int is) {
+  return B >= 0 && F >= 0 && is > 0 && is <= 16384;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jaf_project_gather(const float* cam, const float* verts, const int32_t* faces_idx, int B, int V, int F,
+                       float eye_z, float* faces_xyz, void* stream) {
+  JAF_REQUIRE(cam && verts && faces_idx && faces_xyz, "null pointer");
+  JAF_REQUIRE(B >= 0 && V > 0 && F >= 0, "bad sizes");
+  if ((long)B * F == 0) return JAF_OK;
+  k_project_gather<<<jaf::ceil_div((long)B * F, 256), 256, 0, jaf::as_stream(stream)>>>(cam, verts, faces_idx, B, V,
+                                                                                      F, eye_z, faces_xyz);
+  return jaf::finish_launch("k_project_gather");
+}
+
+size_t jaf_raster_workspace_bytes(int B, int image_size) {
+  if (B <= 0 || image_size <= 0) return 0;
+  return (size_t)B * image_size * image_size * sizeof(unsigned long long);
+}
+
+int jaf_raster_fim_wim(const float* faces_xyz, int B, int F, int image_size, float near_, float far_,
+                       int flip_rows, int32_t* fim, float* wim, float* depth, void* workspace, void* stream) {
+  JAF_REQUIRE(faces_xyz && fim && wim && workspace, "null pointer");
+  JAF_REQUIRE(check_raster_args(B, F, image_size), "bad sizes");
+  if (B == 0) return JAF_OK;
+  cudaStream_t st = jaf::as_stream(stream);
+  auto* zb = static_cast<unsigned long long*>(workspace);
+  const long npix = (long)B * image_size * image_size;
+  JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)npix * 8, st));
+  int launches = 0;
+  if (F > 0) {
+    k_raster_scatter<false><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(
+        faces_xyz, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_, zb, nullptr);
+    ++launches;
+  }
+  k_raster_resolve<false, false><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
+      zb, faces_xyz, nullptr, nullptr, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_, flip_rows,
+      fim, wim, depth, nullptr);
+  return jaf::finish_launch("jaf_raster_fim_wim", launches + 1);
+}
+
+int jaf_render_fim_wim(const float* cam, const float* verts, const int32_t* faces_idx, int B, int V, int F,
+                       int image_size, float eye_z, float near_, float far_, float* faces_xyz, int32_t* fim,
+                       float* wim, void* workspace, void* stream) {
+  JAF_REQUIRE(cam && verts && faces_idx && fim && wim && workspace, "null pointer");
+  JAF_REQUIRE(check_raster_args(B, F, image_size) && V > 0, "bad sizes");
+  if (B == 0) return JAF_OK;
+  cudaStream_t st = jaf::as_stream(stream);
+  auto* zb = static_cast<unsigned long long*>(workspace);
+  const long npix = (long)B * image_size * image_size;
+  JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)npix * 8, st));
+  int launches = 0;
+  if (F > 0) {
+    k_raster_scatter<true><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(
+        nullptr, cam, verts, faces_idx, B, V, F, image_size, eye_z, near_, far_, zb, faces_xyz);
+    ++launches;
+  }
+  k_raster_resolve<true, false><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
+      zb, nullptr, cam, verts, faces_idx, nullptr, nullptr, B, V, F, image_size, eye_z, near_, far_, 1, fim, wim,
+      nullptr, nullptr);
+  return jaf::finish_launch("jaf_render_fim_wim", launches + 1);
+}
+
+int jaf_flow_compose(const float* src_pts, int stride, int negate_y, const int32_t* fim, const float* wim, int B,
+                     int F, int H, int W, float* T, void* stream) {
+  JAF_REQUIRE(src_pts && fim && wim && T, "null pointer");
+  JAF_REQUIRE(stride == 2 || stride == 3, "stride must be 2 or 3");
+  JAF_REQUIRE(B >= 0 && F > 0 && H > 0 && W > 0, "bad sizes");
+  JAF_REQUIRE((reinterpret_cast<uintptr_t>(T) & 7u) == 0, "T must be 8-byte aligned");
+  if (B == 0) return JAF_OK;
+  const long n = (long)B * H * W;
+  k_flow_compose<<<jaf::ceil_div(n, 256), 256, 0, jaf::as_stream(stream)>>>(src_pts, stride, negate_y, fim, wim, B,
+                                                                           F, (long)H * W, T);
+  return jaf::finish_launch("k_flow_compose");
+}
+
+int jaf_cal_flow(const float* src_cam, const float* src_verts, const float* tgt_cam, const float* tgt_verts,
+                 const int32_t* faces_idx, int B, int V, int F, int image_size, float eye_z, float near_,
+                 float far_, float* T, int32_t* fim, float* wim, void* workspace, void* stream) {
+  JAF_REQUIRE(src_cam && src_verts && tgt_cam && tgt_verts && faces_idx && T && workspace, "null pointer");
+  JAF_REQUIRE(check_raster_args(B, F, image_size) && V > 0, "bad sizes");
+  JAF_REQUIRE((reinterpret_cast<uintptr_t>(T) & 7u) == 0, "T must be 8-byte aligned");
+  if (B == 0) return JAF_OK;
+  cudaStream_t st = jaf::as_stream(stream);
+  auto* zb = static_cast<unsigned long long*>(workspace);
+  const long npix = (long)B * image_size * image_size;
+  JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)npix * 8, st));
+  int launches = 0;
+  if (F > 0) {
+    k_raster_scatter<true><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(
+        nullptr, tgt_cam, tgt_verts, faces_idx, B, V, F, image_size, eye_z, near_, far_, zb, nullptr);
+    ++launches;
+  }
+  k_raster_resolve<true, true><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
+      zb, nullptr, tgt_cam, tgt_verts, faces_idx, src_cam, src_verts, B, V, F, image_size, eye_z, near_, far_, 1,
+      fim, wim, nullptr, T);
+  return jaf::finish_launch("jaf_cal_flow", launches + 1);
+}
+
+}  // extern "C"

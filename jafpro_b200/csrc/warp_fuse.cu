@@ -1,0 +1,451 @@
+// Fused bilinear backward warp of K references + visibility / softmax-weighted fusion (row F;
+// rows a10-a12 of SURVEY.md §8a).  See include/jafpro_b200.h for the contract.
+//
+// Two kernels:
+//   k_warp_fuse_nhwc  — the hot kernel.  Features are channels-last bf16, so one bilinear tap of one
+//       reference is C*2 contiguous bytes (128 B = one cache line at C = 64).  A group of LPP = C/8
+//       lanes owns one output pixel; each lane moves 16 bytes (8 channels) per tap with one 128-bit
+//       load, so a warp-wide load instruction fetches whole lines.  Lane k of a group builds
+//       reference k's sample position, bilinear weights and softmax term; the group exchanges them
+//       with warp shuffles and the reduction over K happens in registers.  A CTA sweeps a 8*PPW-pixel
+//       wide strip downwards, so the lower tap row of one step is the upper row of the next and is
+//       served by L1; flows, logits, masks are read once with L1-bypassing loads and outputs are
+//       written once with streaming stores.  RGB (planar f32, the reference layout) rides along on
+//       the first three lanes of each group.
+//   k_warp_fuse_generic — one thread per pixel, any layout / dtype / K <= 16: the reference's NCHW
+//       fp32 call sites (warp_image, crn_model feature warps), per-reference warped outputs, and
+//       every shape the hot kernel does not cover.
+//
+// Arithmetic follows ATen's grid_sampler_2d (bilinear, border): unnormalise, clamp the
+// unnormalised coordinate to [0, size-1], floor, four corner weights, nw/ne/sw/se accumulation
+// (ATen/native/cuda/GridSampler.cuh:14-45 and the kernel body in GridSampler.cu).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxKGeneric = 16;
+
+struct Tap {
+  int off;  // y0 * Ws + x0
+  int dx;   // 0 or 1   (0 when x0 + 1 is outside: that tap has weight exactly 0)
+  int dy;   // 0 or Ws
+  float nw, ne, sw, se;
+};
+
+__device__ __forceinline__ float unnormalize(float c, int size, int align_corners) {
+  if (align_corners) return ((c + 1.f) / 2) * (size - 1);
+  return ((c + 1.f) * size - 1) / 2;
+}
+
+__device__ __forceinline__ Tap make_tap(float gx, float gy, int Ws, int Hs, int align_corners) {
+  float ix = unnormalize(gx, Ws, align_corners);
+  float iy = unnormalize(gy, Hs, align_corners);
+  ix = fminf((float)(Ws - 1), fmaxf(ix, 0.f));  // clip_coordinates (NaN -> 0)
+  iy = fminf((float)(Hs - 1), fmaxf(iy, 0.f));
+  const float fx = floorf(ix), fy = floorf(iy);
+  const float x1 = fx + 1.f, y1 = fy + 1.f;
+  Tap t;
+  const int x0 = (int)fx, y0 = (int)fy;
+  t.off = y0 * Ws + x0;
+  t.dx = (x0 + 1 < Ws) ? 1 : 0;
+  t.dy = (y0 + 1 < Hs) ? Ws : 0;
+  t.nw = (x1 - ix) * (y1 - iy);
+  t.ne = (ix - fx) * (y1 - iy);
+  t.sw = (x1 - ix) * (iy - fy);
+  t.se = (ix - fx) * (iy - fy);
+  return t;
+}
+
+struct WFArgs {
+  int B, K, H, W, Hs, Ws, C, align_corners, mask_c;
+  int rows_per_cta, tiles_x, tiles_y;
+  const float* rgb;
+  const void* feat;
+  const int* ref_index;
+  const float* grid;
+  const float* logits;
+  const float* vis;
+  const int* fim;
+  const float* tgt_mask;
+  const float* fake;
+  const float* conf;
+  float* out_rgb;
+  void* out_feat;
+  float* warped_rgb;
+};
+
+// =====================================================================================
+// Hot kernel: channels-last bf16 features (+ optional planar f32 RGB)
+// =====================================================================================
+template <int LPP, int KT>
+__global__ void __launch_bounds__(256)
+k_warp_fuse_nhwc(const WFArgs a) {
+  static_assert(KT <= LPP, "one lane of the pixel group per reference");
+  constexpr int PPW = 32 / LPP;  // pixels per warp
+  constexpr int TW = 8 * PPW;    // strip width of the CTA (8 warps)
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / LPP;  // pixel group within the warp
+  const int j = lane % LPP;  // lane within the group == reference index it prepares
+  int bid = blockIdx.x;
+  const int tx = bid % a.tiles_x;
+  bid /= a.tiles_x;
+  const int ty = bid % a.tiles_y;
+  const int b = bid / a.tiles_y;
+  const int x = tx * TW + warp * PPW + g;
+  const bool xin = x < a.W;
+  const int y_begin = ty * a.rows_per_cta;
+  const int y_end = min(a.H, y_begin + a.rows_per_cta);
+  const long HW = (long)a.H * a.W;
+  const long HWs = (long)a.Hs * a.Ws;
+  const long r = a.ref_index ? a.ref_index[b] : b;
+  const uint4* __restrict__ feat = reinterpret_cast<const uint4*>(a.feat);
+  const bool has_rgb = a.rgb != nullptr && a.out_rgb != nullptr;
+
+  for (int y = y_begin; y < y_end; ++y) {
+    const long pix = (long)y * a.W + x;
+    // ---- lane j prepares reference j: flow sample, visibility, softmax term
+    float lg = -CUDART_INF_F, v = 0.f;
+    Tap t = {0, 0, 0, 0.f, 0.f, 0.f, 0.f};
+    if (xin && j < KT) {
+      const long bk = ((long)b * KT + j) * HW + pix;
+      lg = a.logits ? ld_stream_f32(a.logits + bk) : 0.f;
+      if (a.vis)
+        v = ld_stream_f32(a.vis + bk);
+      else if (a.fim)
+        v = (ld_stream_s32(a.fim + (long)b * HW + pix) != -1) ? 1.f : 0.f;
+      else
+        v = 1.f;
+      const float2 gxy = ld_stream_f32x2(a.grid + bk * 2);
+      t = make_tap(gxy.x, gxy.y, a.Ws, a.Hs, a.align_corners);
+    }
+    // softmax over the group's K lanes: max by butterfly, sum in reference order k = 0..K-1
+    float m = lg;
+#pragma unroll
+    for (int s = LPP / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
+    const float e = (j < KT) ? expf(lg - m) : 0.f;
+    float ssum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, g * LPP + k);
+    const float aw = (e / ssum) * v;  // alpha_k * vis_k
+    t.nw *= aw;
+    t.ne *= aw;
+    t.sw *= aw;
+    t.se *= aw;
+    const unsigned act = __ballot_sync(FULL, xin && j < KT && aw != 0.f);
+    const int packed = (t.off << 2) | (t.dx) | (t.dy ? 2 : 0);
+
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    float acc_rgb = 0.f;
+
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const int src = g * LPP + k;
+      const int pk = __shfl_sync(FULL, packed, src);
+      const float wnw = __shfl_sync(FULL, t.nw, src), wne = __shfl_sync(FULL, t.ne, src);
+      const float wsw = __shfl_sync(FULL, t.sw, src), wse = __shfl_sync(FULL, t.se, src);
+      if ((act >> src) & 1u) {
+        const int off = pk >> 2;
+        const int dx = pk & 1;
+        const int dy = (pk & 2) ? a.Ws : 0;
+        if (feat) {
+          const uint4* p = feat + (((long)r * KT + k) * HWs + off) * LPP + j;
+          const uint4 q00 = ld_gather_u128(p);
+          const uint4 q01 = ld_gather_u128(p + dx * LPP);
+          const uint4 q10 = ld_gather_u128(p + (long)dy * LPP);
+          const uint4 q11 = ld_gather_u128(p + (long)(dy + dx) * LPP);
+          const uint32_t w00[4] = {q00.x, q00.y, q00.z, q00.w}, w01[4] = {q01.x, q01.y, q01.z, q01.w};
+          const uint32_t w10[4] = {q10.x, q10.y, q10.z, q10.w}, w11[4] = {q11.x, q11.y, q11.z, q11.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[2 * c] = fmaf(bf16_lo(w00[c]), wnw, acc[2 * c]);
+            acc[2 * c + 1] = fmaf(bf16_hi(w00[c]), wnw, acc[2 * c + 1]);
+            acc[2 * c] = fmaf(bf16_lo(w01[c]), wne, acc[2 * c]);
+            acc[2 * c + 1] = fmaf(bf16_hi(w01[c]), wne, acc[2 * c + 1]);
+            acc[2 * c] = fmaf(bf16_lo(w10[c]), wsw, acc[2 * c]);
+            acc[2 * c + 1] = fmaf(bf16_hi(w10[c]), wsw, acc[2 * c + 1]);
+            acc[2 * c] = fmaf(bf16_lo(w11[c]), wse, acc[2 * c]);
+            acc[2 * c + 1] = fmaf(bf16_hi(w11[c]), wse, acc[2 * c + 1]);
+          }
+        }
+        if (has_rgb && j < 3) {
+          const float* p = a.rgb + (((long)r * KT + k) * 3 + j) * HWs + off;
+          float s = __ldg(p) * wnw;
+          s = fmaf(__ldg(p + dx), wne, s);
+          s = fmaf(__ldg(p + dy), wsw, s);
+          s = fmaf(__ldg(p + dy + dx), wse, s);
+          acc_rgb += s;
+        }
+      }
+    }
+
+    if (xin) {
+      const float tm = a.tgt_mask ? ld_stream_f32(a.tgt_mask + ((long)b * a.mask_c) * HW + pix) : 1.f;
+      if (a.out_feat) {
+        if (a.tgt_mask) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] *= tm;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]);
+        o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]);
+        o.w = pack_bf16x2(acc[6], acc[7]);
+        st_stream_u128(reinterpret_cast<uint4*>(a.out_feat) + ((long)b * HW + pix) * LPP + j, o);
+      }
+      if (has_rgb && j < 3) {
+        float o = acc_rgb;
+        if (a.tgt_mask)
+          o *= (a.mask_c == 3) ? ld_stream_f32(a.tgt_mask + ((long)b * 3 + j) * HW + pix) : tm;
+        if (a.fake && a.conf) {
+          const float wc = ld_stream_f32(a.conf + (long)b * HW + pix);
+          const float fk = ld_stream_f32(a.fake + ((long)b * 3 + j) * HW + pix);
+          o = fk * wc + o * (1.0f - wc);  // src/flow_net.py:98
+        }
+        st_stream_f32(a.out_rgb + ((long)b * 3 + j) * HW + pix, o);
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// Generic kernel: one thread per output pixel
+// =====================================================================================
+template <typename T>
+__device__ __forceinline__ float load_as_f32(const T* p);
+template <>
+__device__ __forceinline__ float load_as_f32<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_as_f32<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(__ldg(p));
+}
+template <typename T>
+__device__ __forceinline__ void store_from_f32(T* p, float v);
+template <>
+__device__ __forceinline__ void store_from_f32<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_from_f32<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// IS_RGB: the tensor is a.rgb / a.out_rgb (planar f32, C = 3, per-channel mask, blend, warped output);
+// otherwise a.feat / a.out_feat in layout NHWC ? [.,H,W,C] : [.,C,H,W].
+template <typename T, bool NHWC, bool IS_RGB>
+__global__ void __launch_bounds__(256)
+k_warp_fuse_generic(const WFArgs a) {
+  const long HW = (long)a.H * a.W, HWs = (long)a.Hs * a.Ws;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)a.B * HW) return;
+  const int b = (int)(i / HW);
+  const long pix = i % HW;
+  const long r = a.ref_index ? a.ref_index[b] : b;
+  const int K = a.K;
+  const int C = IS_RGB ? 3 : a.C;
+  const T* __restrict__ src = IS_RGB ? reinterpret_cast<const T*>(a.rgb) : reinterpret_cast<const T*>(a.feat);
+  T* __restrict__ dst = IS_RGB ? reinterpret_cast<T*>(a.out_rgb) : reinterpret_cast<T*>(a.out_feat);
+
+  float aw[kMaxKGeneric];
+  Tap tp[kMaxKGeneric];
+  // softmax (reference order: max, exp, running sum, divide)
+  if (a.logits) {
+    float m = -CUDART_INF_F;
+    for (int k = 0; k < K; ++k) m = fmaxf(m, ld_stream_f32(a.logits + ((long)b * K + k) * HW + pix));
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) {
+      aw[k] = expf(ld_stream_f32(a.logits + ((long)b * K + k) * HW + pix) - m);
+      s += aw[k];
+    }
+    for (int k = 0; k < K; ++k) aw[k] = aw[k] / s;
+  } else {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += 1.0f;
+    for (int k = 0; k < K; ++k) aw[k] = 1.0f / s;
+  }
+  for (int k = 0; k < K; ++k) {
+    float v = 1.f;
+    if (a.vis)
+      v = ld_stream_f32(a.vis + ((long)b * K + k) * HW + pix);
+    else if (a.fim)
+      v = (ld_stream_s32(a.fim + (long)b * HW + pix) != -1) ? 1.f : 0.f;
+    aw[k] *= v;
+    const float2 gxy = ld_stream_f32x2(a.grid + (((long)b * K + k) * HW + pix) * 2);
+    tp[k] = make_tap(gxy.x, gxy.y, a.Ws, a.Hs, a.align_corners);
+  }
+  const float tm1 = a.tgt_mask ? ld_stream_f32(a.tgt_mask + ((long)b * a.mask_c) * HW + pix) : 1.f;
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const Tap& t = tp[k];
+      const bool need = (aw[k] != 0.f) || (IS_RGB && a.warped_rgb);
+      float s = 0.f;
+      if (need) {
+        const T* base = src + ((long)r * K + k) * C * HWs;
+        float v00, v01, v10, v11;
+        if (NHWC) {
+          const T* p = base + (long)t.off * C + c;
+          v00 = load_as_f32(p);
+          v01 = load_as_f32(p + (long)t.dx * C);
+          v10 = load_as_f32(p + (long)t.dy * C);
+          v11 = load_as_f32(p + (long)(t.dy + t.dx) * C);
+        } else {
+          const T* p = base + (long)c * HWs + t.off;
+          v00 = load_as_f32(p);
+          v01 = load_as_f32(p + t.dx);
+          v10 = load_as_f32(p + t.dy);
+          v11 = load_as_f32(p + t.dy + t.dx);
+        }
+        s = fmaf(v00, t.nw, 0.f);
+        s = fmaf(v01, t.ne, s);
+        s = fmaf(v10, t.sw, s);
+        s = fmaf(v11, t.se, s);
+      }
+      if (IS_RGB && a.warped_rgb) a.warped_rgb[(((long)b * K + k) * 3 + c) * HW + pix] = s;
+      acc = fmaf(aw[k], s, acc);
+    }
+    if (a.tgt_mask) {
+      if (IS_RGB && a.mask_c == 3)
+        acc *= ld_stream_f32(a.tgt_mask + ((long)b * 3 + c) * HW + pix);
+      else
+        acc *= tm1;
+    }
+    if (IS_RGB && a.fake && a.conf) {
+      const float wc = ld_stream_f32(a.conf + (long)b * HW + pix);
+      const float fk = ld_stream_f32(a.fake + ((long)b * 3 + c) * HW + pix);
+      acc = fk * wc + acc * (1.0f - wc);
+    }
+    if (dst) {
+      const long o = NHWC ? ((long)b * HW + pix) * C + c : ((long)b * C + c) * HW + pix;
+      store_from_f32(dst + o, acc);
+    }
+  }
+}
+
+template <int LPP>
+bool launch_nhwc_k(const WFArgs& a, int grid, cudaStream_t st) {
+#define JAF_CASE(KV)                                             \
+  case KV:                                                       \
+    if constexpr (KV <= LPP) {                                   \
+      k_warp_fuse_nhwc<LPP, KV><<<grid, 256, 0, st>>>(a);        \
+      return true;                                               \
+    }                                                            \
+    return false;
+  switch (a.K) {
+    JAF_CASE(1)
+    JAF_CASE(2)
+    JAF_CASE(3)
+    JAF_CASE(4)
+    JAF_CASE(5)
+    JAF_CASE(6)
+    JAF_CASE(7)
+    JAF_CASE(8)
+    default:
+      return false;
+  }
+#undef JAF_CASE
+}
+
+// Returns true when the hot kernel was launched.
+bool launch_nhwc(WFArgs a, cudaStream_t st) {
+  const int lpp = a.C / 8;
+  if (a.C % 8 != 0 || !(lpp == 4 || lpp == 8 || lpp == 16 || lpp == 32) || a.K > lpp || a.K > 8) return false;
+  const int ppw = 32 / lpp;
+  const int tw = 8 * ppw;
+  a.tiles_x = (a.W + tw - 1) / tw;
+  a.rows_per_cta = a.H < 32 ? a.H : 32;
+  a.tiles_y = (a.H + a.rows_per_cta - 1) / a.rows_per_cta;
+  const long grid = (long)a.tiles_x * a.tiles_y * a.B;
+  if (grid > 0x7fffffffL) return false;
+  switch (lpp) {
+    case 4: return launch_nhwc_k<4>(a, (int)grid, st);
+    case 8: return launch_nhwc_k<8>(a, (int)grid, st);
+    case 16: return launch_nhwc_k<16>(a, (int)grid, st);
+    case 32: return launch_nhwc_k<32>(a, (int)grid, st);
+  }
+  return false;
+}
+
+}  // namespace
+
+extern "C" int jaf_warp_fuse(const JafWarpFuseParams* p) {
+  JAF_REQUIRE(p != nullptr, "null params");
+  JAF_REQUIRE(p->B >= 0 && p->K >= 1 && p->H > 0 && p->W > 0 && p->Hs > 0 && p->Ws > 0, "bad sizes");
+  JAF_REQUIRE(p->grid != nullptr, "grid is required");
+  JAF_REQUIRE((long)p->Hs * p->Ws < (1L << 29), "reference image too large");
+  JAF_REQUIRE((reinterpret_cast<uintptr_t>(p->grid) & 7u) == 0, "grid must be 8-byte aligned");
+  const bool want_rgb = p->rgb && (p->out_rgb || p->warped_rgb);
+  const bool want_feat = p->feat && p->out_feat && p->C > 0;
+  JAF_REQUIRE(want_rgb || want_feat, "nothing to do: need rgb+out_rgb and/or feat+out_feat");
+  JAF_REQUIRE(!p->tgt_mask || p->mask_c == 1 || p->mask_c == 3, "mask_c must be 1 or 3");
+  JAF_REQUIRE(p->feat_layout == JAF_LAYOUT_PLANAR || p->feat_layout == JAF_LAYOUT_NHWC, "bad feat_layout");
+  JAF_REQUIRE(p->feat_dtype == JAF_DTYPE_F32 || p->feat_dtype == JAF_DTYPE_BF16, "bad feat_dtype");
+  if (p->B == 0) return JAF_OK;
+  cudaStream_t st = jaf::as_stream(p->stream);
+
+  WFArgs a;
+  a.B = p->B; a.K = p->K; a.H = p->H; a.W = p->W; a.Hs = p->Hs; a.Ws = p->Ws; a.C = p->C;
+  a.align_corners = p->align_corners; a.mask_c = p->tgt_mask ? p->mask_c : 1;
+  a.rows_per_cta = 0; a.tiles_x = 0; a.tiles_y = 0;
+  a.rgb = p->rgb; a.feat = p->feat; a.ref_index = p->ref_index; a.grid = p->grid; a.logits = p->logits;
+  a.vis = p->vis; a.fim = p->fim; a.tgt_mask = p->tgt_mask; a.fake = p->fake; a.conf = p->conf;
+  a.out_rgb = p->out_rgb; a.out_feat = p->out_feat; a.warped_rgb = p->warped_rgb;
+
+  int launches = 0;
+  bool rgb_done = !want_rgb, feat_done = !want_feat;
+  // hot path: channels-last bf16 features, 16-byte aligned, RGB fused in unless per-reference
+  // warps are requested
+  if (want_feat && p->feat_layout == JAF_LAYOUT_NHWC && p->feat_dtype == JAF_DTYPE_BF16 &&
+      (reinterpret_cast<uintptr_t>(p->feat) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p->out_feat) & 15u) == 0) {
+    WFArgs h = a;
+    const bool fuse_rgb = want_rgb && !p->warped_rgb && p->out_rgb;
+    if (!fuse_rgb) {
+      h.rgb = nullptr;
+      h.out_rgb = nullptr;
+    }
+    h.warped_rgb = nullptr;
+    if (launch_nhwc(h, st)) {
+      ++launches;
+      feat_done = true;
+      if (fuse_rgb) rgb_done = true;
+    }
+  }
+  const long npix = (long)p->B * p->H * p->W;
+  const int grid = jaf::ceil_div(npix, 256);
+  if (!rgb_done || !feat_done) JAF_REQUIRE(p->K <= kMaxKGeneric, "K > 16 is not supported by the generic kernel");
+  if (!rgb_done) {
+    k_warp_fuse_generic<float, false, true><<<grid, 256, 0, st>>>(a);
+    ++launches;
+  }
+  if (!feat_done) {
+    WFArgs f = a;
+    f.warped_rgb = nullptr;
+    const bool nhwc = p->feat_layout == JAF_LAYOUT_NHWC;
+    if (p->feat_dtype == JAF_DTYPE_F32) {
+      if (nhwc) k_warp_fuse_generic<float, true, false><<<grid, 256, 0, st>>>(f);
+      else      k_warp_fuse_generic<float, false, false><<<grid, 256, 0, st>>>(f);
+    } else {
+      if (nhwc) k_warp_fuse_generic<__nv_bfloat16, true, false><<<grid, 256, 0, st>>>(f);
+      else      k_warp_fuse_generic<__nv_bfloat16, false, false><<<grid, 256, 0, st>>>(f);
+    }
+    ++launches;
+  }
+  return jaf::finish_launch("jaf_warp_fuse", launches);
+}
+
+extern "C" int jaf_warp_image(const float* src, const float* grid, int N, int C, int Hs, int Ws, int H, int W,
+                              int align_corners, float* out, void* stream) {
+  JAF_REQUIRE(src && grid && out, "null pointer");
+  JafWarpFuseParams p = {};
+  p.B = N; p.K = 1; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws; p.C = C;
+  p.align_corners = align_corners;
+  p.feat_layout = JAF_LAYOUT_PLANAR;
+  p.feat_dtype = JAF_DTYPE_F32;
+  p.feat = src;
+  p.grid = grid;
+  p.out_feat = out;
+  p.stream = stream;
+  return jaf_warp_fuse(&p);
+}

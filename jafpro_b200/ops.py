@@ -1,0 +1,369 @@
+"""Tensor-level wrappers over the C ABI: same tensor signatures as the reference call
+sites, CUDA tensors in, CUDA tensors out, launched on torch's current stream.
+
+Error behaviour follows the reference extension (NR/cuda/rasterize_cuda.cpp:66-68,84-89):
+a CPU or non-contiguous tensor raises ``RuntimeError``.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+# float32 value of the look_at eye used by SMPLRenderer (src/nmr.py:177)
+EYE_Z = float(torch.tensor(-(1.0 / math.tan(math.radians(30.0)) + 1.0), dtype=torch.float32))
+DEFAULT_NEAR, DEFAULT_FAR = 0.1, 100.0  # NR/rasterize.py:10-11 (what src/nmr.py:277 ends up using)
+
+_workspaces: dict = {}
+
+
+def _check(t, name, dtype=None):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(dev, nbytes):
+    """Grow-only scratch per device (z-buffer keys).  Stream-ordered use only."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        _workspaces[key] = buf
+    return buf
+
+
+# ----------------------------------------------------------------------------- a1-a3
+def project_gather(cam, vertices, faces_idx, eye_z: float = EYE_Z):
+    """proj_func + y flip + look_at + vertices_to_faces (src/nmr.py:266-276) -> [B,F,3,3]."""
+    cam, vertices = _check(cam, "cam", torch.float32), _check(vertices, "vertices", torch.float32)
+    faces_idx = _check(faces_idx, "faces", torch.int32)
+    B, V, _ = vertices.shape
+    F = faces_idx.shape[-2]
+    out = torch.empty((B, F, 3, 3), dtype=torch.float32, device=vertices.device)
+    with torch.cuda.device(vertices.device):
+        _lib.check(_lib.lib().jaf_project_gather(_ptr(cam), _ptr(vertices), _ptr(faces_idx), B, V, F, eye_z,
+                                                 _ptr(out), _stream()), "project_gather")
+    return out
+
+
+# ----------------------------------------------------------------------------- a4-a6
+def raster_fim_wim(faces, image_size: int, near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR,
+                   flip_rows: bool = True, return_depth: bool = False):
+    """nr.rasterize_face_index_map_and_weight_map (NR/rasterize.py:543-571), anti_aliasing=False."""
+    faces = _check(faces, "faces", torch.float32)
+    if faces.dim() != 4 or faces.shape[2:] != (3, 3):
+        raise RuntimeError("faces must be [batch, num_faces, 3, 3]")
+    B, F = faces.shape[:2]
+    dev = faces.device
+    fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=dev)
+    wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((B, image_size, image_size), dtype=torch.float32, device=dev) if return_depth else None
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, image_size))
+        _lib.check(_lib.lib().jaf_raster_fim_wim(_ptr(faces), B, F, image_size, near, far, int(flip_rows), _ptr(fim),
+                                                 _ptr(wim), _ptr(depth), _ptr(ws), _stream()), "raster_fim_wim")
+    return (fim, wim, depth) if return_depth else (fim, wim)
+
+
+# ----------------------------------------------------------------------------- a7
+def render_fim_wim(cam, vertices, faces_idx, image_size: int, eye_z: float = EYE_Z, near: float = DEFAULT_NEAR,
+                   far: float = DEFAULT_FAR, return_faces: bool = True):
+    """SMPLRenderer.render_fim_wim (src/nmr.py:263-278) in one call -> (faces|None, fim, wim)."""
+    cam, vertices = _check(cam, "cam", torch.float32), _check(vertices, "vertices", torch.float32)
+    faces_idx = _check(faces_idx, "faces", torch.int32)
+    B, V, _ = vertices.shape
+    F = faces_idx.shape[-2]
+    dev = vertices.device
+    faces = torch.empty((B, F, 3, 3), dtype=torch.float32, device=dev) if return_faces else None
+    fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=dev)
+    wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, image_size))
+        _lib.check(_lib.lib().jaf_render_fim_wim(_ptr(cam), _ptr(vertices), _ptr(faces_idx), B, V, F, image_size,
+                                                 eye_z, near, far, _ptr(faces), _ptr(fim), _ptr(wim), _ptr(ws),
+                                                 _stream()), "render_fim_wim")
+    return faces, fim, wim
+
+
+# ----------------------------------------------------------------------------- a9
+def flow_compose(src_f2pts, dst_fims, dst_wims, negate_y: bool = False):
+    """SMPLRenderer.cal_bc_transform (src/nmr.py:617-659).  src_f2pts [B,F,3,2] (or [B,F,3,3])."""
+    src = _check(src_f2pts, "src_f2pts", torch.float32)
+    fim, wim = _check(dst_fims, "dst_fims", torch.int32), _check(dst_wims, "dst_wims", torch.float32)
+    B, F = src.shape[:2]
+    H, W = fim.shape[1:]
+    T = torch.empty((B, H, W, 2), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().jaf_flow_compose(_ptr(src), src.shape[3], int(negate_y), _ptr(fim), _ptr(wim), B, F, H,
+                                               W, _ptr(T), _stream()), "flow_compose")
+    return T
+
+
+# ----------------------------------------------------------------------------- a8
+def cal_flow(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx, image_size: int, eye_z: float = EYE_Z,
+             near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR, return_maps: bool = False):
+    """float_estimate.cal_flow (src/cal_flow.py:28-35) fused -> T [B,S,S,2] (and fim, wim)."""
+    sc, sv = _check(src_cam, "src_cam", torch.float32), _check(src_vertices, "src_vertices", torch.float32)
+    tc, tv = _check(tgt_cam, "tgt_cam", torch.float32), _check(tgt_vertices, "tgt_vertices", torch.float32)
+    faces_idx = _check(faces_idx, "faces", torch.int32)
+    B, V, _ = tv.shape
+    F = faces_idx.shape[-2]
+    dev = tv.device
+    T = torch.empty((B, image_size, image_size, 2), dtype=torch.float32, device=dev)
+    fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=dev) if return_maps else None
+    wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev) if return_maps else None
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, image_size))
+        _lib.check(_lib.lib().jaf_cal_flow(_ptr(sc), _ptr(sv), _ptr(tc), _ptr(tv), _ptr(faces_idx), B, V, F,
+                                           image_size, eye_z, near, far, _ptr(T), _ptr(fim), _ptr(wim), _ptr(ws),
+                                           _stream()), "cal_flow")
+    return (T, fim, wim) if return_maps else T
+
+
+# ----------------------------------------------------------------------------- row F
+def _feat_layout(feat):
+    """-> (layout, dtype code, C, Hs, Ws, dense tensor).  Accepts [R,K,C,H,W] contiguous (planar) or the
+    same logical shape with channels-last strides (dense [R,K,H,W,C] memory)."""
+    if feat.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("features must be float32 or bfloat16")
+    if not feat.is_cuda:
+        raise RuntimeError("feat must be a CUDA tensor")
+    dt = 0 if feat.dtype == torch.float32 else 1
+    if feat.dim() != 5:
+        raise RuntimeError("feat must be [R, K, C, H, W]")
+    R, K, Cc, H, W = feat.shape
+    if feat.is_contiguous():
+        return 0, dt, Cc, H, W
+    if feat.permute(0, 1, 3, 4, 2).is_contiguous():
+        return 1, dt, Cc, H, W
+    raise RuntimeError("feat must be contiguous [R,K,C,H,W] or channels-last (dense [R,K,H,W,C])")
+
+
+def warp_fuse(grid, rgb=None, feat=None, *, logits=None, vis=None, fim=None, tgt_mask=None, fake=None, conf=None,
+              ref_index=None, align_corners: bool = False, return_warped: bool = False):
+    """Fused K-reference warp + fusion (include/jafpro_b200.h).
+
+    grid [B,K,H,W,2] f32; rgb [R,K,3,Hs,Ws] f32; feat [R,K,C,Hs,Ws] f32/bf16 (contiguous, or with
+    channels-last strides — the fast path); logits/vis [B,K,H,W]; fim [B,H,W] int32;
+    tgt_mask [B,1|3,H,W]; fake [B,3,H,W]; conf [B,1,H,W]; ref_index [B] int32.
+    Returns (out_rgb|None, out_feat|None[, warped_rgb]).  out_feat has feat's dtype and memory format."""
+    grid = _check(grid, "grid", torch.float32)
+    if grid.dim() != 5 or grid.shape[-1] != 2:
+        raise RuntimeError("grid must be [B, K, H, W, 2]")
+    B, K, H, W, _ = grid.shape
+    dev = grid.device
+    q = _lib.WarpFuseParams()
+    q.B, q.K, q.H, q.W = B, K, H, W
+    q.align_corners = int(bool(align_corners))
+    q.grid = grid.data_ptr()
+    out_rgb = out_feat = warped = None
+    Hs = Ws = None
+    if rgb is not None:
+        rgb = _check(rgb, "rgb", torch.float32)
+        if rgb.dim() != 5 or rgb.shape[1] != K or rgb.shape[2] != 3:
+            raise RuntimeError("rgb must be [R, K, 3, Hs, Ws]")
+        Hs, Ws = rgb.shape[-2:]
+        out_rgb = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        q.rgb, q.out_rgb = rgb.data_ptr(), out_rgb.data_ptr()
+        if return_warped:
+            warped = torch.empty((B, K, 3, H, W), dtype=torch.float32, device=dev)
+            q.warped_rgb = warped.data_ptr()
+    if feat is not None:
+        layout, dt, Cc, fh, fw = _feat_layout(feat)
+        if feat.shape[1] != K:
+            raise RuntimeError("feat must be [R, K, C, Hs, Ws]")
+        if Hs is not None and (fh, fw) != (Hs, Ws):
+            raise RuntimeError("rgb and feat must share the reference size")
+        Hs, Ws = fh, fw
+        if layout == 1:
+            out_feat = torch.empty((B, H, W, Cc), dtype=feat.dtype, device=dev).permute(0, 3, 1, 2)
+        else:
+            out_feat = torch.empty((B, Cc, H, W), dtype=feat.dtype, device=dev)
+        q.C, q.feat_layout, q.feat_dtype = Cc, layout, dt
+        q.feat, q.out_feat = feat.data_ptr(), out_feat.data_ptr()
+    if Hs is None:
+        raise RuntimeError("warp_fuse needs rgb and/or feat")
+    q.Hs, q.Ws = Hs, Ws
+    keep = []
+    for name, t, dtype, shape in (("logits", logits, torch.float32, (B, K, H, W)),
+                                  ("vis", vis, torch.float32, (B, K, H, W)),
+                                  ("fim", fim, torch.int32, (B, H, W)),
+                                  ("fake", fake, torch.float32, (B, 3, H, W)),
+                                  ("conf", conf, torch.float32, (B, 1, H, W)),
+                                  ("ref_index", ref_index, torch.int32, (B,))):
+        if t is not None:
+            t = _check(t, name, dtype)
+            if tuple(t.shape) != shape:
+                raise RuntimeError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+            setattr(q, name, t.data_ptr())
+            keep.append(t)
+    if tgt_mask is not None:
+        tgt_mask = _check(tgt_mask, "tgt_mask", torch.float32)
+        if tgt_mask.dim() != 4 or tgt_mask.shape[0] != B or tgt_mask.shape[1] not in (1, 3) or \
+                tuple(tgt_mask.shape[2:]) != (H, W):
+            raise RuntimeError("tgt_mask must be [B, 1 or 3, H, W]")
+        q.tgt_mask, q.mask_c = tgt_mask.data_ptr(), tgt_mask.shape[1]
+    if ref_index is None:
+        for t in (rgb, feat):
+            if t is not None and t.shape[0] != B:
+                raise RuntimeError("without ref_index the reference tensors need one set per target frame")
+    with torch.cuda.device(dev):
+        q.stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().jaf_warp_fuse(C.byref(q)), "warp_fuse")
+    if return_warped:
+        return out_rgb, out_feat, warped
+    return out_rgb, out_feat
+
+
+def warp_fuse_host(grid, rgb=None, feat=None, *, feat_channels_last: bool = False, logits=None, vis=None, fim=None,
+                   tgt_mask=None, ref_index=None, align_corners: bool = False, frames_per_chunk: int = 0,
+                   out_rgb=None, out_feat=None):
+    """``jaf_warp_fuse_host``: every tensor lives in HOST memory (pin it for full PCIe speed); the
+    library pipelines H2D, the kernel and D2H itself.  feat is [R,K,C,Hs,Ws], or dense
+    [R,K,Hs,Ws,C] when feat_channels_last.  Returns (out_rgb, out_feat) host tensors."""
+    if grid.is_cuda:
+        raise RuntimeError("warp_fuse_host takes host tensors")
+    B, K, H, W, _ = grid.shape
+    q = _lib.WarpFuseParams()
+    q.B, q.K, q.H, q.W = B, K, H, W
+    q.align_corners = int(bool(align_corners))
+    q.grid = grid.data_ptr()
+    if rgb is not None:
+        q.Hs, q.Ws = rgb.shape[-2:]
+        if out_rgb is None:
+            out_rgb = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+        q.rgb, q.out_rgb = rgb.data_ptr(), out_rgb.data_ptr()
+    if feat is not None:
+        if feat_channels_last:
+            q.Hs, q.Ws, q.C = feat.shape[-3:]
+            shape = (B, H, W, q.C)
+        else:
+            q.C, q.Hs, q.Ws = feat.shape[-3:]
+            shape = (B, q.C, H, W)
+        q.feat_layout = int(feat_channels_last)
+        q.feat_dtype = 0 if feat.dtype == torch.float32 else 1
+        if out_feat is None:
+            out_feat = torch.empty(shape, dtype=feat.dtype).pin_memory()
+        q.feat, q.out_feat = feat.data_ptr(), out_feat.data_ptr()
+    for name, t in (("logits", logits), ("vis", vis), ("fim", fim), ("ref_index", ref_index)):
+        if t is not None:
+            if t.is_cuda or not t.is_contiguous():
+                raise RuntimeError(f"{name} must be a contiguous host tensor")
+            setattr(q, name, t.data_ptr())
+    if tgt_mask is not None:
+        q.tgt_mask, q.mask_c = tgt_mask.data_ptr(), tgt_mask.shape[1]
+    _lib.check(_lib.lib().jaf_warp_fuse_host(C.byref(q), int(frames_per_chunk)), "warp_fuse_host")
+    return out_rgb, out_feat
+
+
+# ----------------------------------------------------------------------------- a10
+def grid_sample_border(src, grid, align_corners: bool = False):
+    """F.grid_sample(src, grid, mode='bilinear', padding_mode='border') — float_estimate.warp_image
+    (src/cal_flow.py:37-39) and the feature warps of src/crn_model.py:463-566."""
+    src, grid = _check(src, "src"), _check(grid, "grid", torch.float32)
+    if src.dim() != 4 or grid.dim() != 4 or grid.shape[0] != src.shape[0] or grid.shape[-1] != 2:
+        raise RuntimeError("expected src [N,C,H,W] and grid [N,Ho,Wo,2]")
+    if src.dtype == torch.float32:
+        N, Cc, Hs, Ws = src.shape
+        H, W = grid.shape[1:3]
+        out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=src.device)
+        with torch.cuda.device(src.device):
+            _lib.check(_lib.lib().jaf_warp_image(_ptr(src), _ptr(grid), N, Cc, Hs, Ws, H, W, int(bool(align_corners)),
+                                                 _ptr(out), _stream()), "warp_image")
+        return out
+    _, out = warp_fuse(grid[:, None], feat=src[:, None], align_corners=align_corners)
+    return out
+
+
+# ----------------------------------------------------------------------------- a11
+def mask_blend(tsf_image, tgt_smpl_mask=None, fake_tgt=None, weight=None):
+    """Propagation3DFlowNet.forward lines 91 / 98 (src/flow_net.py).  Returns (masked, pred|None)."""
+    tsf = _check(tsf_image, "tsf_image", torch.float32)
+    mask = _check(tgt_smpl_mask, "tgt_smpl_mask", torch.float32)
+    fake, w = _check(fake_tgt, "fake_tgt", torch.float32), _check(weight, "weight", torch.float32)
+    B, Cc, H, W = tsf.shape
+    masked = torch.empty_like(tsf)
+    pred = torch.empty_like(tsf) if w is not None else None
+    mc = 1 if mask is None else mask.shape[1]
+    with torch.cuda.device(tsf.device):
+        _lib.check(_lib.lib().jaf_mask_blend(_ptr(fake), _ptr(tsf), _ptr(mask), mc, _ptr(w), B, Cc, H, W,
+                                             _ptr(masked), _ptr(pred), _stream()), "mask_blend")
+    return masked, pred
+
+
+# ----------------------------------------------------------------------------- a12
+def softmax_fuse(feat_cat, logits):
+    """K-reduction of Downsampler_mask.forward (src/networks.py:1264-1286).
+    feat_cat [B,K*C,H,W] f32, logits [B,K,H,W] (pre-softmax) -> [B,C,H,W]."""
+    feat, logits = _check(feat_cat, "feat_cat", torch.float32), _check(logits, "logits", torch.float32)
+    B, KC, H, W = feat.shape
+    K = logits.shape[1]
+    if KC % K != 0:
+        raise RuntimeError("feat_cat channels must be K*C")
+    out = torch.empty((B, KC // K, H, W), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.check(_lib.lib().jaf_softmax_fuse(_ptr(feat), _ptr(logits), B, K, KC // K, H, W, _ptr(out), _stream()),
+                   "softmax_fuse")
+    return out
+
+
+# ----------------------------------------------------------------------------- a13
+def convlstm_step(x, h, c, weight, bias=None):
+    """ConvLSTMCell.forward (src/convLSTM.py:41-56), fp32 NCHW -> (h_next, c_next)."""
+    x, h, c = _check(x, "input", torch.float32), _check(h, "h", torch.float32), _check(c, "c", torch.float32)
+    weight, bias = _check(weight, "weight", torch.float32), _check(bias, "bias", torch.float32)
+    B, Cin, H, W = x.shape
+    Ch = h.shape[1]
+    if weight.shape[0] != 4 * Ch or weight.shape[1] != Cin + Ch:
+        raise RuntimeError("weight must be [4*Ch, Cin+Ch, kh, kw]")
+    kh, kw = weight.shape[2:]
+    h2, c2 = torch.empty_like(h), torch.empty_like(c)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().jaf_convlstm_step_f32(_ptr(x), _ptr(h), _ptr(c), _ptr(weight), _ptr(bias), B, Cin, Ch,
+                                                    H, W, kh, kw, _ptr(h2), _ptr(c2), _stream()), "convlstm_step")
+    return h2, c2
+
+
+def convlstm_pack_weight(weight, Cin: int, Ch: int):
+    """Repack a [4Ch, Cin+Ch, 3, 3] f32 weight for the tensor-core cell (done once per model)."""
+    weight = _check(weight, "weight", torch.float32)
+    if tuple(weight.shape) != (4 * Ch, Cin + Ch, 3, 3):
+        raise RuntimeError("weight must be [4*Ch, Cin+Ch, 3, 3]")
+    n = _lib.lib().jaf_convlstm_wpack_bytes(Cin, Ch)
+    wpack = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.lib().jaf_convlstm_pack_weight(_ptr(weight), Cin, Ch, _ptr(wpack), _stream()), "pack_weight")
+    return wpack
+
+
+def convlstm_step_tc(x, h, c, wpack, bias, Cin: int, Ch: int):
+    """Tensor-core ConvLSTM step (tcgen05): x [B,H,W,Cin] bf16, h [B,H,W,Ch] bf16, c [B,H,W,Ch] f32
+    (all channels-last dense) -> (h_next bf16, c_next f32)."""
+    x, h = _check(x, "x", torch.bfloat16), _check(h, "h", torch.bfloat16)
+    c, bias = _check(c, "c", torch.float32), _check(bias, "bias", torch.float32)
+    B, H, W, _ = x.shape
+    h2, c2 = torch.empty_like(h), torch.empty_like(c)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().jaf_convlstm_step_tc(_ptr(x), _ptr(h), _ptr(c), _ptr(wpack), _ptr(bias), B, Cin, Ch, H,
+                                                   W, _ptr(h2), _ptr(c2), _stream()), "convlstm_step_tc")
+    return h2, c2

@@ -1,0 +1,468 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): every call goes through the C ABI
+(jafpro_b200 -> libjafpro_b200.so) and is compared with the CPU oracle on the same seeded inputs,
+with the committed golden fixtures, with the reference's own CUDA rasteriser (oracle/_ref, built
+from the unmodified reference source), and — for the third-party grid_sample arithmetic — with the
+installed torch.
+
+Bars: bit-exact for face-index maps, barycentric weights, flows and every fp32 gather that has no
+transcendental in it; <= 1e-4 max-abs (stated per test, usually far tighter) where expf or a
+different-but-equivalent summation order is involved; <= 1 bf16 ulp for bf16 feature outputs.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from jafpro_b200 import _lib, ops, synth
+from jafpro_b200.nmr import SMPLRenderer, load_smpl_template
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def _bits(t):
+    return t.detach().cpu().contiguous().view(torch.int32).numpy()
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _bf16_bits(t):
+    return t.detach().cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+
+
+def test_native_library_is_loaded_and_counts_launches():
+    assert torch.cuda.is_available()
+    n0 = _lib.launch_count()
+    ops.grid_sample_border(torch.zeros(1, 1, 4, 4, device=DEV), torch.zeros(1, 4, 4, 2, device=DEV))
+    assert _lib.launch_count() == n0 + 1
+    maps = open("/proc/self/maps").read()
+    assert "libjafpro_b200.so" in maps
+
+
+# ------------------------------------------------------------------ rasteriser (a4-a6)
+def test_teapot_golden_silhouette(golden_dir):
+    d = _load(golden_dir, "teapot_faces.npz")
+    shape = tuple(d["shape"])
+    ref = np.unpackbits(d["silhouette_bits"])[: shape[0] * shape[1]].reshape(shape).astype(bool)
+    faces = _cu(d["faces"][None])
+    fim, wim, depth = ops.raster_fim_wim(faces, 256, return_depth=True)
+    assert np.array_equal(_np(fim[0]) != -1, ref)
+    # NR tests/utils.py:11-27: the sample sits at index 2 of a batch of all-zero meshes
+    batch = torch.zeros((4,) + tuple(faces.shape[1:]), device=DEV)
+    batch[2] = faces[0]
+    fim4, wim4 = ops.raster_fim_wim(batch, 256)
+    assert np.array_equal(_np(fim4[2]) != -1, ref)
+    for i in (0, 1, 3):
+        assert int((fim4[i] != -1).sum()) == 0 and float(wim4[i].abs().max()) == 0.0
+    # against the oracle: every value bit for bit (medium / large faces, warp-cooperative path)
+    ofim, owim, odepth = oracle.raster_fim_wim(d["faces"][None], 256, return_depth=True)
+    assert np.array_equal(_np(fim), ofim)
+    assert np.array_equal(_bits(wim), owim.view(np.int32))
+    assert np.array_equal(_bits(depth), odepth.view(np.int32))
+
+
+def test_raster_matches_reference_cuda_kernels_bit_exact():
+    """fim / wim / depth against the reference's own kernels (rasterize_cuda_kernel.cu:24-169) compiled
+    unmodified for sm_100a — the parity gate of the north star (face-index maps bit-exact)."""
+    try:
+        ref = oracle.RefRaster()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libjaf_ref_raster.so not built (needs /root/reference at build time)")
+    rend = SMPLRenderer(image_size=256).to(DEV)
+    cam, verts = synth.smpl_poses(4, seed=11, device=DEV)
+    faces, fim, wim = rend.render_fim_wim(cam, verts)
+    rfim, rwim, rdepth = ref(faces, 256)
+    assert 0.05 < float((rfim != -1).float().mean()) < 0.3
+    assert torch.equal(fim, rfim)
+    assert np.array_equal(_bits(wim), _bits(rwim))
+    _, _, depth = ops.raster_fim_wim(faces, 256, return_depth=True)
+    assert np.array_equal(_bits(depth), _bits(rdepth))
+    # other sizes and a random triangle soup with big, overlapping, partly off-screen faces
+    g = torch.Generator().manual_seed(5)
+    soup = (torch.rand((2, 300, 3, 3), generator=g) * 2.6 - 1.3)
+    soup[..., 2] = torch.rand((2, 300, 3), generator=g) * 3 + 0.5
+    soup = soup.to(DEV)
+    for size in (64, 200, 512):
+        a = ops.raster_fim_wim(soup, size, return_depth=True)
+        b = ref(soup, size)
+        assert torch.equal(a[0], b[0]), size
+        assert np.array_equal(_bits(a[1]), _bits(b[1])), size
+        assert np.array_equal(_bits(a[2]), _bits(b[2])), size
+    # SMPL mesh at 512 (BASELINE config 5)
+    f512 = ops.raster_fim_wim(faces[:2].contiguous(), 512)
+    r512 = ref(faces[:2].contiguous(), 512)
+    assert torch.equal(f512[0], r512[0]) and np.array_equal(_bits(f512[1]), _bits(r512[1]))
+
+
+def test_raster_matches_oracle_on_smpl_and_edge_cases():
+    _, faces_idx = load_smpl_template()
+    cam, verts = synth.smpl_poses(2, seed=2)
+    ofaces, ofim, owim = oracle.render_fim_wim(cam.numpy(), verts.numpy(), faces_idx, 128)
+    faces, fim, wim = ops.render_fim_wim(cam.to(DEV), verts.to(DEV), _cu(faces_idx), 128)
+    assert np.array_equal(_bits(faces), ofaces.view(np.int32))
+    assert np.array_equal(_np(fim), ofim)
+    assert np.array_equal(_bits(wim), owim.view(np.int32))
+    # two-step path (explicit faces tensor) == fused path
+    fim2, wim2 = ops.raster_fim_wim(faces, 128)
+    assert torch.equal(fim, fim2) and torch.equal(wim, wim2)
+    # depth ties resolve to the lowest face index; exact-edge pixels belong to both neighbours
+    quad = np.array([[[-1, -1, 2], [1, -1, 2], [1, 1, 2]], [[-1, -1, 2], [1, 1, 2], [-1, 1, 2]],
+                     [[-1, -1, 2], [1, -1, 2], [1, 1, 2]]], np.float32)[None]
+    for q in (quad, quad[:, ::-1].copy()):
+        of, ow = oracle.raster_fim_wim(q, 16)
+        gf, gw = ops.raster_fim_wim(_cu(q), 16)
+        assert np.array_equal(_np(gf), of) and np.array_equal(_bits(gw), ow.view(np.int32))
+    # degenerate inputs: zero-area, collinear, NaN / inf vertices, behind near / beyond far, empty
+    rng = np.random.default_rng(0)
+    deg = rng.uniform(-1, 1, (1, 40, 3, 3)).astype(np.float32)
+    deg[..., 2] = rng.uniform(0.5, 3, (1, 40, 3))
+    deg[0, 0] = 0
+    deg[0, 1, 1] = deg[0, 1, 0]
+    deg[0, 2, 2] = 0.5 * (deg[0, 2, 0] + deg[0, 2, 1])
+    deg[0, 3, 0, 0] = np.nan
+    deg[0, 4, 1, 1] = np.inf
+    deg[0, 5, :, 2] = 0.05
+    deg[0, 6, :, 2] = 500.0
+    deg[0, 7] = [[-0.5, 0.03125, 1], [0.5, 0.03125, 1], [0.0, 0.03125, 1]]  # collinear through pixel centres
+    of, ow = oracle.raster_fim_wim(deg, 32)
+    gf, gw = ops.raster_fim_wim(_cu(deg), 32)
+    assert np.array_equal(_np(gf), of)
+    assert np.array_equal(_bits(gw), ow.view(np.int32))
+    ef, ew = ops.raster_fim_wim(torch.zeros((1, 0, 3, 3), device=DEV), 8)
+    assert int((ef != -1).sum()) == 0 and float(ew.abs().max()) == 0
+
+
+def test_project_gather_matches_reference_fixture(golden_dir):
+    d = _load(golden_dir, "render_faces.npz")
+    _, faces_idx = load_smpl_template()
+    out = ops.project_gather(_cu(d["cam"]), _cu(d["verts"]), _cu(faces_idx))
+    assert np.array_equal(_np(out)[:, d["face_subset"]], d["faces_xyz_subset"])
+
+
+# ------------------------------------------------------------------ flow (a8, a9)
+def test_flow_compose_matches_reference_fixture_bit_exact(golden_dir):
+    d = _load(golden_dir, "bc_transform.npz")
+    T = ops.flow_compose(_cu(d["src"]), _cu(d["fim"]), _cu(d["wim"]))
+    assert np.array_equal(_bits(T), d["T"].view(np.int32))
+
+
+def test_cal_flow_fused_equals_stepwise_and_oracle():
+    from jafpro_b200.cal_flow import float_estimate
+    _, faces_idx = load_smpl_template()
+    cam, verts = synth.smpl_poses(4, seed=4)
+    sc, sv, tc, tv = cam[:2], verts[:2], cam[2:], verts[2:]
+    oT, ofim, owim = oracle.cal_flow(sc.numpy(), sv.numpy(), tc.numpy(), tv.numpy(), faces_idx, 128)
+    fe = float_estimate(image_size=128).to(DEV)
+    args = (sc.to(DEV), None, sv.to(DEV), None, tc.to(DEV), None, tv.to(DEV), None)
+    T = fe.cal_flow(*args)
+    assert np.array_equal(_bits(T), oT.view(np.int32))
+    fe.fused = False
+    T2 = fe.cal_flow(*args)
+    assert torch.equal(T, T2)
+    T3, fim, wim = fe.render.cal_flow(sc.to(DEV), sv.to(DEV), tc.to(DEV), tv.to(DEV), return_maps=True)
+    assert torch.equal(T, T3) and np.array_equal(_np(fim), ofim) and np.array_equal(_bits(wim), owim.view(np.int32))
+    assert bool((T[fim == -1] == -2).all())
+    # forward(): warp a source frame into the target pose == torch grid_sample on the same flow
+    img = torch.rand(2, 3, 128, 128, device=DEV) * 2 - 1
+    out = fe(img, [sc.to(DEV), None, sv.to(DEV), None], [tc.to(DEV), None, tv.to(DEV), None])
+    ref = F.grid_sample(img, T, mode="bilinear", padding_mode="border", align_corners=False)
+    assert float((out - ref).abs().max()) <= 1e-5
+
+
+# ------------------------------------------------------------------ warp (a10)
+@pytest.mark.parametrize("align_corners", [False, True])
+def test_grid_sample_matches_torch_cuda_and_oracle(align_corners):
+    g = torch.Generator().manual_seed(0)
+    N, C, Hs, Ws, H, W = 3, 5, 37, 29, 41, 23
+    src = torch.randn((N, C, Hs, Ws), generator=g)
+    grid = torch.rand((N, H, W, 2), generator=g) * 2.6 - 1.3
+    grid[0, 0, :4] = -2.0                      # background sentinel (src/nmr.py:627)
+    grid[0, 1, 0] = torch.tensor([1.0, -1.0])  # exact corners
+    grid[0, 1, 1] = torch.tensor([-1.0, 1.0])
+    grid[1, 2, 2] = torch.tensor([55.0, -97.0])
+    out = ops.grid_sample_border(src.to(DEV), grid.to(DEV), align_corners)
+    ref = F.grid_sample(src.to(DEV), grid.to(DEV), mode="bilinear", padding_mode="border", align_corners=align_corners)
+    assert float((out - ref).abs().max()) <= 1e-5  # tolerance of the north star is 1e-4
+    orc = oracle.grid_sample_border(src.numpy(), grid.numpy(), align_corners)
+    assert np.array_equal(_bits(out), orc.view(np.int32))
+
+
+def test_config1_single_reference_frame():
+    """BASELINE config 1: one 256x256 RGB reference, batch 1, synthetic transfer flow."""
+    rgb, _ = synth.reference_sets(1, 1, 0, 256, 256, seed=1)
+    grid = synth.dense_flows(1, 1, 256, 256, seed=1)
+    out = ops.grid_sample_border(rgb[:, 0].to(DEV), grid[:, 0].to(DEV))
+    ref = F.grid_sample(rgb[:, 0], grid[:, 0], mode="bilinear", padding_mode="border", align_corners=False)
+    assert float((out.cpu() - ref).abs().max()) <= 1e-5
+    assert np.array_equal(_bits(out), oracle.grid_sample_border(rgb[:, 0].numpy(), grid[:, 0].numpy()).view(np.int32))
+
+
+# ------------------------------------------------------------------ row F
+def _rand_case(B, K, C, H, W, seed, Hs=None, Ws=None, R=None):
+    rng = np.random.default_rng(seed)
+    Hs, Ws, R = Hs or H, Ws or W, R or B
+    return dict(
+        rgb=rng.normal(size=(R, K, 3, Hs, Ws)).astype(np.float32),
+        feat=rng.normal(size=(R, K, C, Hs, Ws)).astype(np.float32),
+        grid=rng.uniform(-1.15, 1.15, size=(B, K, H, W, 2)).astype(np.float32),
+        logits=rng.normal(size=(B, K, H, W)).astype(np.float32),
+        vis=(rng.random((B, K, H, W)) > 0.25).astype(np.float32),
+        mask=(rng.random((B, 1, H, W)) > 0.2).astype(np.float32),
+        fim=rng.integers(-1, 3, size=(B, H, W)).astype(np.int32),
+        fake=rng.normal(size=(B, 3, H, W)).astype(np.float32),
+        conf=rng.random((B, 1, H, W)).astype(np.float32))
+
+
+def _ulp_bf16_diff(a_bits, b_bits):
+    """|a - b| in units of bf16 ulps for same-sign finite values (monotone bit patterns)."""
+    a = a_bits.astype(np.int32)
+    b = b_bits.astype(np.int32)
+    a = np.where(a & 0x8000, 0x8000 - a, a)
+    b = np.where(b & 0x8000, 0x8000 - b, b)
+    return np.abs(a - b)
+
+
+@pytest.mark.parametrize("K,C", [(1, 64), (4, 64), (8, 64), (3, 32), (4, 128), (2, 256)])
+def test_warp_fuse_hot_kernel_matches_oracle(K, C):
+    B, H, W = 2, 40, 52  # ragged: W is not a multiple of the CTA strip, H not of the row chunk
+    c = _rand_case(B, K, C, H, W, seed=K * 100 + C, Hs=33, Ws=47)
+    feat_bits = oracle.f32_to_bf16_bits(c["feat"].transpose(0, 1, 3, 4, 2))        # dense [R,K,Hs,Ws,C]
+    o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=feat_bits, feat_layout="nhwc", feat_bf16=True,
+                         logits=c["logits"], vis=c["vis"], tgt_mask=c["mask"])
+    feat = _cu(feat_bits.view(np.int16)).view(torch.bfloat16).permute(0, 1, 4, 2, 3)  # channels-last strides
+    n0 = _lib.launch_count()
+    out_rgb, out_feat = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, logits=_cu(c["logits"]),
+                                      vis=_cu(c["vis"]), tgt_mask=_cu(c["mask"]))
+    assert _lib.launch_count() == n0 + 1, "RGB + features must be ONE fused launch"
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 2e-6
+    got = _bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous())
+    d = _ulp_bf16_diff(got, o["out_feat"])
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3, (d.max(), (d > 0).mean())
+    # and against the same operation written with torch primitives in bf16 (the reference's path): <= 2e-2
+    ft = feat.float()
+    warped = torch.stack([F.grid_sample(ft[:, k], _cu(c["grid"])[:, k], padding_mode="border", align_corners=False)
+                          for k in range(K)], 1)
+    a = torch.softmax(_cu(c["logits"]), 1) * _cu(c["vis"])
+    ref = (warped * a[:, :, None]).sum(1) * _cu(c["mask"])
+    assert float((out_feat.float() - ref).abs().max()) <= 2e-2
+
+
+def test_warp_fuse_k1_is_exactly_warp_image_times_mask():
+    c = _rand_case(2, 1, 64, 32, 32, seed=9)
+    mask3 = np.repeat(c["mask"], 3, axis=1)
+    rgb, grid = _cu(c["rgb"]), _cu(c["grid"])
+    out_rgb, _ = ops.warp_fuse(grid, rgb=rgb, tgt_mask=_cu(mask3))
+    ws = ops.grid_sample_border(rgb[:, 0].contiguous(), grid[:, 0].contiguous())
+    assert torch.equal(out_rgb, ws * _cu(mask3))
+    ref = oracle.warp_fuse(c["grid"], rgb=c["rgb"], tgt_mask=mask3)["out_rgb"]
+    assert np.array_equal(_bits(out_rgb), ref.view(np.int32))
+    # hot kernel, K = 1, no logits: bf16 features bit-exact too
+    fb = oracle.f32_to_bf16_bits(c["feat"].transpose(0, 1, 3, 4, 2))
+    o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=fb, feat_layout="nhwc", feat_bf16=True, tgt_mask=c["mask"])
+    feat = _cu(fb.view(np.int16)).view(torch.bfloat16).permute(0, 1, 4, 2, 3)
+    r2, f2 = ops.warp_fuse(grid, rgb=rgb, feat=feat, tgt_mask=_cu(c["mask"]))
+    assert np.array_equal(_bits(r2), o["out_rgb"].view(np.int32))
+    assert np.array_equal(_bf16_bits(f2.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
+
+
+@pytest.mark.parametrize("layout,dtype", [("planar", "f32"), ("nhwc", "f32"), ("planar", "bf16"), ("nhwc", "bf16")])
+def test_warp_fuse_generic_kernel_all_layouts(layout, dtype):
+    B, K, C, H, W = 2, 3, 12, 19, 27  # C = 12: one of the reference's own channel counts, not hot-path eligible
+    c = _rand_case(B, K, C, H, W, seed=21, R=3)
+    ref_index = np.array([2, 0], np.int32)
+    src = c["feat"] if layout == "planar" else c["feat"].transpose(0, 1, 3, 4, 2)
+    if dtype == "bf16":
+        src_o = oracle.f32_to_bf16_bits(src)
+        t = _cu(src_o.view(np.int16)).view(torch.bfloat16)
+    else:
+        src_o = src
+        t = _cu(src)
+    if layout == "nhwc":
+        t = t.permute(0, 1, 4, 2, 3)
+    o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=src_o, feat_layout=layout, feat_bf16=(dtype == "bf16"),
+                         logits=c["logits"], fim=c["fim"], tgt_mask=c["mask"], fake=c["fake"], conf=c["conf"],
+                         ref_index=ref_index, return_warped=True)
+    out_rgb, out_feat, warped = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=t, logits=_cu(c["logits"]),
+                                              fim=_cu(c["fim"]), tgt_mask=_cu(c["mask"]), fake=_cu(c["fake"]),
+                                              conf=_cu(c["conf"]), ref_index=_cu(ref_index), return_warped=True)
+    assert np.array_equal(_bits(warped), o["warped_rgb"].view(np.int32))  # pure gathers: bit-exact
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 2e-6       # expf ulps only
+    of = out_feat.permute(0, 2, 3, 1).contiguous() if layout == "nhwc" else out_feat
+    if dtype == "bf16":
+        d = _ulp_bf16_diff(_bf16_bits(of), o["out_feat"])
+        assert d.max() <= 1 and (d > 0).mean() < 2e-3
+    else:
+        assert float(np.abs(_np(of) - o["out_feat"]).max()) <= 2e-6
+
+
+def test_warp_fuse_default_visibility_and_background_skip():
+    """vis defaults to fim != -1 (the -2 sentinel of src/nmr.py:627,644): background pixels come out 0
+    whatever the references hold there, foreground pixels ignore the sentinel."""
+    c = _rand_case(1, 4, 64, 32, 32, seed=5)
+    c["grid"][0, :, :8] = -2.0
+    c["fim"][0, :8] = -1
+    c["fim"][0, 8:] = 7
+    fb = oracle.f32_to_bf16_bits(c["feat"].transpose(0, 1, 3, 4, 2))
+    feat = _cu(fb.view(np.int16)).view(torch.bfloat16).permute(0, 1, 4, 2, 3)
+    out_rgb, out_feat = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, logits=_cu(c["logits"]),
+                                      fim=_cu(c["fim"]))
+    assert float(out_rgb[0, :, :8].abs().max()) == 0 and float(out_feat[0, :, :8].float().abs().max()) == 0
+    o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=fb, feat_layout="nhwc", feat_bf16=True, logits=c["logits"],
+                         fim=c["fim"])
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 2e-6
+
+
+def test_warp_fuse_rejects_bad_arguments():
+    g = torch.zeros(1, 1, 4, 4, 2, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.warp_fuse(g)                                           # nothing to warp
+    with pytest.raises(RuntimeError):
+        ops.warp_fuse(g, rgb=torch.zeros(1, 2, 3, 4, 4, device=DEV))  # K mismatch
+    with pytest.raises(RuntimeError):
+        ops.warp_fuse(g, rgb=torch.zeros(1, 1, 3, 4, 4, device=DEV), logits=torch.zeros(1, 1, 4, 5, device=DEV))
+    with pytest.raises(RuntimeError):
+        ops.warp_fuse(g[..., :1], rgb=torch.zeros(1, 1, 3, 4, 4, device=DEV))
+
+
+def test_full_size_properties_256_k4_c64():
+    """BASELINE config 2 shape (one video's worth): size-independent properties at full resolution."""
+    B, K, C, H, W = 6, 4, 64, 256, 256
+    rgb, feat = synth.reference_sets(B, K, C, H, W, seed=3, device=DEV)
+    logits = torch.randn(B, K, H, W, device=DEV)
+    ident = synth.identity_grid(H, W, DEV)[None, None].expand(B, K, H, W, 2).contiguous()
+    # (1) identity flow: the warp is the identity, so fused == softmax-weighted sum of the references
+    out_rgb, out_feat = ops.warp_fuse(ident, rgb=rgb, feat=feat, logits=logits)
+    a = torch.softmax(logits, 1)
+    assert float((out_rgb - (rgb * a[:, :, None]).sum(1)).abs().max()) <= 1e-5
+    assert float((out_feat.float() - (feat.float() * a[:, :, None]).sum(1)).abs().max()) <= 2e-2
+    # (2) one-hot logits select one reference: fused == warp of that reference alone (bit-exact)
+    grid = synth.dense_flows(B, K, H, W, seed=4, device=DEV)
+    onehot = torch.full((B, K, H, W), -1e30, device=DEV)
+    onehot[:, 2] = 0
+    r_sel, f_sel = ops.warp_fuse(grid, rgb=rgb, feat=feat, logits=onehot)
+    r_one, f_one = ops.warp_fuse(grid[:, 2:3].contiguous(), rgb=rgb[:, 2:3].contiguous(),
+                                 feat=feat[:, 2:3].permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3))
+    assert torch.equal(r_sel, r_one) and torch.equal(f_sel, f_one)
+    # (3) linearity in the references (fp32 RGB): F(a*x + y) == a*F(x) + F(y) within rounding
+    rgb2 = torch.randn_like(rgb)
+    lhs, _ = ops.warp_fuse(grid, rgb=2.0 * rgb + rgb2, logits=logits)
+    rhs = 2.0 * ops.warp_fuse(grid, rgb=rgb, logits=logits)[0] + ops.warp_fuse(grid, rgb=rgb2, logits=logits)[0]
+    assert float((lhs - rhs).abs().max()) <= 2e-5
+    # (4) against torch's grid_sample composition at full size: <= 1e-4 fp32, <= 2e-2 bf16 (north star)
+    warped = torch.stack([F.grid_sample(rgb[:, k], grid[:, k], padding_mode="border", align_corners=False)
+                          for k in range(K)], 1)
+    ref = (warped * a[:, :, None]).sum(1)
+    got, gotf = ops.warp_fuse(grid, rgb=rgb, feat=feat, logits=logits)
+    assert float((got - ref).abs().max()) <= 1e-4
+    wf = torch.stack([F.grid_sample(feat[:, k].float(), grid[:, k], padding_mode="border", align_corners=False)
+                      for k in range(K)], 1)
+    assert float((gotf.float() - (wf * a[:, :, None]).sum(1)).abs().max()) <= 2e-2
+    # (5) a sub-batch of the oracle at full size (seconds on CPU)
+    o = oracle.warp_fuse(_np(grid[:1]), rgb=_np(rgb[:1]), logits=_np(logits[:1]))
+    assert float(np.abs(_np(got[:1]) - o["out_rgb"]).max()) <= 2e-6
+
+
+def test_warp_fuse_host_pipeline_matches_device_path():
+    """e2e entry point: host buffers in, host buffers out, chunked + pipelined inside the library."""
+    B, K, C, H, W = 7, 4, 64, 64, 64
+    rgb, feat = synth.reference_sets(2, K, C, H, W, seed=8)
+    feat_dense = feat.permute(0, 1, 3, 4, 2).contiguous()  # [R,K,H,W,C]
+    grid = synth.dense_flows(B, K, H, W, seed=8)
+    logits = torch.randn(B, K, H, W)
+    ref_index = torch.tensor([0, 0, 0, 1, 1, 1, 1], dtype=torch.int32)
+    pin = lambda t: t.contiguous().pin_memory()
+    o_rgb, o_feat = ops.warp_fuse_host(pin(grid), rgb=pin(rgb), feat=pin(feat_dense), feat_channels_last=True,
+                                       logits=pin(logits), ref_index=ref_index, frames_per_chunk=2)
+    d_rgb, d_feat = ops.warp_fuse(grid.to(DEV), rgb=rgb.to(DEV), feat=feat.to(DEV), logits=logits.to(DEV),
+                                  ref_index=ref_index.to(DEV))
+    assert torch.equal(o_rgb, d_rgb.cpu())
+    assert torch.equal(o_feat, d_feat.permute(0, 2, 3, 1).contiguous().cpu())
+    # per-frame reference sets (no ref_index), pageable memory, odd chunking
+    rgb7, _ = synth.reference_sets(B, K, 0, H, W, seed=9)
+    o2, _ = ops.warp_fuse_host(grid, rgb=rgb7, logits=logits, frames_per_chunk=3)
+    d2, _ = ops.warp_fuse(grid.to(DEV), rgb=rgb7.to(DEV), logits=logits.to(DEV))
+    assert torch.equal(o2, d2.cpu())
+
+
+# ------------------------------------------------------------------ a11, a12
+def test_mask_blend_matches_reference_fixture(golden_dir):
+    d = _load(golden_dir, "mask_blend.npz")
+    masked, pred = ops.mask_blend(_cu(d["tsf"]), _cu(d["mask"]), _cu(d["fake"]), _cu(d["weight"]))
+    assert np.array_equal(_np(masked), d["tsf"] * d["mask"])
+    assert float(np.abs(_np(pred) - d["pred"]).max()) <= 1e-6
+    om, op_ = oracle.mask_blend(d["tsf"], d["mask"], d["fake"], d["weight"])
+    assert np.array_equal(_bits(pred), op_.view(np.int32))
+    # drop-in module with an injected confidence net
+    from jafpro_b200.flow_net import Propagation3DFlowNet
+    w = _cu(d["weight"])
+    net = Propagation3DFlowNet(lambda x: w)
+    out = net({'fake_tgt': _cu(d["fake"]), 'tsf_image': _cu(d["tsf"]), 'tgt_IUV': None, 'use_IUV': False,
+               'use_mask': True, 'tgt_smpl_mask': _cu(d["mask"])})
+    assert float(np.abs(_np(out['pred_target']) - d["pred"]).max()) <= 1e-6
+    # ragged plane size (scalar path)
+    t = torch.randn(1, 3, 5, 7, device=DEV)
+    m = (torch.rand(1, 1, 5, 7, device=DEV) > 0.5).float()
+    assert torch.equal(ops.mask_blend(t, m)[0], t * m)
+
+
+def test_softmax_fuse_matches_reference_fixture(golden_dir):
+    d = _load(golden_dir, "softmax_fuse.npz")
+    out = ops.softmax_fuse(_cu(d["feat"]), _cu(d["logits"]))
+    assert float(np.abs(_np(out) - d["out"]).max()) <= 1e-6
+    assert float(np.abs(_np(out) - oracle.softmax_fuse(d["feat"], d["logits"])).max()) <= 1e-6
+    f = torch.randn(2, 5 * 6, 7, 9, device=DEV)  # K=5, ragged plane
+    l = torch.randn(2, 5, 7, 9, device=DEV)
+    ref = (f.view(2, 5, 6, 7, 9) * torch.softmax(l, 1)[:, :, None]).sum(1)
+    assert float((ops.softmax_fuse(f, l) - ref).abs().max()) <= 1e-5
+
+
+# ------------------------------------------------------------------ a13
+def test_convlstm_cell_matches_reference_fixture(golden_dir):
+    d = _load(golden_dir, "convlstm.npz")
+    h2, c2 = ops.convlstm_step(_cu(d["x"]), _cu(d["h"]), _cu(d["c"]), _cu(d["weight"]), _cu(d["bias"]))
+    assert float(np.abs(_np(h2) - d["h_out"]).max()) <= 1e-5
+    assert float(np.abs(_np(c2) - d["c_out"]).max()) <= 1e-5
+    from jafpro_b200.convLSTM import ConvLSTM
+    B, K, Cin, H, W = d["seq_x"].shape
+    Ch = d["seq_h"].shape[1]
+    lstm = ConvLSTM((H, W), Cin, Ch, (3, 3), 1, batch_first=True, bias=True).to(DEV)
+    lstm.load_state_dict({"cell_list.0.conv.weight": torch.from_numpy(d["seq_weight"]),
+                          "cell_list.0.conv.bias": torch.from_numpy(d["seq_bias"])})
+    out, last = lstm(_cu(d["seq_x"]))  # default zero state on the module's device
+    assert float(np.abs(_np(out) - d["seq_out"]).max()) <= 2e-5
+    assert float(np.abs(_np(last[0][1]) - d["seq_c"]).max()) <= 2e-5
+
+
+@pytest.mark.parametrize("Cin,Ch,H,W,k", [(12, 12, 50, 50, 3), (24, 48, 25, 25, 3), (7, 5, 13, 13, 5), (3, 2, 9, 20, 7)])
+def test_convlstm_cell_reference_sizes_vs_torch(Cin, Ch, H, W, k):
+    """The reference's own cell sizes (src/networks.py:1304-1313) against torch conv2d + gates in fp32."""
+    torch.manual_seed(Cin)
+    torch.backends.cudnn.allow_tf32 = False
+    B = 3
+    x, h, c = (torch.randn(B, n, H, W, device=DEV) for n in (Cin, Ch, Ch))
+    wgt = torch.randn(4 * Ch, Cin + Ch, k, k, device=DEV) * 0.1
+    bias = torch.randn(4 * Ch, device=DEV)
+    cc = F.conv2d(torch.cat((x, h), 1), wgt, bias, padding=k // 2)
+    i, f, o, g = torch.split(cc, Ch, dim=1)
+    c_ref = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+    h_ref = torch.sigmoid(o) * torch.tanh(c_ref)
+    h2, c2 = ops.convlstm_step(x, h, c, wgt, bias)
+    assert float((c2 - c_ref).abs().max()) <= 5e-5 and float((h2 - h_ref).abs().max()) <= 5e-5
+    h3, c3 = ops.convlstm_step(x, h, c, wgt, None)
+    cc = F.conv2d(torch.cat((x, h), 1), wgt, None, padding=k // 2)
+    i, f, o, g = torch.split(cc, Ch, dim=1)
+    assert float((c3 - (torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g))).abs().max()) <= 5e-5
