@@ -334,8 +334,12 @@ def main():
     ap.add_argument("--flow", default="dense", choices=["dense", "smpl"],
                     help="dense: every pixel visible (worst case, headline); smpl: real transfer flows, ~12%% foreground")
     ap.add_argument("--e2e-frames", type=int, default=60)
+    ap.add_argument("--videos-per-gpu", type=int, default=0, help="override the workload's videos per GPU (profiling)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.videos_per_gpu > 0:
+        w = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (args.videos_per_gpu,) + tuple(w[1:])
     if args.impl == "reference":
         run_reference(args)
     else:

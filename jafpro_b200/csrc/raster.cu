@@ -325,7 +325,7 @@ size_t jaf_raster_workspace_bytes(int B, int image_size) {
 
 int jaf_raster_fim_wim(const float* faces_xyz, int B, int F, int image_size, float near_, float far_,
                        int flip_rows, int32_t* fim, float* wim, float* depth, void* workspace, void* stream) {
-  JAF_REQUIRE(faces_xyz && fim && wim && workspace, "null pointer");
+  JAF_REQUIRE((faces_xyz || F == 0) && fim && wim && workspace, "null pointer");
   JAF_REQUIRE(check_raster_args(B, F, image_size), "bad sizes");
   if (B == 0) return JAF_OK;
   cudaStream_t st = jaf::as_stream(stream);

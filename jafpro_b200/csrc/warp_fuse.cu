@@ -34,9 +34,11 @@ struct Tap {
   float nw, ne, sw, se;
 };
 
+// Every operation is pinned (no compiler-chosen contraction): (c + 1) * size - 1 is the one place
+// where nvcc fuses ATen's expression into an FMA, and the oracle restates exactly that.
 __device__ __forceinline__ float unnormalize(float c, int size, int align_corners) {
-  if (align_corners) return ((c + 1.f) / 2) * (size - 1);
-  return ((c + 1.f) * size - 1) / 2;
+  if (align_corners) return __fmul_rn(__fmul_rn(__fadd_rn(c, 1.f), 0.5f), (float)(size - 1));
+  return __fmul_rn(__fmaf_rn(__fadd_rn(c, 1.f), (float)size, -1.f), 0.5f);
 }
 
 __device__ __forceinline__ Tap make_tap(float gx, float gy, int Ws, int Hs, int align_corners) {
@@ -45,16 +47,17 @@ __device__ __forceinline__ Tap make_tap(float gx, float gy, int Ws, int Hs, int 
   ix = fminf((float)(Ws - 1), fmaxf(ix, 0.f));  // clip_coordinates (NaN -> 0)
   iy = fminf((float)(Hs - 1), fmaxf(iy, 0.f));
   const float fx = floorf(ix), fy = floorf(iy);
-  const float x1 = fx + 1.f, y1 = fy + 1.f;
+  const float x1 = fx + 1.f, y1 = fy + 1.f;  // exact (small integers)
   Tap t;
   const int x0 = (int)fx, y0 = (int)fy;
   t.off = y0 * Ws + x0;
   t.dx = (x0 + 1 < Ws) ? 1 : 0;
   t.dy = (y0 + 1 < Hs) ? Ws : 0;
-  t.nw = (x1 - ix) * (y1 - iy);
-  t.ne = (ix - fx) * (y1 - iy);
-  t.sw = (x1 - ix) * (iy - fy);
-  t.se = (ix - fx) * (iy - fy);
+  const float ax = __fsub_rn(x1, ix), bx = __fsub_rn(ix, fx), ay = __fsub_rn(y1, iy), by = __fsub_rn(iy, fy);
+  t.nw = __fmul_rn(ax, ay);
+  t.ne = __fmul_rn(bx, ay);
+  t.sw = __fmul_rn(ax, by);
+  t.se = __fmul_rn(bx, by);
   return t;
 }
 
