@@ -21,6 +21,8 @@
 // (ATen/native/cuda/GridSampler.cuh:14-45 and the kernel body in GridSampler.cu).
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -82,16 +84,47 @@ struct WFArgs {
 // =====================================================================================
 // Hot kernel: channels-last bf16 features (+ optional planar f32 RGB)
 // =====================================================================================
-template <int LPP, int KT>
-__global__ void __launch_bounds__(256)
+// Sample position for the hot kernel: identical values to make_tap(), but the integer corner is
+// clamped to [0, size-2] so that all four taps are always in bounds (when the clamped coordinate sits
+// exactly on the last row/column the weights become (0, 1) instead of (1, skipped) — the same sum,
+// bit for bit — and no per-tap border flags have to travel with the offset).
+struct HotTap {
+  int off;  // y0 * Ws + x0 with x0 <= Ws-2, y0 <= Hs-2
+  float nw, ne, sw, se;
+};
+__device__ __forceinline__ HotTap make_hot_tap(float gx, float gy, int Ws, int Hs, int align_corners) {
+  float ix = unnormalize(gx, Ws, align_corners);
+  float iy = unnormalize(gy, Hs, align_corners);
+  ix = fminf((float)(Ws - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(Hs - 1), fmaxf(iy, 0.f));
+  const float fx = fminf(floorf(ix), (float)(Ws - 2)), fy = fminf(floorf(iy), (float)(Hs - 2));
+  const float ax = __fsub_rn(fx + 1.f, ix), bx = __fsub_rn(ix, fx);
+  const float ay = __fsub_rn(fy + 1.f, iy), by = __fsub_rn(iy, fy);
+  HotTap t;
+  t.off = (int)fy * Ws + (int)fx;
+  t.nw = __fmul_rn(ax, ay);
+  t.ne = __fmul_rn(bx, ay);
+  t.sw = __fmul_rn(ax, by);
+  t.se = __fmul_rn(bx, by);
+  return t;
+}
+
+template <int LPP, int KT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_warp_fuse_nhwc(const WFArgs a) {
   static_assert(KT <= LPP, "one lane of the pixel group per reference");
   constexpr int PPW = 32 / LPP;  // pixels per warp
   constexpr int TW = 8 * PPW;    // strip width of the CTA (8 warps)
+  constexpr int NREP = (LPP / KT) < 3 ? (LPP / KT) : 3;  // lanes sharing one reference's RGB planes
+  constexpr int CS = (3 + NREP - 1) / NREP;              // RGB channels per such lane
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned PIXB = LPP * 16;  // bytes of one channels-last pixel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / LPP;  // pixel group within the warp
-  const int j = lane % LPP;  // lane within the group == reference index it prepares
+  const int j = lane % LPP;  // lane within the group: owns channels 8j..8j+7
+  const int kk = j % KT;     // the reference whose sample position / weights this lane prepares
+  const int rep = j / KT;    // replica index among the lanes preparing reference kk (RGB work split)
+  const int gl = g * LPP;    // first lane of this pixel group
   int bid = blockIdx.x;
   const int tx = bid % a.tiles_x;
   bid /= a.tiles_x;
@@ -101,115 +134,142 @@ k_warp_fuse_nhwc(const WFArgs a) {
   const bool xin = x < a.W;
   const int y_begin = ty * a.rows_per_cta;
   const int y_end = min(a.H, y_begin + a.rows_per_cta);
-  const long HW = (long)a.H * a.W;
-  const long HWs = (long)a.Hs * a.Ws;
-  const long r = a.ref_index ? a.ref_index[b] : b;
-  const uint4* __restrict__ feat = reinterpret_cast<const uint4*>(a.feat);
+  const size_t HW = (size_t)a.H * a.W;
+  const size_t HWs = (size_t)a.Hs * a.Ws;
+  const size_t r = a.ref_index ? a.ref_index[b] : b;
   const bool has_rgb = a.rgb != nullptr && a.out_rgb != nullptr;
+  const bool rgb_lane = has_rgb && rep < NREP;
+  const int Ws = a.Ws;
+  // ---- per-CTA 64-bit bases; inside the row loop every address is one IMAD.WIDE on a 32-bit offset
+  const char* fk[KT];  // this lane's 16-byte column of reference k
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+    fk[k] = reinterpret_cast<const char*>(a.feat) + ((r * KT + k) * HWs) * PIXB + j * 16;
+  const float* rgb_c[CS];  // RGB plane(s) this lane gathers from (reference kk)
+#pragma unroll
+  for (int sl = 0; sl < CS; ++sl) {
+    const int c = min(rep + sl * NREP, 2);
+    rgb_c[sl] = has_rgb ? a.rgb + ((r * KT + kk) * 3 + c) * HWs : nullptr;
+  }
+  const size_t bk0 = ((size_t)b * KT + kk) * HW;
+  const float* __restrict__ p_logit = a.logits ? a.logits + bk0 : nullptr;
+  const float* __restrict__ p_vis = a.vis ? a.vis + bk0 : nullptr;
+  const int* __restrict__ p_fim = (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr;
+  const float2* __restrict__ p_grid = reinterpret_cast<const float2*>(a.grid) + bk0;
+  const float* __restrict__ p_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
+  uint4* __restrict__ p_out = reinterpret_cast<uint4*>(a.out_feat) + (size_t)b * HW * LPP + j;
 
-  for (int y = y_begin; y < y_end; ++y) {
-    const long pix = (long)y * a.W + x;
-    // ---- lane j prepares reference j: flow sample, visibility, softmax term
-    float lg = -CUDART_INF_F, v = 0.f;
-    Tap t = {0, 0, 0, 0.f, 0.f, 0.f, 0.f};
-    if (xin && j < KT) {
-      const long bk = ((long)b * KT + j) * HW + pix;
-      lg = a.logits ? ld_stream_f32(a.logits + bk) : 0.f;
-      if (a.vis)
-        v = ld_stream_f32(a.vis + bk);
-      else if (a.fim)
-        v = (ld_stream_s32(a.fim + (long)b * HW + pix) != -1) ? 1.f : 0.f;
-      else
-        v = 1.f;
-      const float2 gxy = ld_stream_f32x2(a.grid + bk * 2);
-      t = make_tap(gxy.x, gxy.y, a.Ws, a.Hs, a.align_corners);
+  unsigned pix = (unsigned)y_begin * (unsigned)a.W + (unsigned)x;  // in-frame pixel index (< 2^29)
+  for (int y = y_begin; y < y_end; ++y, pix += (unsigned)a.W) {
+    // ---- this lane's reference kk: flow sample, visibility, softmax term
+    float lg = 0.f, v = 1.f;
+    float2 gxy = make_float2(0.f, 0.f);
+    if (xin) {
+      gxy = ld_stream_f32x2(reinterpret_cast<const float*>(p_grid + pix));
+      if (p_logit) lg = ld_stream_f32(p_logit + pix);
+      if (p_vis) v = ld_stream_f32(p_vis + pix);
+      if (p_fim) v = (ld_stream_s32(p_fim + pix) != -1) ? 1.f : 0.f;
     }
-    // softmax over the group's K lanes: max by butterfly, sum in reference order k = 0..K-1
+    // softmax over the group's references: max by butterfly (replica lanes hold copies, so the
+    // full-group max is the max over k), sum in reference order k = 0..K-1
     float m = lg;
 #pragma unroll
     for (int s = LPP / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
-    const float e = (j < KT) ? expf(lg - m) : 0.f;
+    const float e = expf(lg - m);
     float ssum = 0.f;
 #pragma unroll
-    for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, g * LPP + k);
-    const float aw = (e / ssum) * v;  // alpha_k * vis_k
+    for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, gl + k);
+    const float aw = xin ? __fdividef(e, ssum) * v : 0.f;  // alpha_k * vis_k
+    HotTap t = make_hot_tap(gxy.x, gxy.y, Ws, a.Hs, a.align_corners);
     t.nw *= aw;
     t.ne *= aw;
     t.sw *= aw;
     t.se *= aw;
-    const unsigned act = __ballot_sync(FULL, xin && j < KT && aw != 0.f);
-    const int packed = (t.off << 2) | (t.dx) | (t.dy ? 2 : 0);
+    const bool act = aw != 0.f;
+    // invisible references still issue their (weight-0) loads, from pixel 0 of the reference: no
+    // divergent branch in the gather loop and no new cache lines
+    const unsigned off = act ? (unsigned)t.off : 0u;
+    const bool any = __ballot_sync(FULL, act) != 0u;  // warp-uniform: nothing visible => skip the gathers
 
-    float acc[8];
+    float2 acc[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    float acc_rgb = 0.f;
+    for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
+    float rgb_tot[CS];
+#pragma unroll
+    for (int sl = 0; sl < CS; ++sl) rgb_tot[sl] = 0.f;
 
+    if (any) {
+      // RGB: lane (kk, rep) gathers channel(s) rep, rep+NREP of reference kk with its own tap
+      float sv[CS];
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      const int src = g * LPP + k;
-      const int pk = __shfl_sync(FULL, packed, src);
-      const float wnw = __shfl_sync(FULL, t.nw, src), wne = __shfl_sync(FULL, t.ne, src);
-      const float wsw = __shfl_sync(FULL, t.sw, src), wse = __shfl_sync(FULL, t.se, src);
-      if ((act >> src) & 1u) {
-        const int off = pk >> 2;
-        const int dx = pk & 1;
-        const int dy = (pk & 2) ? a.Ws : 0;
-        if (feat) {
-          const uint4* p = feat + (((long)r * KT + k) * HWs + off) * LPP + j;
-          const uint4 q00 = ld_gather_u128(p);
-          const uint4 q01 = ld_gather_u128(p + dx * LPP);
-          const uint4 q10 = ld_gather_u128(p + (long)dy * LPP);
-          const uint4 q11 = ld_gather_u128(p + (long)(dy + dx) * LPP);
-          const uint32_t w00[4] = {q00.x, q00.y, q00.z, q00.w}, w01[4] = {q01.x, q01.y, q01.z, q01.w};
-          const uint32_t w10[4] = {q10.x, q10.y, q10.z, q10.w}, w11[4] = {q11.x, q11.y, q11.z, q11.w};
+      for (int sl = 0; sl < CS; ++sl) {
+        sv[sl] = 0.f;
+        if (rgb_lane && rep + sl * NREP < 3) {
+          const float* p0 = rgb_c[sl] + off;
+          const float* p1 = rgb_c[sl] + (off + (unsigned)Ws);
+          float q = __ldg(p0) * t.nw;
+          q = fmaf(__ldg(p0 + 1), t.ne, q);
+          q = fmaf(__ldg(p1), t.sw, q);
+          sv[sl] = fmaf(__ldg(p1 + 1), t.se, q);
+        }
+      }
+      // features: reference after reference; every lane of the group gets reference k's offset and
+      // weights by shuffle and moves its own 16 bytes of each of the 4 taps
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            acc[2 * c] = fmaf(bf16_lo(w00[c]), wnw, acc[2 * c]);
-            acc[2 * c + 1] = fmaf(bf16_hi(w00[c]), wnw, acc[2 * c + 1]);
-            acc[2 * c] = fmaf(bf16_lo(w01[c]), wne, acc[2 * c]);
-            acc[2 * c + 1] = fmaf(bf16_hi(w01[c]), wne, acc[2 * c + 1]);
-            acc[2 * c] = fmaf(bf16_lo(w10[c]), wsw, acc[2 * c]);
-            acc[2 * c + 1] = fmaf(bf16_hi(w10[c]), wsw, acc[2 * c + 1]);
-            acc[2 * c] = fmaf(bf16_lo(w11[c]), wse, acc[2 * c]);
-            acc[2 * c + 1] = fmaf(bf16_hi(w11[c]), wse, acc[2 * c + 1]);
-          }
+      for (int k = 0; k < KT; ++k) {
+        const unsigned ok = __shfl_sync(FULL, off, gl + k);
+        const uint4* p0 = reinterpret_cast<const uint4*>(fk[k] + (size_t)ok * PIXB);
+        const uint4* p1 = reinterpret_cast<const uint4*>(fk[k] + (size_t)(ok + (unsigned)Ws) * PIXB);
+        uint4 q[4];
+        q[0] = ld_gather_u128(p0);
+        q[1] = ld_gather_u128(p0 + LPP);
+        q[2] = ld_gather_u128(p1);
+        q[3] = ld_gather_u128(p1 + LPP);
+        float wt[4];
+        wt[0] = __shfl_sync(FULL, t.nw, gl + k);
+        wt[1] = __shfl_sync(FULL, t.ne, gl + k);
+        wt[2] = __shfl_sync(FULL, t.sw, gl + k);
+        wt[3] = __shfl_sync(FULL, t.se, gl + k);
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+          const float2 w2 = make_float2(wt[tp], wt[tp]);
+          const uint32_t wd[4] = {q[tp].x, q[tp].y, q[tp].z, q[tp].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)  // packed fp32x2 FMA: two channels per instruction
+            acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
         }
-        if (has_rgb && j < 3) {
-          const float* p = a.rgb + (((long)r * KT + k) * 3 + j) * HWs + off;
-          float s = __ldg(p) * wnw;
-          s = fmaf(__ldg(p + dx), wne, s);
-          s = fmaf(__ldg(p + dy), wsw, s);
-          s = fmaf(__ldg(p + dy + dx), wse, s);
-          acc_rgb += s;
-        }
+      }
+      if (has_rgb) {  // sum over k in reference order
+#pragma unroll
+        for (int sl = 0; sl < CS; ++sl)
+#pragma unroll
+          for (int k = 0; k < KT; ++k) rgb_tot[sl] += __shfl_sync(FULL, sv[sl], (gl + rep * KT + k) & 31);
       }
     }
 
     if (xin) {
-      const float tm = a.tgt_mask ? ld_stream_f32(a.tgt_mask + ((long)b * a.mask_c) * HW + pix) : 1.f;
-      if (a.out_feat) {
-        if (a.tgt_mask) {
+      const float tm = p_mask ? ld_stream_f32(p_mask + pix) : 1.f;
+      uint4 o;
+      o.x = pack_bf16x2(acc[0].x * tm, acc[0].y * tm);
+      o.y = pack_bf16x2(acc[1].x * tm, acc[1].y * tm);
+      o.z = pack_bf16x2(acc[2].x * tm, acc[2].y * tm);
+      o.w = pack_bf16x2(acc[3].x * tm, acc[3].y * tm);
+      st_stream_u128(p_out + (size_t)pix * LPP, o);
+      if (rgb_lane && kk == 0) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] *= tm;
+        for (int sl = 0; sl < CS; ++sl) {
+          const int c = rep + sl * NREP;
+          if (c < 3) {
+            float ov = rgb_tot[sl];
+            if (p_mask) ov *= (a.mask_c == 3) ? ld_stream_f32(p_mask + (size_t)c * HW + pix) : tm;
+            if (a.fake && a.conf) {
+              const float wc = ld_stream_f32(a.conf + (size_t)b * HW + pix);
+              const float fkv = ld_stream_f32(a.fake + ((size_t)b * 3 + c) * HW + pix);
+              ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+            }
+            st_stream_f32(a.out_rgb + ((size_t)b * 3 + c) * HW + pix, ov);
+          }
         }
-        uint4 o;
-        o.x = pack_bf16x2(acc[0], acc[1]);
-        o.y = pack_bf16x2(acc[2], acc[3]);
-        o.z = pack_bf16x2(acc[4], acc[5]);
-        o.w = pack_bf16x2(acc[6], acc[7]);
-        st_stream_u128(reinterpret_cast<uint4*>(a.out_feat) + ((long)b * HW + pix) * LPP + j, o);
-      }
-      if (has_rgb && j < 3) {
-        float o = acc_rgb;
-        if (a.tgt_mask)
-          o *= (a.mask_c == 3) ? ld_stream_f32(a.tgt_mask + ((long)b * 3 + j) * HW + pix) : tm;
-        if (a.fake && a.conf) {
-          const float wc = ld_stream_f32(a.conf + (long)b * HW + pix);
-          const float fk = ld_stream_f32(a.fake + ((long)b * 3 + j) * HW + pix);
-          o = fk * wc + o * (1.0f - wc);  // src/flow_net.py:98
-        }
-        st_stream_f32(a.out_rgb + ((long)b * 3 + j) * HW + pix, o);
       }
     }
   }
@@ -327,34 +387,51 @@ k_warp_fuse_generic(const WFArgs a) {
   }
 }
 
+// resident CTAs per SM the kernel is compiled for (register cap = 65536 / (256 * MINB)); tunable
+int wf_minb() {
+  static int mb = [] {
+    const char* e = getenv("JAF_WF_MINB");
+    const int v = e ? atoi(e) : 4;
+    return (v >= 3 && v <= 6) ? v : 4;
+  }();
+  return mb;
+}
+
+template <int LPP, int KV>
+bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
+  if constexpr (KV <= LPP) {
+    switch (wf_minb()) {
+      case 3: k_warp_fuse_nhwc<LPP, KV, 3><<<grid, 256, 0, st>>>(a); break;
+      case 5: k_warp_fuse_nhwc<LPP, KV, 5><<<grid, 256, 0, st>>>(a); break;
+      case 6: k_warp_fuse_nhwc<LPP, KV, 6><<<grid, 256, 0, st>>>(a); break;
+      default: k_warp_fuse_nhwc<LPP, KV, 4><<<grid, 256, 0, st>>>(a); break;
+    }
+    return true;
+  } else {
+    return false;
+  }
+}
+
 template <int LPP>
 bool launch_nhwc_k(const WFArgs& a, int grid, cudaStream_t st) {
-#define JAF_CASE(KV)                                             \
-  case KV:                                                       \
-    if constexpr (KV <= LPP) {                                   \
-      k_warp_fuse_nhwc<LPP, KV><<<grid, 256, 0, st>>>(a);        \
-      return true;                                               \
-    }                                                            \
-    return false;
   switch (a.K) {
-    JAF_CASE(1)
-    JAF_CASE(2)
-    JAF_CASE(3)
-    JAF_CASE(4)
-    JAF_CASE(5)
-    JAF_CASE(6)
-    JAF_CASE(7)
-    JAF_CASE(8)
-    default:
-      return false;
+    case 1: return launch_nhwc_kc<LPP, 1>(a, grid, st);
+    case 2: return launch_nhwc_kc<LPP, 2>(a, grid, st);
+    case 3: return launch_nhwc_kc<LPP, 3>(a, grid, st);
+    case 4: return launch_nhwc_kc<LPP, 4>(a, grid, st);
+    case 5: return launch_nhwc_kc<LPP, 5>(a, grid, st);
+    case 6: return launch_nhwc_kc<LPP, 6>(a, grid, st);
+    case 7: return launch_nhwc_kc<LPP, 7>(a, grid, st);
+    case 8: return launch_nhwc_kc<LPP, 8>(a, grid, st);
+    default: return false;
   }
-#undef JAF_CASE
 }
 
 // Returns true when the hot kernel was launched.
 bool launch_nhwc(WFArgs a, cudaStream_t st) {
   const int lpp = a.C / 8;
   if (a.C % 8 != 0 || !(lpp == 4 || lpp == 8 || lpp == 16 || lpp == 32) || a.K > lpp || a.K > 8) return false;
+  if (a.Ws < 2 || a.Hs < 2 || (long)a.H * a.W >= (1L << 29)) return false;
   const int ppw = 32 / lpp;
   const int tw = 8 * ppw;
   a.tiles_x = (a.W + tw - 1) / tw;
