@@ -38,6 +38,8 @@ WORKLOADS = {
     "dancevideo_256_k4_c64": (8, 30, 256, 4, 64),      # BASELINE configs[1]  (the headline)
     "scaled_512_k8_c64": (8, 30, 512, 8, 64),          # BASELINE configs[4]: 64 videos over 8 GPUs
     "rgb_only_256_k4": (8, 30, 256, 4, 0),
+    "diag_240_k4_c64": (8, 30, 240, 4, 64),            # non-power-of-two strides (diagnostics)
+    "diag_272_k4_c64": (8, 30, 272, 4, 64),
 }
 
 
