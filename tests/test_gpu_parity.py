@@ -468,3 +468,60 @@ def test_convlstm_cell_reference_sizes_vs_torch(Cin, Ch, H, W, k):
     h3, c3 = ops.convlstm_step(x, h, c, wgt, None)
     h_ref3, c_ref3 = ref(None)
     assert float((c3 - c_ref3).abs().max()) <= 5e-5 and float((h3 - h_ref3).abs().max()) <= 5e-5
+
+
+# ------------------------------------------------------------------ a13 on tensor cores (tcgen05)
+def _convlstm_ref_nhwc(x, h, c, wgt, bias):
+    """fp64 torch reference of src/convLSTM.py:41-56 on the bf16-rounded operands (NHWC in / out)."""
+    Ch = h.shape[-1]
+    xin = torch.cat((x.float(), h.float()), -1).permute(0, 3, 1, 2).double()
+    cc = F.conv2d(xin, wgt.to(torch.bfloat16).double(), None if bias is None else bias.double(), padding=1)
+    i, f, o, g = torch.split(cc, Ch, dim=1)
+    c_r = torch.sigmoid(f) * c.permute(0, 3, 1, 2).double() + torch.sigmoid(i) * torch.tanh(g)
+    h_r = torch.sigmoid(o) * torch.tanh(c_r)
+    return h_r.permute(0, 2, 3, 1).float(), c_r.permute(0, 2, 3, 1).float()
+
+
+@pytest.mark.parametrize("B,Cin,Ch,H,W,use_bias", [(2, 64, 64, 8, 64, True), (1, 128, 64, 4, 32, False),
+                                                  (3, 64, 128, 2, 128, True), (2, 256, 256, 64, 64, True)])
+def test_convlstm_tensor_core_cell(B, Cin, Ch, H, W, use_bias):
+    """tcgen05 implicit-GEMM cell (bf16 operands, fp32 accumulate and state) vs an fp64 reference on the
+    same bf16-rounded operands: c within 2e-3, h within 2e-2 (north star: <= 2e-2 for bf16 features).
+    The last case is the BASELINE config-4 layer shape (256+256 -> 1024 channels, 64x64) at batch 2."""
+    torch.manual_seed(B * 1000 + Cin)
+    x = torch.randn(B, H, W, Cin, device=DEV).to(torch.bfloat16)
+    h = torch.randn(B, H, W, Ch, device=DEV).to(torch.bfloat16)
+    c = torch.randn(B, H, W, Ch, device=DEV)
+    wgt = torch.randn(4 * Ch, Cin + Ch, 3, 3, device=DEV) * (1.0 / (3.0 * (Cin + Ch) ** 0.5))
+    bias = torch.randn(4 * Ch, device=DEV) if use_bias else None
+    wpack = ops.convlstm_pack_weight(wgt, Cin, Ch)
+    h2, c2 = ops.convlstm_step_tc(x, h, c, wpack, bias, Cin, Ch)
+    h_ref, c_ref = _convlstm_ref_nhwc(x, h, c, wgt, bias)
+    assert float((c2 - c_ref).abs().max()) <= 2e-3
+    assert float((h2.float() - h_ref).abs().max()) <= 2e-2
+    # the fp32 CUDA-core cell on the same (bf16-rounded) operands agrees as well
+    h3, c3 = ops.convlstm_step(x.float().permute(0, 3, 1, 2).contiguous(), h.float().permute(0, 3, 1, 2).contiguous(),
+                               c.permute(0, 3, 1, 2).contiguous(), wgt.to(torch.bfloat16).float(), bias)
+    assert float((c3.permute(0, 2, 3, 1) - c2).abs().max()) <= 2e-3
+    # K = 4 sequential steps from zero state through the module wrapper (config 4: K = 4 references)
+    from jafpro_b200.convLSTM import ConvLSTMCellTC
+    cell = ConvLSTMCellTC(Cin, Ch, wgt, bias)
+    hs = torch.zeros(B, H, W, Ch, device=DEV, dtype=torch.bfloat16)
+    cs = torch.zeros(B, H, W, Ch, device=DEV)
+    hr, cr = hs, cs
+    for t in range(4):
+        xt = torch.randn(B, H, W, Cin, device=DEV).to(torch.bfloat16)
+        hs, cs = cell(xt, (hs, cs))
+        hr, cr = _convlstm_ref_nhwc(xt, hr, cr, wgt, bias)
+        hr = hr.to(torch.bfloat16)
+    assert float((cs - cr).abs().max()) <= 2e-2 and float((hs.float() - hr.float()).abs().max()) <= 3e-2
+
+
+def test_convlstm_tensor_core_rejects_unsupported_shapes():
+    x = torch.zeros(1, 4, 48, 64, device=DEV, dtype=torch.bfloat16)  # W = 48 does not divide 128
+    c = torch.zeros(1, 4, 48, 64, device=DEV)
+    wp = torch.zeros(_lib.lib().jaf_convlstm_wpack_bytes(64, 64), dtype=torch.uint8, device=DEV)
+    with pytest.raises(RuntimeError, match="W must divide 128"):
+        ops.convlstm_step_tc(x, x, c, wp, None, 64, 64)
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        ops.convlstm_pack_weight(torch.zeros(4 * 24, 36, 3, 3, device=DEV), 12, 24)
