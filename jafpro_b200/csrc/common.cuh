@@ -54,6 +54,24 @@ __device__ __forceinline__ int ld_stream_s32(const int* p) {
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+// L1-bypassing loads that ask L2 to retain the line (the data is read once more, later, by the same CTA)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float ld_stream_keep_f32(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ld_stream_keep_f32x2(const float* p, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+               : "=f"(v.x), "=f"(v.y)
+               : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ uint4 ld_gather_u128(const uint4* p) {
   // read-only path, L1-allocating: neighbouring output pixels re-use the same taps
   return __ldg(p);

@@ -109,170 +109,195 @@ __device__ __forceinline__ HotTap make_hot_tap(float gx, float gy, int Ws, int H
   return t;
 }
 
+// Two phases per CTA tile (a strip of TW = 8 * 32/LPP pixel columns x rows_per_cta rows):
+//
+// Phase A, features.  A group of LPP = C/8 lanes owns one pixel column; lane j owns channels 8j..8j+7 and
+//   PREPARES reference kk = j % KT: flow sample, clamped corner, bilinear weights pre-multiplied by
+//   softmax * visibility.  Offsets and weights travel by warp shuffle; each lane gathers its 16 bytes of
+//   every tap with 128-bit loads (a warp-wide load = whole 128-byte lines) and reduces over K in registers
+//   with packed fp32x2 FMAs.  The CTA sweeps downwards, so the lower tap row of one step is the upper
+//   row of the next (L1 hits).
+// Phase B, RGB.  The same threads re-walk the tile one thread per pixel (coalesced planar fp32 reads:
+//   one or two lines per warp-wide load), re-reading the tile's flow / logit lines from L2.  Softmax in
+//   the reference's sequential order, ATen's accumulation order: bit-identical to the generic kernel.
 template <int LPP, int KT, int MINB, bool SKIP>
 __global__ void __launch_bounds__(256, MINB)
 k_warp_fuse_nhwc(const WFArgs a) {
   static_assert(KT <= LPP, "one lane of the pixel group per reference");
-  constexpr int PPW = 32 / LPP;  // pixels per warp
+  constexpr int PPW = 32 / LPP;  // pixel columns per warp
   constexpr int TW = 8 * PPW;    // strip width of the CTA (8 warps)
-  constexpr int NREP = (LPP / KT) < 3 ? (LPP / KT) : 3;  // lanes sharing one reference's RGB planes
-  constexpr int CS = (3 + NREP - 1) / NREP;              // RGB channels per such lane
+  constexpr bool KPOW2 = (KT & (KT - 1)) == 0;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr unsigned PIXB = LPP * 16;  // bytes of one channels-last pixel
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane / LPP;  // pixel group within the warp
-  const int j = lane % LPP;  // lane within the group: owns channels 8j..8j+7
-  const int kk = j % KT;     // the reference whose sample position / weights this lane prepares
-  const int rep = j / KT;    // replica index among the lanes preparing reference kk (RGB work split)
-  const int gl = g * LPP;    // first lane of this pixel group
   int bid = blockIdx.x;
   const int tx = bid % a.tiles_x;
   bid /= a.tiles_x;
   const int ty = bid % a.tiles_y;
   const int b = bid / a.tiles_y;
-  const int x = tx * TW + warp * PPW + g;
-  const bool xin = x < a.W;
   const int y_begin = ty * a.rows_per_cta;
   const int y_end = min(a.H, y_begin + a.rows_per_cta);
-  const size_t HW = (size_t)a.H * a.W;
-  const size_t HWs = (size_t)a.Hs * a.Ws;
-  const size_t r = a.ref_index ? a.ref_index[b] : b;
-  const bool has_rgb = a.rgb != nullptr && a.out_rgb != nullptr;
-  const bool rgb_lane = has_rgb && rep < NREP;
-  const int Ws = a.Ws;
-  // ---- per-CTA 64-bit bases; inside the row loop every address is one IMAD.WIDE on a 32-bit offset
-  const char* fk[KT];  // this lane's 16-byte column of reference k
-#pragma unroll
-  for (int k = 0; k < KT; ++k)
-    fk[k] = reinterpret_cast<const char*>(a.feat) + ((r * KT + k) * HWs) * PIXB + j * 16;
-  const float* rgb_c[CS];  // RGB plane(s) this lane gathers from (reference kk)
-#pragma unroll
-  for (int sl = 0; sl < CS; ++sl) {
-    const int c = min(rep + sl * NREP, 2);
-    rgb_c[sl] = has_rgb ? a.rgb + ((r * KT + kk) * 3 + c) * HWs : nullptr;
-  }
-  const size_t bk0 = ((size_t)b * KT + kk) * HW;
-  const float* __restrict__ p_logit = a.logits ? a.logits + bk0 : nullptr;
-  const float* __restrict__ p_vis = a.vis ? a.vis + bk0 : nullptr;
-  const int* __restrict__ p_fim = (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr;
-  const float2* __restrict__ p_grid = reinterpret_cast<const float2*>(a.grid) + bk0;
-  const float* __restrict__ p_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
-  uint4* __restrict__ p_out = reinterpret_cast<uint4*>(a.out_feat) + (size_t)b * HW * LPP + j;
+  const unsigned W = (unsigned)a.W, Ws = (unsigned)a.Ws;
+  const unsigned HW = (unsigned)a.H * W, HWs = (unsigned)a.Hs * Ws;
+  const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
+  const size_t bK = (size_t)b * KT * HW;
+  // CTA-uniform 64-bit bases + 32-bit per-lane offsets: one IMAD.WIDE per address
+  const float* __restrict__ b_logit = a.logits ? a.logits + bK : nullptr;
+  const float* __restrict__ b_vis = a.vis ? a.vis + bK : nullptr;
+  const int* __restrict__ b_fim = (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr;
+  const float2* __restrict__ b_grid = reinterpret_cast<const float2*>(a.grid) + bK;
+  const float* __restrict__ b_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
 
-  unsigned pix = (unsigned)y_begin * (unsigned)a.W + (unsigned)x;  // in-frame pixel index (< 2^29)
-  for (int y = y_begin; y < y_end; ++y, pix += (unsigned)a.W) {
-    // ---- this lane's reference kk: flow sample, visibility, softmax term
-    float lg = 0.f, v = 1.f;
-    float2 gxy = make_float2(0.f, 0.f);
-    if (xin) {
-      gxy = ld_stream_f32x2(reinterpret_cast<const float*>(p_grid + pix));
-      if (p_logit) lg = ld_stream_f32(p_logit + pix);
-      if (p_vis) v = ld_stream_f32(p_vis + pix);
-      if (p_fim) v = (ld_stream_s32(p_fim + pix) != -1) ? 1.f : 0.f;
-    }
-    // softmax over the group's references: max by butterfly (replica lanes hold copies, so the
-    // full-group max is the max over k), sum in reference order k = 0..K-1
-    float m = lg;
-#pragma unroll
-    for (int s = LPP / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
-    const float e = expf(lg - m);
-    float ssum = 0.f;
-#pragma unroll
-    for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, gl + k);
-    const float aw = xin ? __fdividef(e, ssum) * v : 0.f;  // alpha_k * vis_k
-    HotTap t = make_hot_tap(gxy.x, gxy.y, Ws, a.Hs, a.align_corners);
-    t.nw *= aw;
-    t.ne *= aw;
-    t.sw *= aw;
-    t.se *= aw;
-    const bool act = aw != 0.f;
-    // invisible references still issue their (weight-0) loads, from pixel 0 of the reference: no
-    // divergent branch in the gather loop and no new cache lines
-    const unsigned off = act ? (unsigned)t.off : 0u;
-    // SKIP (chosen by the host when a visibility input exists): warp-uniform early-out when nothing is
-    // visible.  Without a visibility input every pixel is visible and the branch would only get in the
-    // way of the scheduler (measured: -10..20 % on the dense workload).
-    const bool any = SKIP ? (__ballot_sync(FULL, act) != 0u) : true;
+  // =========================== phase A: features ===========================
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPP, j = lane % LPP, gl = g * LPP;
+    const int kk = j % KT;
+    const int x = tx * TW + warp * PPW + g;
+    const bool xin = x < (int)W;
+    const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + j * 16;
+    uint4* __restrict__ o_lane = reinterpret_cast<uint4*>(a.out_feat) + (size_t)b * HW * LPP + j;
+    const unsigned lane_in = (unsigned)kk * HW;  // this lane's (b, kk) plane of flow / logit / vis
 
-    float2 acc[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
-    float rgb_tot[CS];
-#pragma unroll
-    for (int sl = 0; sl < CS; ++sl) rgb_tot[sl] = 0.f;
-
-    if (any) {
-      // RGB: lane (kk, rep) gathers channel(s) rep, rep+NREP of reference kk with its own tap
-      float sv[CS];
-#pragma unroll
-      for (int sl = 0; sl < CS; ++sl) {
-        sv[sl] = 0.f;
-        if (rgb_lane && rep + sl * NREP < 3) {
-          const float* p0 = rgb_c[sl] + off;
-          const float* p1 = rgb_c[sl] + (off + (unsigned)Ws);
-          float q = __ldg(p0) * t.nw;
-          q = fmaf(__ldg(p0 + 1), t.ne, q);
-          q = fmaf(__ldg(p1), t.sw, q);
-          sv[sl] = fmaf(__ldg(p1 + 1), t.se, q);
-        }
+    // flow / logit lines are read again by phase B ~100 us later: ask L2 to keep them (evict_last)
+    const uint64_t keep = l2_policy_evict_last();
+    unsigned pix = (unsigned)y_begin * W + (unsigned)x;
+    for (int y = y_begin; y < y_end; ++y, pix += W) {
+      float lg = 0.f, v = 1.f;
+      float2 gxy = make_float2(0.f, 0.f);
+      if (xin) {
+        gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
+        if (b_logit) lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
+        if (b_vis) v = ld_stream_f32(b_vis + (lane_in + pix));
+        if (b_fim) v = (ld_stream_s32(b_fim + pix) != -1) ? 1.f : 0.f;
       }
-      // features: reference after reference; every lane of the group gets reference k's offset and
-      // weights by shuffle and moves its own 16 bytes of each of the 4 taps
+      // softmax over the group's references (replica lanes j >= KT hold copies of lane j % KT)
+      float m = lg, ssum;
+      if constexpr (KPOW2) {
 #pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        const unsigned ok = __shfl_sync(FULL, off, gl + k);
-        const uint4* p0 = reinterpret_cast<const uint4*>(fk[k] + (size_t)ok * PIXB);
-        const uint4* p1 = reinterpret_cast<const uint4*>(fk[k] + (size_t)(ok + (unsigned)Ws) * PIXB);
-        uint4 q[4];
-        q[0] = ld_gather_u128(p0);
-        q[1] = ld_gather_u128(p0 + LPP);
-        q[2] = ld_gather_u128(p1);
-        q[3] = ld_gather_u128(p1 + LPP);
-        float wt[4];
-        wt[0] = __shfl_sync(FULL, t.nw, gl + k);
-        wt[1] = __shfl_sync(FULL, t.ne, gl + k);
-        wt[2] = __shfl_sync(FULL, t.sw, gl + k);
-        wt[3] = __shfl_sync(FULL, t.se, gl + k);
+        for (int s = KT / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
+      } else {
 #pragma unroll
-        for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
-          const float2 w2 = make_float2(wt[tp], wt[tp]);
-          const uint32_t wd[4] = {q[tp].x, q[tp].y, q[tp].z, q[tp].w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c)  // packed fp32x2 FMA: two channels per instruction
-            acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
-        }
+        for (int k = 0; k < KT; ++k) m = fmaxf(m, __shfl_sync(FULL, lg, gl + k));
       }
-      if (has_rgb) {  // sum over k in reference order
+      const float e = expf(lg - m);
+      if constexpr (KPOW2) {
+        ssum = e;
 #pragma unroll
-        for (int sl = 0; sl < CS; ++sl)
+        for (int s = 1; s < KT; s <<= 1) ssum += __shfl_xor_sync(FULL, ssum, s);
+      } else {
+        ssum = 0.f;
 #pragma unroll
-          for (int k = 0; k < KT; ++k) rgb_tot[sl] += __shfl_sync(FULL, sv[sl], (gl + rep * KT + k) & 31);
+        for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, gl + k);
       }
-    }
+      const float aw = xin ? __fdividef(e, ssum) * v : 0.f;  // alpha_k * vis_k
+      HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
+      t.nw *= aw;
+      t.ne *= aw;
+      t.sw *= aw;
+      t.se *= aw;
+      // invisible references still issue their (weight-0) loads, from pixel 0 of the reference: no
+      // divergent branch in the gather loop and no new cache lines
+      const unsigned off = (aw != 0.f) ? (unsigned)t.off : 0u;
+      // SKIP (host-selected when a visibility input exists): warp-uniform early-out when nothing is visible
+      const bool any = SKIP ? (__ballot_sync(FULL, aw != 0.f) != 0u) : true;
 
-    if (xin) {
-      const float tm = p_mask ? ld_stream_f32(p_mask + pix) : 1.f;
-      uint4 o;
-      o.x = pack_bf16x2(acc[0].x * tm, acc[0].y * tm);
-      o.y = pack_bf16x2(acc[1].x * tm, acc[1].y * tm);
-      o.z = pack_bf16x2(acc[2].x * tm, acc[2].y * tm);
-      o.w = pack_bf16x2(acc[3].x * tm, acc[3].y * tm);
-      st_stream_u128(p_out + (size_t)pix * LPP, o);
-      if (rgb_lane && kk == 0) {
+      float2 acc[4];
 #pragma unroll
-        for (int sl = 0; sl < CS; ++sl) {
-          const int c = rep + sl * NREP;
-          if (c < 3) {
-            float ov = rgb_tot[sl];
-            if (p_mask) ov *= (a.mask_c == 3) ? ld_stream_f32(p_mask + (size_t)c * HW + pix) : tm;
-            if (a.fake && a.conf) {
-              const float wc = ld_stream_f32(a.conf + (size_t)b * HW + pix);
-              const float fkv = ld_stream_f32(a.fake + ((size_t)b * 3 + c) * HW + pix);
-              ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
-            }
-            st_stream_f32(a.out_rgb + ((size_t)b * 3 + c) * HW + pix, ov);
+      for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
+      if (any) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          const unsigned o0 = __shfl_sync(FULL, off, gl + k) + (unsigned)k * HWs;
+          const uint4* p0 = reinterpret_cast<const uint4*>(f_lane + (size_t)o0 * PIXB);
+          const uint4* p1 = reinterpret_cast<const uint4*>(f_lane + (size_t)(o0 + Ws) * PIXB);
+          uint4 q[4];
+          q[0] = ld_gather_u128(p0);
+          q[1] = ld_gather_u128(p0 + LPP);
+          q[2] = ld_gather_u128(p1);
+          q[3] = ld_gather_u128(p1 + LPP);
+          float wt[4];
+          wt[0] = __shfl_sync(FULL, t.nw, gl + k);
+          wt[1] = __shfl_sync(FULL, t.ne, gl + k);
+          wt[2] = __shfl_sync(FULL, t.sw, gl + k);
+          wt[3] = __shfl_sync(FULL, t.se, gl + k);
+#pragma unroll
+          for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+            const float2 w2 = make_float2(wt[tp], wt[tp]);
+            const uint32_t wd[4] = {q[tp].x, q[tp].y, q[tp].z, q[tp].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)  // packed fp32x2 FMA: two channels per instruction
+              acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
           }
         }
+      }
+      if (xin) {
+        const float tm = b_mask ? ld_stream_f32(b_mask + pix) : 1.f;
+        uint4 o;
+        o.x = pack_bf16x2(acc[0].x * tm, acc[0].y * tm);
+        o.y = pack_bf16x2(acc[1].x * tm, acc[1].y * tm);
+        o.z = pack_bf16x2(acc[2].x * tm, acc[2].y * tm);
+        o.w = pack_bf16x2(acc[3].x * tm, acc[3].y * tm);
+        st_stream_u128(o_lane + (size_t)pix * LPP, o);
+      }
+    }
+  }
+
+  // =========================== phase B: RGB ===========================
+  if (a.rgb != nullptr && a.out_rgb != nullptr) {
+    const float* __restrict__ rgb_base = a.rgb + r * KT * 3 * (size_t)HWs;
+    const float* __restrict__ b_fake = (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr;
+    const float* __restrict__ b_conf = (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr;
+    float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
+    const int npx = TW * (y_end - y_begin);
+    for (int p = threadIdx.x; p < npx; p += 256) {
+      const int x = tx * TW + p % TW, y = y_begin + p / TW;
+      if (x >= (int)W) continue;
+      const unsigned pix = (unsigned)y * W + (unsigned)x;
+      // softmax in the reference order: max, exp, running sum, divide
+      float aw[KT];
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        aw[k] = b_logit ? __ldg(b_logit + ((unsigned)k * HW + pix)) : 0.f;
+        m = fmaxf(m, aw[k]);
+      }
+      float ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        aw[k] = expf(aw[k] - m);
+        ssum += aw[k];
+      }
+      const float vf = b_fim ? ((__ldg(b_fim + pix) != -1) ? 1.f : 0.f) : 1.f;
+      float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const float v = b_vis ? __ldg(b_vis + ((unsigned)k * HW + pix)) : vf;
+        const float w = (aw[k] / ssum) * v;
+        if (w != 0.f) {
+          const float2 gxy = __ldg(b_grid + ((unsigned)k * HW + pix));
+          const HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float* p0 = rgb_base + ((unsigned)(k * 3 + c) * HWs + (unsigned)t.off);
+            float s = fmaf(__ldg(p0), t.nw, 0.f);
+            s = fmaf(__ldg(p0 + 1), t.ne, s);
+            s = fmaf(__ldg(p0 + Ws), t.sw, s);
+            s = fmaf(__ldg(p0 + Ws + 1), t.se, s);
+            acc[c] = fmaf(w, s, acc[c]);
+          }
+        }
+      }
+      const float tm = b_mask ? __ldg(b_mask + pix) : 1.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float ov = acc[c];
+        if (b_mask) ov *= (a.mask_c == 3) ? __ldg(b_mask + ((unsigned)c * HW + pix)) : tm;
+        if (b_fake) {
+          const float wc = __ldg(b_conf + pix);
+          const float fkv = __ldg(b_fake + ((unsigned)c * HW + pix));
+          ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+        }
+        st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
       }
     }
   }
