@@ -120,7 +120,7 @@ __device__ __forceinline__ HotTap make_hot_tap(float gx, float gy, int Ws, int H
 // Phase B, RGB.  The same threads re-walk the tile one thread per pixel (coalesced planar fp32 reads:
 //   one or two lines per warp-wide load), re-reading the tile's flow / logit lines from L2.  Softmax in
 //   the reference's sequential order, ATen's accumulation order: bit-identical to the generic kernel.
-template <int LPP, int KT, int MINB, bool SKIP>
+template <int LPP, int KT, int MINB, bool SKIP, int KC = 1>
 __global__ void __launch_bounds__(256, MINB)
 k_warp_fuse_nhwc(const WFArgs a) {
   static_assert(KT <= LPP, "one lane of the pixel group per reference");
@@ -206,27 +206,40 @@ k_warp_fuse_nhwc(const WFArgs a) {
       for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
       if (any) {
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          const unsigned o0 = __shfl_sync(FULL, off, gl + k) + (unsigned)k * HWs;
-          const uint4* p0 = reinterpret_cast<const uint4*>(f_lane + (size_t)o0 * PIXB);
-          const uint4* p1 = reinterpret_cast<const uint4*>(f_lane + (size_t)(o0 + Ws) * PIXB);
-          uint4 q[4];
-          q[0] = ld_gather_u128(p0);
-          q[1] = ld_gather_u128(p0 + LPP);
-          q[2] = ld_gather_u128(p1);
-          q[3] = ld_gather_u128(p1 + LPP);
-          float wt[4];
-          wt[0] = __shfl_sync(FULL, t.nw, gl + k);
-          wt[1] = __shfl_sync(FULL, t.ne, gl + k);
-          wt[2] = __shfl_sync(FULL, t.sw, gl + k);
-          wt[3] = __shfl_sync(FULL, t.se, gl + k);
+        for (int k0 = 0; k0 < KT; k0 += KC) {
+          uint4 q[KC][4];
+          // the KC references of a chunk have their 4*KC gathers in flight together
 #pragma unroll
-          for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
-            const float2 w2 = make_float2(wt[tp], wt[tp]);
-            const uint32_t wd[4] = {q[tp].x, q[tp].y, q[tp].z, q[tp].w};
+          for (int kc = 0; kc < KC; ++kc) {
+            const int k = k0 + kc;
+            if (k < KT) {
+              const unsigned o0 = __shfl_sync(FULL, off, gl + k) + (unsigned)k * HWs;
+              const uint4* p0 = reinterpret_cast<const uint4*>(f_lane + (size_t)o0 * PIXB);
+              const uint4* p1 = reinterpret_cast<const uint4*>(f_lane + (size_t)(o0 + Ws) * PIXB);
+              q[kc][0] = ld_gather_u128(p0);
+              q[kc][1] = ld_gather_u128(p0 + LPP);
+              q[kc][2] = ld_gather_u128(p1);
+              q[kc][3] = ld_gather_u128(p1 + LPP);
+            }
+          }
 #pragma unroll
-            for (int c = 0; c < 4; ++c)  // packed fp32x2 FMA: two channels per instruction
-              acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
+          for (int kc = 0; kc < KC; ++kc) {
+            const int k = k0 + kc;
+            if (k < KT) {
+              float wt[4];
+              wt[0] = __shfl_sync(FULL, t.nw, gl + k);
+              wt[1] = __shfl_sync(FULL, t.ne, gl + k);
+              wt[2] = __shfl_sync(FULL, t.sw, gl + k);
+              wt[3] = __shfl_sync(FULL, t.se, gl + k);
+#pragma unroll
+              for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+                const float2 w2 = make_float2(wt[tp], wt[tp]);
+                const uint32_t wd[4] = {q[kc][tp].x, q[kc][tp].y, q[kc][tp].z, q[kc][tp].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)  // packed fp32x2 FMA: two channels per instruction
+                  acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
+              }
+            }
           }
         }
       }
@@ -273,7 +286,7 @@ k_warp_fuse_nhwc(const WFArgs a) {
       for (int k = 0; k < KT; ++k) {
         const float v = b_vis ? __ldg(b_vis + ((unsigned)k * HW + pix)) : vf;
         const float w = (aw[k] / ssum) * v;
-        if (w != 0.f) {
+        if (!SKIP || w != 0.f) {  // without a visibility input nothing is skipped: no branch, loads of all k overlap
           const float2 gxy = __ldg(b_grid + ((unsigned)k * HW + pix));
           const HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
 #pragma unroll
@@ -415,12 +428,17 @@ k_warp_fuse_generic(const WFArgs a) {
   }
 }
 
+int wf_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 // resident CTAs per SM the kernel is compiled for (register cap = 65536 / (256 * MINB)); tunable
 int wf_minb() {
   static int mb = [] {
     const char* e = getenv("JAF_WF_MINB");
-    const int v = e ? atoi(e) : 5;
-    return (v >= 3 && v <= 6) ? v : 5;
+    const int v = e ? atoi(e) : 6;
+    return (v >= 3 && v <= 6) ? v : 6;
   }();
   return mb;
 }
@@ -431,12 +449,13 @@ bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
     const bool skip = a.vis != nullptr || a.fim != nullptr;
     if constexpr (LPP == 8 && KV == 4) {  // the headline shape carries the occupancy variants
       const int mb = wf_minb();
-#define JAF_V(MB) if (mb == MB) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false><<<grid, 256, 0, st>>>(a); return true; }
-      JAF_V(3) JAF_V(4) JAF_V(5) JAF_V(6)
+      static const int kc = wf_env("JAF_WF_KC", 1);
+#define JAF_V(MB, C) if (mb == MB && kc == C) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true, C><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, C><<<grid, 256, 0, st>>>(a); return true; }
+      JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1) JAF_V(4, 2) JAF_V(5, 2) JAF_V(6, 2) JAF_V(4, 4) JAF_V(5, 4)
 #undef JAF_V
     }
-    if (skip) k_warp_fuse_nhwc<LPP, KV, 5, true><<<grid, 256, 0, st>>>(a);
-    else k_warp_fuse_nhwc<LPP, KV, 5, false><<<grid, 256, 0, st>>>(a);
+    if (skip) k_warp_fuse_nhwc<LPP, KV, 6, true><<<grid, 256, 0, st>>>(a);
+    else k_warp_fuse_nhwc<LPP, KV, 6, false><<<grid, 256, 0, st>>>(a);
     return true;
   } else {
     return false;
@@ -466,7 +485,8 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
   const int ppw = 32 / lpp;
   const int tw = 8 * ppw;
   a.tiles_x = (a.W + tw - 1) / tw;
-  a.rows_per_cta = a.H < 32 ? a.H : 32;
+  static const int rows_env = wf_env("JAF_WF_ROWS_PER_CTA", 16);
+  a.rows_per_cta = a.H < rows_env ? a.H : rows_env;
   a.tiles_y = (a.H + a.rows_per_cta - 1) / a.rows_per_cta;
   const long grid = (long)a.tiles_x * a.tiles_y * a.B;
   if (grid > 0x7fffffffL) return false;
