@@ -169,6 +169,7 @@ k_warp_fuse_nhwc(const WFArgs a) {
         if (b_logit) lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
         if (b_vis) v = ld_stream_f32(b_vis + (lane_in + pix));
         if (b_fim) v = (ld_stream_s32(b_fim + pix) != -1) ? 1.f : 0.f;
+        if (b_mask) v *= ld_stream_f32(b_mask + pix);  // fused * tgt_mask == sum_k (alpha_k vis_k mask) warped_k
       }
       // softmax over the group's references (replica lanes j >= KT hold copies of lane j % KT)
       float m = lg, ssum;
@@ -244,12 +245,11 @@ k_warp_fuse_nhwc(const WFArgs a) {
         }
       }
       if (xin) {
-        const float tm = b_mask ? ld_stream_f32(b_mask + pix) : 1.f;
         uint4 o;
-        o.x = pack_bf16x2(acc[0].x * tm, acc[0].y * tm);
-        o.y = pack_bf16x2(acc[1].x * tm, acc[1].y * tm);
-        o.z = pack_bf16x2(acc[2].x * tm, acc[2].y * tm);
-        o.w = pack_bf16x2(acc[3].x * tm, acc[3].y * tm);
+        o.x = pack_bf16x2(acc[0].x, acc[0].y);
+        o.y = pack_bf16x2(acc[1].x, acc[1].y);
+        o.z = pack_bf16x2(acc[2].x, acc[2].y);
+        o.w = pack_bf16x2(acc[3].x, acc[3].y);
         st_stream_u128(o_lane + (size_t)pix * LPP, o);
       }
     }
@@ -289,13 +289,15 @@ k_warp_fuse_nhwc(const WFArgs a) {
         if (!SKIP || w != 0.f) {  // without a visibility input nothing is skipped: no branch, loads of all k overlap
           const float2 gxy = __ldg(b_grid + ((unsigned)k * HW + pix));
           const HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
+          const unsigned ok = (unsigned)(k * 3) * HWs + (unsigned)t.off;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float* p0 = rgb_base + ((unsigned)(k * 3 + c) * HWs + (unsigned)t.off);
+            const float* p0 = rgb_base + (ok + (unsigned)c * HWs);
+            const float* p1 = rgb_base + (ok + (unsigned)c * HWs + Ws);
             float s = fmaf(__ldg(p0), t.nw, 0.f);
             s = fmaf(__ldg(p0 + 1), t.ne, s);
-            s = fmaf(__ldg(p0 + Ws), t.sw, s);
-            s = fmaf(__ldg(p0 + Ws + 1), t.se, s);
+            s = fmaf(__ldg(p1), t.sw, s);
+            s = fmaf(__ldg(p1 + 1), t.se, s);
             acc[c] = fmaf(w, s, acc[c]);
           }
         }
