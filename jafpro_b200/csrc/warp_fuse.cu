@@ -109,6 +109,65 @@ __device__ __forceinline__ HotTap make_hot_tap(float gx, float gy, int Ws, int H
   return t;
 }
 
+// One output pixel of the RGB planes (planar fp32, the reference layout): softmax in the reference's
+// sequential order, ATen's tap order, acc += w_k * warped_k — bit-identical to k_warp_fuse_generic.
+template <int KT, bool SKIP>
+__device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restrict__ rgb_base,
+                                          const float2* __restrict__ b_grid, const float* __restrict__ b_logit,
+                                          const float* __restrict__ b_vis, const int* __restrict__ b_fim,
+                                          const float* __restrict__ b_mask, const float* __restrict__ b_fake,
+                                          const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
+                                          unsigned HW, unsigned HWs, unsigned Ws) {
+  // softmax in the reference order: max, exp, running sum, divide
+  float aw[KT];
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    aw[k] = b_logit ? __ldg(b_logit + ((unsigned)k * HW + pix)) : 0.f;
+    m = fmaxf(m, aw[k]);
+  }
+  float ssum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    aw[k] = expf(aw[k] - m);
+    ssum += aw[k];
+  }
+  const float vf = b_fim ? ((__ldg(b_fim + pix) != -1) ? 1.f : 0.f) : 1.f;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    const float v = b_vis ? __ldg(b_vis + ((unsigned)k * HW + pix)) : vf;
+    const float w = (aw[k] / ssum) * v;
+    if (!SKIP || w != 0.f) {  // without a visibility input nothing is skipped: no branch, loads of all k overlap
+      const float2 gxy = __ldg(b_grid + ((unsigned)k * HW + pix));
+      const HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
+      const unsigned ok = (unsigned)(k * 3) * HWs + (unsigned)t.off;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* p0 = rgb_base + (ok + (unsigned)c * HWs);
+        const float* p1 = rgb_base + (ok + (unsigned)c * HWs + Ws);
+        float s = fmaf(__ldg(p0), t.nw, 0.f);
+        s = fmaf(__ldg(p0 + 1), t.ne, s);
+        s = fmaf(__ldg(p1), t.sw, s);
+        s = fmaf(__ldg(p1 + 1), t.se, s);
+        acc[c] = fmaf(w, s, acc[c]);
+      }
+    }
+  }
+  const float tm = b_mask ? __ldg(b_mask + pix) : 1.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float ov = acc[c];
+    if (b_mask) ov *= (a.mask_c == 3) ? __ldg(b_mask + ((unsigned)c * HW + pix)) : tm;
+    if (b_fake) {
+      const float wc = __ldg(b_conf + pix);
+      const float fkv = __ldg(b_fake + ((unsigned)c * HW + pix));
+      ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+    }
+    st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
+  }
+}
+
 // Two phases per CTA tile (a strip of TW = 8 * 32/LPP pixel columns x rows_per_cta rows):
 //
 // Phase A, features.  A group of LPP = C/8 lanes owns one pixel column; lane j owns channels 8j..8j+7 and
@@ -120,7 +179,7 @@ __device__ __forceinline__ HotTap make_hot_tap(float gx, float gy, int Ws, int H
 // Phase B, RGB.  The same threads re-walk the tile one thread per pixel (coalesced planar fp32 reads:
 //   one or two lines per warp-wide load), re-reading the tile's flow / logit lines from L2.  Softmax in
 //   the reference's sequential order, ATen's accumulation order: bit-identical to the generic kernel.
-template <int LPP, int KT, int MINB, bool SKIP, int KC = 1>
+template <int LPP, int KT, int MINB, bool SKIP, int KC = 1, bool PREFETCH = false>
 __global__ void __launch_bounds__(256, MINB)
 k_warp_fuse_nhwc(const WFArgs a) {
   static_assert(KT <= LPP, "one lane of the pixel group per reference");
@@ -161,10 +220,32 @@ k_warp_fuse_nhwc(const WFArgs a) {
     // flow / logit lines are read again by phase B ~100 us later: ask L2 to keep them (evict_last)
     const uint64_t keep = l2_policy_evict_last();
     unsigned pix = (unsigned)y_begin * W + (unsigned)x;
+    // raw inputs of the NEXT row are fetched one iteration ahead (flow, logit, mask: the always-hot ones)
+    float2 n_g = make_float2(0.f, 0.f);
+    float n_lg = 0.f, n_m = 1.f;
+    if (PREFETCH && xin) {
+      n_g = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
+      if (b_logit) n_lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
+      if (b_mask) n_m = ld_stream_f32(b_mask + pix);
+    }
+#pragma unroll 1
     for (int y = y_begin; y < y_end; ++y, pix += W) {
       float lg = 0.f, v = 1.f;
       float2 gxy = make_float2(0.f, 0.f);
-      if (xin) {
+      if (PREFETCH) {
+        gxy = n_g;
+        lg = n_lg;
+        v = n_m;
+        if (xin && y + 1 < y_end) {
+          n_g = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix + W)), keep);
+          if (b_logit) n_lg = ld_stream_keep_f32(b_logit + (lane_in + pix + W), keep);
+          if (b_mask) n_m = ld_stream_f32(b_mask + pix + W);
+        }
+        if (xin) {
+          if (b_vis) v *= ld_stream_f32(b_vis + (lane_in + pix));
+          if (b_fim) v *= (ld_stream_s32(b_fim + pix) != -1) ? 1.f : 0.f;
+        }
+      } else if (xin) {
         gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
         if (b_logit) lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
         if (b_vis) v = ld_stream_f32(b_vis + (lane_in + pix));
@@ -265,57 +346,53 @@ k_warp_fuse_nhwc(const WFArgs a) {
     for (int p = threadIdx.x; p < npx; p += 256) {
       const int x = tx * TW + p % TW, y = y_begin + p / TW;
       if (x >= (int)W) continue;
-      const unsigned pix = (unsigned)y * W + (unsigned)x;
-      // softmax in the reference order: max, exp, running sum, divide
-      float aw[KT];
-      float m = -CUDART_INF_F;
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        aw[k] = b_logit ? __ldg(b_logit + ((unsigned)k * HW + pix)) : 0.f;
-        m = fmaxf(m, aw[k]);
-      }
-      float ssum = 0.f;
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        aw[k] = expf(aw[k] - m);
-        ssum += aw[k];
-      }
-      const float vf = b_fim ? ((__ldg(b_fim + pix) != -1) ? 1.f : 0.f) : 1.f;
-      float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        const float v = b_vis ? __ldg(b_vis + ((unsigned)k * HW + pix)) : vf;
-        const float w = (aw[k] / ssum) * v;
-        if (!SKIP || w != 0.f) {  // without a visibility input nothing is skipped: no branch, loads of all k overlap
-          const float2 gxy = __ldg(b_grid + ((unsigned)k * HW + pix));
-          const HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
-          const unsigned ok = (unsigned)(k * 3) * HWs + (unsigned)t.off;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float* p0 = rgb_base + (ok + (unsigned)c * HWs);
-            const float* p1 = rgb_base + (ok + (unsigned)c * HWs + Ws);
-            float s = fmaf(__ldg(p0), t.nw, 0.f);
-            s = fmaf(__ldg(p0 + 1), t.ne, s);
-            s = fmaf(__ldg(p1), t.sw, s);
-            s = fmaf(__ldg(p1 + 1), t.se, s);
-            acc[c] = fmaf(w, s, acc[c]);
-          }
-        }
-      }
-      const float tm = b_mask ? __ldg(b_mask + pix) : 1.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float ov = acc[c];
-        if (b_mask) ov *= (a.mask_c == 3) ? __ldg(b_mask + ((unsigned)c * HW + pix)) : tm;
-        if (b_fake) {
-          const float wc = __ldg(b_conf + pix);
-          const float fkv = __ldg(b_fake + ((unsigned)c * HW + pix));
-          ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
-        }
-        st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
-      }
+      rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
     }
   }
+}
+
+// RGB-only calls (no feature tensor): one thread per pixel, the same per-pixel code as phase B
+template <int KT, bool SKIP>
+__global__ void __launch_bounds__(256)
+k_warp_fuse_rgb(const WFArgs a) {
+  const unsigned W = (unsigned)a.W, Ws = (unsigned)a.Ws;
+  const unsigned HW = (unsigned)a.H * W, HWs = (unsigned)a.Hs * Ws;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)a.B * HW) return;
+  const int b = (int)(i / HW);
+  const unsigned pix = (unsigned)(i % HW);
+  const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
+  const size_t bK = (size_t)b * KT * HW;
+  rgb_pixel<KT, SKIP>(a, a.rgb + r * KT * 3 * (size_t)HWs, reinterpret_cast<const float2*>(a.grid) + bK,
+                      a.logits ? a.logits + bK : nullptr, a.vis ? a.vis + bK : nullptr,
+                      (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr,
+                      a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr,
+                      (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr,
+                      (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr, a.out_rgb + (size_t)b * 3 * HW, pix, HW,
+                      HWs, Ws);
+}
+
+template <int KT>
+void launch_rgb_k(const WFArgs& a, int grid, cudaStream_t st) {
+  if (a.vis != nullptr || a.fim != nullptr) k_warp_fuse_rgb<KT, true><<<grid, 256, 0, st>>>(a);
+  else k_warp_fuse_rgb<KT, false><<<grid, 256, 0, st>>>(a);
+}
+
+bool launch_rgb(const WFArgs& a, cudaStream_t st) {
+  if (a.K > 8 || a.Ws < 2 || a.Hs < 2 || (long)a.H * a.W >= (1L << 29) || a.warped_rgb != nullptr || !a.out_rgb) return false;
+  const int grid = jaf::ceil_div((long)a.B * a.H * a.W, 256);
+  switch (a.K) {
+    case 1: launch_rgb_k<1>(a, grid, st); break;
+    case 2: launch_rgb_k<2>(a, grid, st); break;
+    case 3: launch_rgb_k<3>(a, grid, st); break;
+    case 4: launch_rgb_k<4>(a, grid, st); break;
+    case 5: launch_rgb_k<5>(a, grid, st); break;
+    case 6: launch_rgb_k<6>(a, grid, st); break;
+    case 7: launch_rgb_k<7>(a, grid, st); break;
+    case 8: launch_rgb_k<8>(a, grid, st); break;
+    default: return false;
+  }
+  return true;
 }
 
 // =====================================================================================
@@ -451,9 +528,9 @@ bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
     const bool skip = a.vis != nullptr || a.fim != nullptr;
     if constexpr (LPP == 8 && KV == 4) {  // the headline shape carries the occupancy variants
       const int mb = wf_minb();
-      static const int kc = wf_env("JAF_WF_KC", 1);
-#define JAF_V(MB, C) if (mb == MB && kc == C) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true, C><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, C><<<grid, 256, 0, st>>>(a); return true; }
-      JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1) JAF_V(4, 2) JAF_V(5, 2) JAF_V(6, 2) JAF_V(4, 4) JAF_V(5, 4)
+      static const int pf = wf_env("JAF_WF_PREFETCH", 0);
+#define JAF_V(MB, P) if (mb == MB && pf == P) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true, 1, (P != 0)><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, 1, (P != 0)><<<grid, 256, 0, st>>>(a); return true; }
+      JAF_V(4, 0) JAF_V(5, 0) JAF_V(6, 0) JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1)
 #undef JAF_V
     }
     if (skip) k_warp_fuse_nhwc<LPP, KV, 6, true><<<grid, 256, 0, st>>>(a);
@@ -549,7 +626,7 @@ extern "C" int jaf_warp_fuse(const JafWarpFuseParams* p) {
   const int grid = jaf::ceil_div(npix, 256);
   if (!rgb_done || !feat_done) JAF_REQUIRE(p->K <= kMaxKGeneric, "K > 16 is not supported by the generic kernel");
   if (!rgb_done) {
-    k_warp_fuse_generic<float, false, true><<<grid, 256, 0, st>>>(a);
+    if (!launch_rgb(a, st)) k_warp_fuse_generic<float, false, true><<<grid, 256, 0, st>>>(a);
     ++launches;
   }
   if (!feat_done) {
@@ -576,9 +653,15 @@ extern "C" int jaf_warp_image(const float* src, const float* grid, int N, int C,
   p.align_corners = align_corners;
   p.feat_layout = JAF_LAYOUT_PLANAR;
   p.feat_dtype = JAF_DTYPE_F32;
-  p.feat = src;
   p.grid = grid;
-  p.out_feat = out;
+  if (C == 3) {  // an RGB frame (src/cal_flow.py:37-39): the templated per-pixel RGB kernel
+    p.C = 0;
+    p.rgb = src;
+    p.out_rgb = out;
+  } else {
+    p.feat = src;
+    p.out_feat = out;
+  }
   p.stream = stream;
   return jaf_warp_fuse(&p);
 }
