@@ -179,10 +179,13 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
 // Phase B, RGB.  The same threads re-walk the tile one thread per pixel (coalesced planar fp32 reads:
 //   one or two lines per warp-wide load), re-reading the tile's flow / logit lines from L2.  Softmax in
 //   the reference's sequential order, ATen's accumulation order: bit-identical to the generic kernel.
-template <int LPP, int KT, int MINB, bool SKIP, int KC = 1, bool PREFETCH = false>
+template <int LPP, int KT, int MINB, bool SKIP, int ROWS_REQ = 1>
 __global__ void __launch_bounds__(256, MINB)
 k_warp_fuse_nhwc(const WFArgs a) {
   static_assert(KT <= LPP, "one lane of the pixel group per reference");
+  // ROWS = 2: the group's spare lanes prepare the NEXT row as well, so one pass of sample-position /
+  // softmax arithmetic serves two output rows
+  constexpr int ROWS = (ROWS_REQ >= 2 && LPP >= 2 * KT) ? 2 : 1;
   constexpr int PPW = 32 / LPP;  // pixel columns per warp
   constexpr int TW = 8 * PPW;    // strip width of the CTA (8 warps)
   constexpr bool KPOW2 = (KT & (KT - 1)) == 0;
@@ -211,55 +214,38 @@ k_warp_fuse_nhwc(const WFArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LPP, j = lane % LPP, gl = g * LPP;
     const int kk = j % KT;
+    const int rr = (ROWS == 2) ? min(j / KT, 1) : 0;  // row slot this lane prepares (surplus lanes replicate)
     const int x = tx * TW + warp * PPW + g;
     const bool xin = x < (int)W;
     const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + j * 16;
     uint4* __restrict__ o_lane = reinterpret_cast<uint4*>(a.out_feat) + (size_t)b * HW * LPP + j;
-    const unsigned lane_in = (unsigned)kk * HW;  // this lane's (b, kk) plane of flow / logit / vis
+    const unsigned lane_in = (unsigned)kk * HW + (unsigned)rr * W;  // this lane's (b, kk) plane, row slot rr
 
     // flow / logit lines are read again by phase B ~100 us later: ask L2 to keep them (evict_last)
     const uint64_t keep = l2_policy_evict_last();
     unsigned pix = (unsigned)y_begin * W + (unsigned)x;
-    // raw inputs of the NEXT row are fetched one iteration ahead (flow, logit, mask: the always-hot ones)
-    float2 n_g = make_float2(0.f, 0.f);
-    float n_lg = 0.f, n_m = 1.f;
-    if (PREFETCH && xin) {
-      n_g = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
-      if (b_logit) n_lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
-      if (b_mask) n_m = ld_stream_f32(b_mask + pix);
-    }
 #pragma unroll 1
-    for (int y = y_begin; y < y_end; ++y, pix += W) {
+    for (int y = y_begin; y < y_end; y += ROWS, pix += ROWS * W) {
+      // ---- prepare: (row slot rr, reference kk)
+      const bool pin = xin && (y + rr < y_end);
       float lg = 0.f, v = 1.f;
       float2 gxy = make_float2(0.f, 0.f);
-      if (PREFETCH) {
-        gxy = n_g;
-        lg = n_lg;
-        v = n_m;
-        if (xin && y + 1 < y_end) {
-          n_g = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix + W)), keep);
-          if (b_logit) n_lg = ld_stream_keep_f32(b_logit + (lane_in + pix + W), keep);
-          if (b_mask) n_m = ld_stream_f32(b_mask + pix + W);
-        }
-        if (xin) {
-          if (b_vis) v *= ld_stream_f32(b_vis + (lane_in + pix));
-          if (b_fim) v *= (ld_stream_s32(b_fim + pix) != -1) ? 1.f : 0.f;
-        }
-      } else if (xin) {
+      if (pin) {
         gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
         if (b_logit) lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
         if (b_vis) v = ld_stream_f32(b_vis + (lane_in + pix));
-        if (b_fim) v = (ld_stream_s32(b_fim + pix) != -1) ? 1.f : 0.f;
-        if (b_mask) v *= ld_stream_f32(b_mask + pix);  // fused * tgt_mask == sum_k (alpha_k vis_k mask) warped_k
+        if (b_fim) v = (ld_stream_s32(b_fim + (pix + (unsigned)rr * W)) != -1) ? 1.f : 0.f;
+        if (b_mask) v *= ld_stream_f32(b_mask + (pix + (unsigned)rr * W));  // fused*mask == sum_k (alpha_k vis_k mask) warped_k
       }
-      // softmax over the group's references (replica lanes j >= KT hold copies of lane j % KT)
+      // softmax over the KT lanes of this row slot (they are an aligned block when KT is a power of two)
+      const int kb = gl + rr * KT;
       float m = lg, ssum;
       if constexpr (KPOW2) {
 #pragma unroll
         for (int s = KT / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
       } else {
 #pragma unroll
-        for (int k = 0; k < KT; ++k) m = fmaxf(m, __shfl_sync(FULL, lg, gl + k));
+        for (int k = 0; k < KT; ++k) m = fmaxf(m, __shfl_sync(FULL, lg, (kb + k) & 31));
       }
       const float e = expf(lg - m);
       if constexpr (KPOW2) {
@@ -269,9 +255,9 @@ k_warp_fuse_nhwc(const WFArgs a) {
       } else {
         ssum = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, gl + k);
+        for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, (kb + k) & 31);
       }
-      const float aw = xin ? __fdividef(e, ssum) * v : 0.f;  // alpha_k * vis_k
+      const float aw = pin ? __fdividef(e, ssum) * v : 0.f;  // alpha_k * vis_k * mask
       HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
       t.nw *= aw;
       t.ne *= aw;
@@ -283,55 +269,47 @@ k_warp_fuse_nhwc(const WFArgs a) {
       // SKIP (host-selected when a visibility input exists): warp-uniform early-out when nothing is visible
       const bool any = SKIP ? (__ballot_sync(FULL, aw != 0.f) != 0u) : true;
 
-      float2 acc[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
-      if (any) {
+      for (int rs = 0; rs < ROWS; ++rs) {
+        if (ROWS == 2 && rs == 1 && y + 1 >= y_end) break;  // uniform
+        float2 acc[4];
 #pragma unroll
-        for (int k0 = 0; k0 < KT; k0 += KC) {
-          uint4 q[KC][4];
-          // the KC references of a chunk have their 4*KC gathers in flight together
+        for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
+        if (any) {
 #pragma unroll
-          for (int kc = 0; kc < KC; ++kc) {
-            const int k = k0 + kc;
-            if (k < KT) {
-              const unsigned o0 = __shfl_sync(FULL, off, gl + k) + (unsigned)k * HWs;
-              const uint4* p0 = reinterpret_cast<const uint4*>(f_lane + (size_t)o0 * PIXB);
-              const uint4* p1 = reinterpret_cast<const uint4*>(f_lane + (size_t)(o0 + Ws) * PIXB);
-              q[kc][0] = ld_gather_u128(p0);
-              q[kc][1] = ld_gather_u128(p0 + LPP);
-              q[kc][2] = ld_gather_u128(p1);
-              q[kc][3] = ld_gather_u128(p1 + LPP);
-            }
-          }
+          for (int k = 0; k < KT; ++k) {
+            const int src = gl + rs * KT + k;
+            const unsigned o0 = __shfl_sync(FULL, off, src) + (unsigned)k * HWs;
+            const uint4* p0 = reinterpret_cast<const uint4*>(f_lane + (size_t)o0 * PIXB);
+            const uint4* p1 = reinterpret_cast<const uint4*>(f_lane + (size_t)(o0 + Ws) * PIXB);
+            uint4 q[4];
+            q[0] = ld_gather_u128(p0);
+            q[1] = ld_gather_u128(p0 + LPP);
+            q[2] = ld_gather_u128(p1);
+            q[3] = ld_gather_u128(p1 + LPP);
+            float wt[4];
+            wt[0] = __shfl_sync(FULL, t.nw, src);
+            wt[1] = __shfl_sync(FULL, t.ne, src);
+            wt[2] = __shfl_sync(FULL, t.sw, src);
+            wt[3] = __shfl_sync(FULL, t.se, src);
 #pragma unroll
-          for (int kc = 0; kc < KC; ++kc) {
-            const int k = k0 + kc;
-            if (k < KT) {
-              float wt[4];
-              wt[0] = __shfl_sync(FULL, t.nw, gl + k);
-              wt[1] = __shfl_sync(FULL, t.ne, gl + k);
-              wt[2] = __shfl_sync(FULL, t.sw, gl + k);
-              wt[3] = __shfl_sync(FULL, t.se, gl + k);
+            for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+              const float2 w2 = make_float2(wt[tp], wt[tp]);
+              const uint32_t wd[4] = {q[tp].x, q[tp].y, q[tp].z, q[tp].w};
 #pragma unroll
-              for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
-                const float2 w2 = make_float2(wt[tp], wt[tp]);
-                const uint32_t wd[4] = {q[kc][tp].x, q[kc][tp].y, q[kc][tp].z, q[kc][tp].w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c)  // packed fp32x2 FMA: two channels per instruction
-                  acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
-              }
+              for (int c = 0; c < 4; ++c)  // packed fp32x2 FMA: two channels per instruction
+                acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
             }
           }
         }
-      }
-      if (xin) {
-        uint4 o;
-        o.x = pack_bf16x2(acc[0].x, acc[0].y);
-        o.y = pack_bf16x2(acc[1].x, acc[1].y);
-        o.z = pack_bf16x2(acc[2].x, acc[2].y);
-        o.w = pack_bf16x2(acc[3].x, acc[3].y);
-        st_stream_u128(o_lane + (size_t)pix * LPP, o);
+        if (xin) {
+          uint4 o;
+          o.x = pack_bf16x2(acc[0].x, acc[0].y);
+          o.y = pack_bf16x2(acc[1].x, acc[1].y);
+          o.z = pack_bf16x2(acc[2].x, acc[2].y);
+          o.w = pack_bf16x2(acc[3].x, acc[3].y);
+          st_stream_u128(o_lane + (size_t)(pix + (unsigned)rs * W) * LPP, o);
+        }
       }
     }
   }
@@ -515,9 +493,8 @@ int wf_env(const char* name, int dflt) {
 // resident CTAs per SM the kernel is compiled for (register cap = 65536 / (256 * MINB)); tunable
 int wf_minb() {
   static int mb = [] {
-    const char* e = getenv("JAF_WF_MINB");
-    const int v = e ? atoi(e) : 6;
-    return (v >= 3 && v <= 6) ? v : 6;
+    const int v = wf_env("JAF_WF_MINB", 5);
+    return (v >= 4 && v <= 6) ? v : 5;
   }();
   return mb;
 }
@@ -528,9 +505,9 @@ bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
     const bool skip = a.vis != nullptr || a.fim != nullptr;
     if constexpr (LPP == 8 && KV == 4) {  // the headline shape carries the occupancy variants
       const int mb = wf_minb();
-      static const int pf = wf_env("JAF_WF_PREFETCH", 0);
-#define JAF_V(MB, P) if (mb == MB && pf == P) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true, 1, (P != 0)><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, 1, (P != 0)><<<grid, 256, 0, st>>>(a); return true; }
-      JAF_V(4, 0) JAF_V(5, 0) JAF_V(6, 0) JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1)
+      static const int rows = wf_env("JAF_WF_ROWS", 2);
+#define JAF_V(MB, R) if (mb == MB && rows == R) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true, R><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, R><<<grid, 256, 0, st>>>(a); return true; }
+      JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1) JAF_V(4, 2) JAF_V(5, 2) JAF_V(6, 2)
 #undef JAF_V
     }
     if (skip) k_warp_fuse_nhwc<LPP, KV, 6, true><<<grid, 256, 0, st>>>(a);
