@@ -204,6 +204,18 @@ int jaf_convlstm_step_tc(const void* x, const void* h, const float* c, const voi
                          const float* bias, int B, int Cin, int Ch, int H, int W, void* h_out,
                          float* c_out, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * SURVEY §8f rank 1  IUV texture lookup
+ * replaces: texture_warp_pytorch (test/conv_pro_test.py:41-74; train/4.convLSTM_flowpro_interval.py:43-76):
+ *           24 x (torch.where x2, grid build, F.grid_sample of one part texture with zero padding,
+ *           torch.where) per target frame -> one pass.
+ * tex_parts [P,3,Ht,Wt] f32 (P = 24 body-part textures); iuv [B,H,W,3] uint8 (part index, U, V);
+ * out [B,3,H,W]: bilinear sample of part iuv[...,0]-1 at x = ((255-V)/255 - .5)*2, y = (U/255 - .5)*2,
+ * 0 where the part index is 0 or > P.
+ * --------------------------------------------------------------------------------- */
+int jaf_texture_warp(const float* tex_parts, int P, int Ht, int Wt, const uint8_t* iuv, int B, int H, int W,
+                     int align_corners, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

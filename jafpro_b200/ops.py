@@ -42,6 +42,26 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _on:
+    """Device guard that costs nothing when the tensor already lives on the current device."""
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        idx = self.dev.index if self.dev.index is not None else cur
+        self.prev = cur if idx != cur else -1
+        if self.prev >= 0:
+            torch.cuda.set_device(idx)
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _workspace(dev, nbytes):
     """Grow-only scratch per device (z-buffer keys).  Stream-ordered use only."""
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
@@ -60,7 +80,7 @@ def project_gather(cam, vertices, faces_idx, eye_z: float = EYE_Z):
     B, V, _ = vertices.shape
     F = faces_idx.shape[-2]
     out = torch.empty((B, F, 3, 3), dtype=torch.float32, device=vertices.device)
-    with torch.cuda.device(vertices.device):
+    with _on(vertices.device):
         _lib.check(_lib.lib().jaf_project_gather(_ptr(cam), _ptr(vertices), _ptr(faces_idx), B, V, F, eye_z,
                                                  _ptr(out), _stream()), "project_gather")
     return out
@@ -78,7 +98,7 @@ def raster_fim_wim(faces, image_size: int, near: float = DEFAULT_NEAR, far: floa
     fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=dev)
     wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev)
     depth = torch.empty((B, image_size, image_size), dtype=torch.float32, device=dev) if return_depth else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, image_size))
         _lib.check(_lib.lib().jaf_raster_fim_wim(_ptr(faces), B, F, image_size, near, far, int(flip_rows), _ptr(fim),
                                                  _ptr(wim), _ptr(depth), _ptr(ws), _stream()), "raster_fim_wim")
@@ -97,7 +117,7 @@ def render_fim_wim(cam, vertices, faces_idx, image_size: int, eye_z: float = EYE
     faces = torch.empty((B, F, 3, 3), dtype=torch.float32, device=dev) if return_faces else None
     fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=dev)
     wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, image_size))
         _lib.check(_lib.lib().jaf_render_fim_wim(_ptr(cam), _ptr(vertices), _ptr(faces_idx), B, V, F, image_size,
                                                  eye_z, near, far, _ptr(faces), _ptr(fim), _ptr(wim), _ptr(ws),
@@ -113,7 +133,7 @@ def flow_compose(src_f2pts, dst_fims, dst_wims, negate_y: bool = False):
     B, F = src.shape[:2]
     H, W = fim.shape[1:]
     T = torch.empty((B, H, W, 2), dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         _lib.check(_lib.lib().jaf_flow_compose(_ptr(src), src.shape[3], int(negate_y), _ptr(fim), _ptr(wim), B, F, H,
                                                W, _ptr(T), _stream()), "flow_compose")
     return T
@@ -132,7 +152,7 @@ def cal_flow(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx, image_size
     T = torch.empty((B, image_size, image_size, 2), dtype=torch.float32, device=dev)
     fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=dev) if return_maps else None
     wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev) if return_maps else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, image_size))
         _lib.check(_lib.lib().jaf_cal_flow(_ptr(sc), _ptr(sv), _ptr(tc), _ptr(tv), _ptr(faces_idx), B, V, F,
                                            image_size, eye_z, near, far, _ptr(T), _ptr(fim), _ptr(wim), _ptr(ws),
@@ -227,7 +247,7 @@ def warp_fuse(grid, rgb=None, feat=None, *, logits=None, vis=None, fim=None, tgt
         for t in (rgb, feat):
             if t is not None and t.shape[0] != B:
                 raise RuntimeError("without ref_index the reference tensors need one set per target frame")
-    with torch.cuda.device(dev):
+    with _on(dev):
         q.stream = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.lib().jaf_warp_fuse(C.byref(q)), "warp_fuse")
     if return_warped:
@@ -287,7 +307,7 @@ def grid_sample_border(src, grid, align_corners: bool = False):
         N, Cc, Hs, Ws = src.shape
         H, W = grid.shape[1:3]
         out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=src.device)
-        with torch.cuda.device(src.device):
+        with _on(src.device):
             _lib.check(_lib.lib().jaf_warp_image(_ptr(src), _ptr(grid), N, Cc, Hs, Ws, H, W, int(bool(align_corners)),
                                                  _ptr(out), _stream()), "warp_image")
         return out
@@ -305,7 +325,7 @@ def mask_blend(tsf_image, tgt_smpl_mask=None, fake_tgt=None, weight=None):
     masked = torch.empty_like(tsf)
     pred = torch.empty_like(tsf) if w is not None else None
     mc = 1 if mask is None else mask.shape[1]
-    with torch.cuda.device(tsf.device):
+    with _on(tsf.device):
         _lib.check(_lib.lib().jaf_mask_blend(_ptr(fake), _ptr(tsf), _ptr(mask), mc, _ptr(w), B, Cc, H, W,
                                              _ptr(masked), _ptr(pred), _stream()), "mask_blend")
     return masked, pred
@@ -321,7 +341,7 @@ def softmax_fuse(feat_cat, logits):
     if KC % K != 0:
         raise RuntimeError("feat_cat channels must be K*C")
     out = torch.empty((B, KC // K, H, W), dtype=torch.float32, device=feat.device)
-    with torch.cuda.device(feat.device):
+    with _on(feat.device):
         _lib.check(_lib.lib().jaf_softmax_fuse(_ptr(feat), _ptr(logits), B, K, KC // K, H, W, _ptr(out), _stream()),
                    "softmax_fuse")
     return out
@@ -338,7 +358,7 @@ def convlstm_step(x, h, c, weight, bias=None):
         raise RuntimeError("weight must be [4*Ch, Cin+Ch, kh, kw]")
     kh, kw = weight.shape[2:]
     h2, c2 = torch.empty_like(h), torch.empty_like(c)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(_lib.lib().jaf_convlstm_step_f32(_ptr(x), _ptr(h), _ptr(c), _ptr(weight), _ptr(bias), B, Cin, Ch,
                                                     H, W, kh, kw, _ptr(h2), _ptr(c2), _stream()), "convlstm_step")
     return h2, c2
@@ -351,7 +371,7 @@ def convlstm_pack_weight(weight, Cin: int, Ch: int):
         raise RuntimeError("weight must be [4*Ch, Cin+Ch, 3, 3]")
     n = _lib.lib().jaf_convlstm_wpack_bytes(Cin, Ch)
     wpack = torch.empty(n, dtype=torch.uint8, device=weight.device)
-    with torch.cuda.device(weight.device):
+    with _on(weight.device):
         _lib.check(_lib.lib().jaf_convlstm_pack_weight(_ptr(weight), Cin, Ch, _ptr(wpack), _stream()), "pack_weight")
     return wpack
 
@@ -363,7 +383,23 @@ def convlstm_step_tc(x, h, c, wpack, bias, Cin: int, Ch: int):
     c, bias = _check(c, "c", torch.float32), _check(bias, "bias", torch.float32)
     B, H, W, _ = x.shape
     h2, c2 = torch.empty_like(h), torch.empty_like(c)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(_lib.lib().jaf_convlstm_step_tc(_ptr(x), _ptr(h), _ptr(c), _ptr(wpack), _ptr(bias), B, Cin, Ch, H,
                                                    W, _ptr(h2), _ptr(c2), _stream()), "convlstm_step_tc")
     return h2, c2
+
+
+# ----------------------------------------------------------------------------- §8f rank 1
+def texture_warp(tex_parts, iuv, align_corners: bool = False):
+    """IUV texture lookup (test/conv_pro_test.py:41-74).  tex_parts [P,3,Ht,Wt] f32, iuv [B,H,W,3] uint8
+    -> [B,3,H,W] f32."""
+    tex, iuv = _check(tex_parts, "tex_parts", torch.float32), _check(iuv, "IUV", torch.uint8)
+    if tex.dim() != 4 or tex.shape[1] != 3 or iuv.dim() != 4 or iuv.shape[-1] != 3:
+        raise RuntimeError("expected tex_parts [P,3,Ht,Wt] and IUV [B,H,W,3]")
+    P, _, Ht, Wt = tex.shape
+    B, H, W, _ = iuv.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=iuv.device)
+    with _on(iuv.device):
+        _lib.check(_lib.lib().jaf_texture_warp(_ptr(tex), P, Ht, Wt, _ptr(iuv), B, H, W, int(bool(align_corners)),
+                                               _ptr(out), _stream()), "texture_warp")
+    return out

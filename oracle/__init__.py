@@ -300,3 +300,19 @@ class RefRaster:
         if flip_rows:
             fim, wim, depth = torch.flip(fim, dims=(1,)), torch.flip(wim, dims=(1,)), torch.flip(depth, dims=(1,))
         return fim, wim, depth
+
+
+# --------------------------------------------------------------------------- §8f rank 1
+def texture_warp(tex_parts, iuv, align_corners: bool = False):
+    """test/conv_pro_test.py:41-74 (texture_warp_pytorch).  tex_parts [P,3,Ht,Wt] f32, iuv [B,H,W,3] or
+    [H,W,3] uint8 -> [B,3,H,W] (or [3,H,W])."""
+    tex = _f32(tex_parts)
+    iuv = np.ascontiguousarray(iuv, np.uint8)
+    single = iuv.ndim == 3
+    if single:
+        iuv = iuv[None]
+    B, H, W, _ = iuv.shape
+    P, _, Ht, Wt = tex.shape
+    out = np.empty((B, 3, H, W), np.float32)
+    lib().orc_texture_warp(_p(tex), P, Ht, Wt, _p(iuv), B, H, W, int(bool(align_corners)), _p(out))
+    return out[0] if single else out

@@ -238,7 +238,7 @@ def _bf16_close(got_bits, ref_bits):
 
 @pytest.mark.parametrize("K,C", [(1, 64), (4, 64), (8, 64), (3, 32), (4, 128), (2, 256)])
 def test_warp_fuse_hot_kernel_matches_oracle(K, C):
-    B, H, W = 2, 40, 52  # ragged: W is not a multiple of the CTA strip, H not of the row chunk
+    B, H, W = 2, 41, 52  # ragged: W is not a multiple of the CTA strip, H is odd and not a multiple of the row chunk
     c = _rand_case(B, K, C, H, W, seed=K * 100 + C, Hs=33, Ws=47)
     feat_bits = oracle.f32_to_bf16_bits(c["feat"].transpose(0, 1, 3, 4, 2))        # dense [R,K,Hs,Ws,C]
     o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=feat_bits, feat_layout="nhwc", feat_bf16=True,
@@ -526,3 +526,22 @@ def test_convlstm_tensor_core_rejects_unsupported_shapes():
         ops.convlstm_step_tc(x, x, c, wp, None, 64, 64)
     with pytest.raises(RuntimeError, match="multiples of 64"):
         ops.convlstm_pack_weight(torch.zeros(4 * 24, 36, 3, 3, device=DEV), 12, 24)
+
+
+# ------------------------------------------------------------------ §8f rank 1: IUV texture lookup
+@pytest.mark.parametrize("align_corners", [False, True])
+def test_texture_warp_matches_reference_and_oracle(golden_dir, align_corners):
+    from jafpro_b200.texture import texture_warp_pytorch
+    d = _load(golden_dir, "texture_warp.npz")
+    got = texture_warp_pytorch([torch.from_numpy(t) for t in d["tex"]], d["iuv"], "cuda", align_corners=align_corners)
+    orc = oracle.texture_warp(d["tex"], d["iuv"], align_corners=align_corners)
+    assert np.array_equal(_bits(got), orc.view(np.int32))  # bit-exact vs the oracle
+    if not align_corners:
+        assert float(np.abs(_np(got) - d["out"]).max()) <= 1e-6  # the reference's own output
+    # a batch of DanceVideo-sized frames with 200x200 part textures (the reference's texture size)
+    rng = np.random.default_rng(5)
+    tex = rng.normal(size=(24, 3, 200, 200)).astype(np.float32)
+    iuv = rng.integers(0, 256, (4, 256, 256, 3)).astype(np.uint8)
+    iuv[..., 0] = rng.integers(0, 26, (4, 256, 256))  # includes an out-of-range part id (25)
+    out = ops.texture_warp(_cu(tex), _cu(iuv), align_corners)
+    assert np.array_equal(_bits(out), oracle.texture_warp(tex, iuv, align_corners).view(np.int32))

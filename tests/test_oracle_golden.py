@@ -212,3 +212,14 @@ def test_flow_self_transfer_reproduces_pixel_centres():
     assert np.abs(T[0][fg][:, 0] - cx).max() < 2e-3
     assert np.abs(T[0][fg][:, 1] - cy).max() < 2e-3
     assert np.all(T[0][~fg] == -2.0)
+
+
+def test_texture_warp_matches_reference_function(golden_dir):
+    """test/conv_pro_test.py:41-74 executed from the reference script itself (tools/make_golden.py)."""
+    d = _load(golden_dir, "texture_warp.npz")
+    out = oracle.texture_warp(d["tex"], d["iuv"], align_corners=False)
+    assert np.abs(out - d["out"]).max() <= 1e-6
+    assert np.all(out[:, d["iuv"][..., 0] == 0] == 0)
+    # batched call == per-frame calls
+    both = oracle.texture_warp(d["tex"], np.stack([d["iuv"], d["iuv"][::-1].copy()]))
+    assert np.array_equal(both[0], out)

@@ -24,6 +24,7 @@ Fixtures (all small, float32 unless noted):
   softmax_fuse.npz     src/networks.py Downsampler_mask.forward K-reduction (:1259-1286), captured
                        with forward hooks at the first scale.
   mask_blend.npz       src/flow_net.py Propagation3DFlowNet.forward (:87-99).
+  texture_warp.npz     test/conv_pro_test.py texture_warp_pytorch (:41-74), the IUV texture lookup.
 """
 import os
 import sys
@@ -198,6 +199,29 @@ def mask_blend():
     print("mask_blend:", out['pred_target'].shape)
 
 
+def texture_warp():
+    """test/conv_pro_test.py:41-74 texture_warp_pytorch, executed from the reference script file itself
+    (the function is lifted out with ast because importing the script runs its CLI and needs a GPU)."""
+    import ast
+    src = open(os.path.join(REF, "test", "conv_pro_test.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "texture_warp_pytorch"][0]
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "conv_pro_test.py", "exec"), ns)
+    rng = np.random.default_rng(0)
+    H = W = 48
+    Ht = Wt = 20
+    tex = [torch.from_numpy(rng.normal(size=(3, Ht, Wt)).astype(np.float32)) for _ in range(24)]
+    iuv = np.zeros((H, W, 3), np.uint8)
+    iuv[..., 0] = rng.integers(0, 25, (H, W))
+    iuv[..., 1] = rng.integers(0, 256, (H, W))
+    iuv[..., 2] = rng.integers(0, 256, (H, W))
+    iuv[0, :8, 1], iuv[0, :8, 2], iuv[1, :8, 1], iuv[1, :8, 2] = 0, 255, 255, 0  # texture corners
+    out = ns["texture_warp_pytorch"](tex, iuv, "cpu")
+    np.savez_compressed(os.path.join(GOLD, "texture_warp.npz"), tex=np.stack([t.numpy() for t in tex]), iuv=iuv,
+                        out=out.numpy())
+    print("texture_warp:", tuple(out.shape))
+
+
 def smpl_template():
     """mapper.txt `v` lines (6890 T-pose vertices) + smpl_faces.npy -> jafpro_b200/data/."""
     vs = []
@@ -225,3 +249,4 @@ if __name__ == "__main__":
     convlstm()
     softmax_fuse()
     mask_blend()
+    texture_warp()
