@@ -66,6 +66,7 @@ __device__ __forceinline__ Tap make_tap(float gx, float gy, int Ws, int Hs, int 
 struct WFArgs {
   int B, K, H, W, Hs, Ws, C, align_corners, mask_c;
   int rows_per_cta, tiles_x, tiles_y;
+  int c_chunk;  // generic kernel: channels per blockIdx.y slice
   const float* rgb;
   const void* feat;
   const int* ref_index;
@@ -395,7 +396,9 @@ __device__ __forceinline__ void store_from_f32<__nv_bfloat16>(__nv_bfloat16* p, 
 
 // IS_RGB: the tensor is a.rgb / a.out_rgb (planar f32, C = 3, per-channel mask, blend, warped output);
 // otherwise a.feat / a.out_feat in layout NHWC ? [.,H,W,C] : [.,C,H,W].
-template <typename T, bool NHWC, bool IS_RGB>
+// KT > 0: compile-time K (taps and weights stay in registers); KT == 0: runtime K <= 16.
+// blockIdx.y slices the channels so that small images with many channels still fill the GPU.
+template <typename T, bool NHWC, bool IS_RGB, int KT>
 __global__ void __launch_bounds__(256)
 k_warp_fuse_generic(const WFArgs a) {
   const long HW = (long)a.H * a.W, HWs = (long)a.Hs * a.Ws;
@@ -404,28 +407,36 @@ k_warp_fuse_generic(const WFArgs a) {
   const int b = (int)(i / HW);
   const long pix = i % HW;
   const long r = a.ref_index ? a.ref_index[b] : b;
-  const int K = a.K;
+  const int K = KT > 0 ? KT : a.K;
   const int C = IS_RGB ? 3 : a.C;
+  const int c_begin = IS_RGB ? 0 : (int)blockIdx.y * a.c_chunk;
+  const int c_end = IS_RGB ? 3 : min(C, c_begin + a.c_chunk);
   const T* __restrict__ src = IS_RGB ? reinterpret_cast<const T*>(a.rgb) : reinterpret_cast<const T*>(a.feat);
   T* __restrict__ dst = IS_RGB ? reinterpret_cast<T*>(a.out_rgb) : reinterpret_cast<T*>(a.out_feat);
 
-  float aw[kMaxKGeneric];
-  Tap tp[kMaxKGeneric];
+  float aw[KT > 0 ? KT : kMaxKGeneric];
+  Tap tp[KT > 0 ? KT : kMaxKGeneric];
   // softmax (reference order: max, exp, running sum, divide)
   if (a.logits) {
     float m = -CUDART_INF_F;
+#pragma unroll
     for (int k = 0; k < K; ++k) m = fmaxf(m, ld_stream_f32(a.logits + ((long)b * K + k) * HW + pix));
     float s = 0.f;
+#pragma unroll
     for (int k = 0; k < K; ++k) {
       aw[k] = expf(ld_stream_f32(a.logits + ((long)b * K + k) * HW + pix) - m);
       s += aw[k];
     }
+#pragma unroll
     for (int k = 0; k < K; ++k) aw[k] = aw[k] / s;
   } else {
     float s = 0.f;
+#pragma unroll
     for (int k = 0; k < K; ++k) s += 1.0f;
+#pragma unroll
     for (int k = 0; k < K; ++k) aw[k] = 1.0f / s;
   }
+#pragma unroll
   for (int k = 0; k < K; ++k) {
     float v = 1.f;
     if (a.vis)
@@ -437,8 +448,9 @@ k_warp_fuse_generic(const WFArgs a) {
     tp[k] = make_tap(gxy.x, gxy.y, a.Ws, a.Hs, a.align_corners);
   }
   const float tm1 = a.tgt_mask ? ld_stream_f32(a.tgt_mask + ((long)b * a.mask_c) * HW + pix) : 1.f;
-  for (int c = 0; c < C; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     float acc = 0.f;
+#pragma unroll
     for (int k = 0; k < K; ++k) {
       const Tap& t = tp[k];
       const bool need = (aw[k] != 0.f) || (IS_RGB && a.warped_rgb);
@@ -533,6 +545,18 @@ bool launch_nhwc_k(const WFArgs& a, int grid, cudaStream_t st) {
   }
 }
 
+template <typename T, bool NHWC, bool IS_RGB>
+void launch_generic(const WFArgs& a, int gx, int gy, cudaStream_t st) {
+  const dim3 grid((unsigned)gx, (unsigned)gy);
+  switch (a.K) {
+    case 1: k_warp_fuse_generic<T, NHWC, IS_RGB, 1><<<grid, 256, 0, st>>>(a); break;
+    case 2: k_warp_fuse_generic<T, NHWC, IS_RGB, 2><<<grid, 256, 0, st>>>(a); break;
+    case 3: k_warp_fuse_generic<T, NHWC, IS_RGB, 3><<<grid, 256, 0, st>>>(a); break;
+    case 4: k_warp_fuse_generic<T, NHWC, IS_RGB, 4><<<grid, 256, 0, st>>>(a); break;
+    default: k_warp_fuse_generic<T, NHWC, IS_RGB, 0><<<grid, 256, 0, st>>>(a); break;
+  }
+}
+
 // Returns true when the hot kernel was launched.
 bool launch_nhwc(WFArgs a, cudaStream_t st) {
   const int lpp = a.C / 8;
@@ -603,19 +627,26 @@ extern "C" int jaf_warp_fuse(const JafWarpFuseParams* p) {
   const int grid = jaf::ceil_div(npix, 256);
   if (!rgb_done || !feat_done) JAF_REQUIRE(p->K <= kMaxKGeneric, "K > 16 is not supported by the generic kernel");
   if (!rgb_done) {
-    if (!launch_rgb(a, st)) k_warp_fuse_generic<float, false, true><<<grid, 256, 0, st>>>(a);
+    if (!launch_rgb(a, st)) launch_generic<float, false, true>(a, grid, 1, st);
     ++launches;
   }
   if (!feat_done) {
     WFArgs f = a;
     f.warped_rgb = nullptr;
+    // slice the channels over blockIdx.y until ~600k threads are in flight
+    long want = (600000 + npix - 1) / npix;
+    if (want < 1) want = 1;
+    if (want > p->C) want = p->C;
+    if (want > 65535) want = 65535;
+    f.c_chunk = (int)((p->C + want - 1) / want);
+    const int ny = (p->C + f.c_chunk - 1) / f.c_chunk;
     const bool nhwc = p->feat_layout == JAF_LAYOUT_NHWC;
     if (p->feat_dtype == JAF_DTYPE_F32) {
-      if (nhwc) k_warp_fuse_generic<float, true, false><<<grid, 256, 0, st>>>(f);
-      else      k_warp_fuse_generic<float, false, false><<<grid, 256, 0, st>>>(f);
+      if (nhwc) launch_generic<float, true, false>(f, grid, ny, st);
+      else      launch_generic<float, false, false>(f, grid, ny, st);
     } else {
-      if (nhwc) k_warp_fuse_generic<__nv_bfloat16, true, false><<<grid, 256, 0, st>>>(f);
-      else      k_warp_fuse_generic<__nv_bfloat16, false, false><<<grid, 256, 0, st>>>(f);
+      if (nhwc) launch_generic<__nv_bfloat16, true, false>(f, grid, ny, st);
+      else      launch_generic<__nv_bfloat16, false, false>(f, grid, ny, st);
     }
     ++launches;
   }
