@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjafpro_b200.so")
+LIB_PATH = os.environ.get("JAFPRO_B200_LIB") or os.path.join(_HERE, "libjafpro_b200.so")  # override: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 
 _vp, _i, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_uint64

@@ -110,6 +110,83 @@ __device__ __forceinline__ HotTap make_hot_tap(float gx, float gy, int Ws, int H
   return t;
 }
 
+// Stand-alone flavour of rgb_pixel for the RGB-only kernel: constants hoisted, one reciprocal instead of K
+// divisions, byte addressing.  (Inlined into the fused kernel it costs phase A 2 % through register
+// allocation, measured, so the fused kernel keeps the plain version below.)
+// One output pixel of the RGB planes (planar fp32, the reference layout): softmax in the reference's
+// sequential order, ATen's tap order, acc += w_k * warped_k — bit-identical to k_warp_fuse_generic.
+template <int KT, bool SKIP>
+__device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __restrict__ rgb_base,
+                                          const float2* __restrict__ b_grid, const float* __restrict__ b_logit,
+                                          const float* __restrict__ b_vis, const int* __restrict__ b_fim,
+                                          const float* __restrict__ b_mask, const float* __restrict__ b_fake,
+                                          const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
+                                          unsigned HW, unsigned HWs, unsigned Ws) {
+  // softmax in the reference order: max, exp, running sum; one correctly-rounded reciprocal replaces the
+  // K divisions (identical for K = 1, within 1 ulp otherwise)
+  float aw[KT];
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    aw[k] = b_logit ? __ldg(b_logit + ((unsigned)k * HW + pix)) : 0.f;
+    m = fmaxf(m, aw[k]);
+  }
+  float ssum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    aw[k] = expf(aw[k] - m);
+    ssum += aw[k];
+  }
+  const float inv = (KT == 1) ? 1.0f : __frcp_rn(ssum);
+  const float vf = b_fim ? ((__ldg(b_fim + pix) != -1) ? 1.f : 0.f) : 1.f;
+  // constants of the sample-position arithmetic, once per pixel instead of once per reference
+  const int Hs = a.Hs;
+  const float wsf = (float)Ws, hsf = (float)Hs, wm1 = (float)(Ws - 1), hm1 = (float)(Hs - 1);
+  const float wm2 = (float)(Ws - 2), hm2 = (float)(Hs - 2);
+  const bool ac = a.align_corners != 0;
+  const char* __restrict__ rgb_bytes = reinterpret_cast<const char*>(rgb_base);
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    const float v = b_vis ? __ldg(b_vis + ((unsigned)k * HW + pix)) : vf;
+    const float w = (KT == 1) ? aw[k] * v : (aw[k] * inv) * v;
+    if (!SKIP || w != 0.f) {  // without a visibility input nothing is skipped: no branch, loads of all k overlap
+      const float2 gxy = __ldg(b_grid + ((unsigned)k * HW + pix));
+      // == make_hot_tap (same pinned operations)
+      float ix = ac ? __fmul_rn(__fmul_rn(__fadd_rn(gxy.x, 1.f), 0.5f), wm1) : __fmul_rn(__fmaf_rn(__fadd_rn(gxy.x, 1.f), wsf, -1.f), 0.5f);
+      float iy = ac ? __fmul_rn(__fmul_rn(__fadd_rn(gxy.y, 1.f), 0.5f), hm1) : __fmul_rn(__fmaf_rn(__fadd_rn(gxy.y, 1.f), hsf, -1.f), 0.5f);
+      ix = fminf(wm1, fmaxf(ix, 0.f));
+      iy = fminf(hm1, fmaxf(iy, 0.f));
+      const float fx = fminf(floorf(ix), wm2), fy = fminf(floorf(iy), hm2);
+      const float ax = __fsub_rn(fx + 1.f, ix), bx = __fsub_rn(ix, fx), ay = __fsub_rn(fy + 1.f, iy), by = __fsub_rn(iy, fy);
+      const float nw = __fmul_rn(ax, ay), ne = __fmul_rn(bx, ay), sw = __fmul_rn(ax, by), se = __fmul_rn(bx, by);
+      const unsigned ok = (unsigned)(k * 3) * HWs + (unsigned)((int)fy * (int)Ws + (int)fx);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* p0 = reinterpret_cast<const float*>(rgb_bytes + (size_t)(ok + (unsigned)c * HWs) * 4u);
+        const float* p1 = reinterpret_cast<const float*>(rgb_bytes + (size_t)(ok + (unsigned)c * HWs + Ws) * 4u);
+        float s = fmaf(__ldg(p0), nw, 0.f);
+        s = fmaf(__ldg(p0 + 1), ne, s);
+        s = fmaf(__ldg(p1), sw, s);
+        s = fmaf(__ldg(p1 + 1), se, s);
+        acc[c] = fmaf(w, s, acc[c]);
+      }
+    }
+  }
+  const float tm = b_mask ? __ldg(b_mask + pix) : 1.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float ov = acc[c];
+    if (b_mask) ov *= (a.mask_c == 3) ? __ldg(b_mask + ((unsigned)c * HW + pix)) : tm;
+    if (b_fake) {
+      const float wc = __ldg(b_conf + pix);
+      const float fkv = __ldg(b_fake + ((unsigned)c * HW + pix));
+      ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+    }
+    st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
+  }
+}
+
 // One output pixel of the RGB planes (planar fp32, the reference layout): softmax in the reference's
 // sequential order, ATen's tap order, acc += w_k * warped_k — bit-identical to k_warp_fuse_generic.
 template <int KT, bool SKIP>
@@ -342,7 +419,7 @@ k_warp_fuse_rgb(const WFArgs a) {
   const unsigned pix = (unsigned)(i % HW);
   const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
   const size_t bK = (size_t)b * KT * HW;
-  rgb_pixel<KT, SKIP>(a, a.rgb + r * KT * 3 * (size_t)HWs, reinterpret_cast<const float2*>(a.grid) + bK,
+  rgb_pixel_lean<KT, SKIP>(a, a.rgb + r * KT * 3 * (size_t)HWs, reinterpret_cast<const float2*>(a.grid) + bK,
                       a.logits ? a.logits + bK : nullptr, a.vis ? a.vis + bK : nullptr,
                       (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr,
                       a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr,
