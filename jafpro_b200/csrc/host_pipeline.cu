@@ -94,7 +94,9 @@ extern "C" int jaf_warp_fuse_host(const JafWarpFuseParams* hp, int frames_per_ch
   const size_t fe = esz(hp->feat_dtype);
   const size_t rgb_set = (size_t)K * 3 * HWs * 4;          // one reference set, RGB
   const size_t feat_set = (size_t)K * hp->C * HWs * fe;    // one reference set, features
-  const size_t per_frame = K * HW * 16 + (want_rgb ? rgb_set : 0) + (want_feat ? feat_set : 0) + HW * 64;
+  // bytes a target frame moves through a slot (resident reference sets addressed by ref_index do not count)
+  const size_t per_frame = K * HW * 16 + HW * 64 + (want_feat ? (size_t)hp->C * HW * fe : 0) +
+                           (hp->ref_index ? 0 : (want_rgb ? rgb_set : 0) + (want_feat ? feat_set : 0));
   int n = frames_per_chunk;
   if (n <= 0) {
     const size_t fit = ((size_t)256 << 20) / (per_frame > 0 ? per_frame : 1);  // ~256 MB per slot
