@@ -19,7 +19,20 @@
 namespace {
 
 constexpr unsigned long long kEmptyKey = ~0ull;
-constexpr int kBigBox = 64;  // boxes above this many pixels are walked by the whole warp
+constexpr int kBigBox = 64;     // boxes above this many pixels are walked by the whole warp
+constexpr int kHugeBox = 2048;  // boxes above this go to a queue that a follow-up launch spreads over the GPU
+constexpr int kHugeCap = 1024;  // queue capacity (entries beyond it are walked by their warp)
+constexpr int kHugeRun = 128;   // entries x chunks covered by the follow-up grid per launch
+constexpr int kHugeChunks = 32;
+
+struct HugeEntry {
+  int b, fn, x_lo, y_lo, bw, npx, pad0, pad1;
+};
+struct HugeQueue {
+  unsigned int count;
+  unsigned int pad[15];
+  HugeEntry e[kHugeCap];
+};
 
 // ---- a1-a3: src/nmr.py:10-28 (s*(X+t)), :271 (y *= -1), NR/look_at.py:59 (v - eye; the rotation
 // is exactly the identity for SMPLRenderer's eye), NR/vertices_to_faces.py:19-22 (gather).
@@ -74,8 +87,17 @@ __device__ __forceinline__ float face_setup(const float* f, int is, float* inv, 
 // ---- rasterize_cuda_kernel.cu:96-97, :115-137.  true => the face is a z-buffer candidate at (xi, yi).
 __device__ __forceinline__ bool pixel_test(const float* f, const float* inv, int xi, int yi, int is,
                                            float near_, float far_, float* w, float* zp_out) {
-  const float yp = (float)((2. * yi + 1 - is) / is);
-  const float xp = (float)((2. * xi + 1 - is) / is);
+  // :96-97 `(2. * yi + 1 - is) / is` in double, rounded to float.  For is <= 4096 the numerator is a small
+  // integer and a correctly rounded fp32 division gives the same bits (no double-rounding case exists for
+  // quotients of integers below 2^13; checked exhaustively in tools/), without the fp64 divide.
+  float yp, xp;
+  if (is <= 4096) {
+    yp = __fdiv_rn((float)(2 * yi + 1 - is), (float)is);
+    xp = __fdiv_rn((float)(2 * xi + 1 - is), (float)is);
+  } else {
+    yp = (float)((2. * yi + 1 - is) / is);
+    xp = (float)((2. * xi + 1 - is) / is);
+  }
   if (__fmul_rn(__fsub_rn(yp, f[1]), __fsub_rn(f[3], f[0])) < __fmul_rn(__fsub_rn(xp, f[0]), __fsub_rn(f[4], f[1])))
     return false;
   if (__fmul_rn(__fsub_rn(yp, f[4]), __fsub_rn(f[6], f[3])) < __fmul_rn(__fsub_rn(xp, f[3]), __fsub_rn(f[7], f[4])))
@@ -128,8 +150,13 @@ __device__ __forceinline__ Box face_box(const float* px, const float* py, float 
     bx.x_lo = 0; bx.y_lo = 0; bx.x_hi = is - 1; bx.y_hi = is - 1;
     return bx;
   }
+  // A pixel outside the exact triangle can only pass the three fp32 edge comparisons if its distance d to
+  // each violated edge line satisfies d <= 3.6e-7 * D (three roundings of 2^-24 per product; D = distance
+  // to the edge's vertex <= ~1.5 * (is + |p|max) px); beyond the apex of a needle of apex angle ~ 1/sliver
+  // that allows an overshoot t <= 2 * sliver * d.  Twice that bound is the margin.
   const float sliver = l2 / aden;  // ~2.3 for an equilateral face, large for slivers
-  const float mf = fminf((float)is, 1.0f + floorf(1.6e-5f * (float)is * sliver));
+  const float pmax = fmaxf(fmaxf(fabsf(xmin), fabsf(xmax)), fmaxf(fabsf(ymin), fabsf(ymax)));
+  const float mf = fminf((float)is, 1.0f + floorf(2.2e-6f * ((float)is + pmax) * sliver));
   const float lim = 2.0f * (float)is + 4.0f;
   bx.x_lo = max(0, (int)fmaxf(floorf(xmin) - mf, -lim));
   bx.y_lo = max(0, (int)fmaxf(floorf(ymin) - mf, -lim));
@@ -153,7 +180,7 @@ __global__ void __launch_bounds__(256)
 k_raster_scatter(const float* __restrict__ faces_xyz, const float* __restrict__ cam,
                  const float* __restrict__ verts, const int* __restrict__ fidx, int B, int V, int F, int is,
                  float eye_z, float near_, float far_, unsigned long long* __restrict__ zbuf,
-                 float* __restrict__ faces_out) {
+                 float* __restrict__ faces_out, HugeQueue* __restrict__ huge) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   float f[9], inv[9];
@@ -180,7 +207,16 @@ k_raster_scatter(const float* __restrict__ faces_xyz, const float* __restrict__ 
   }
   const int bw = bx.x_hi - bx.x_lo + 1, bh = bx.y_hi - bx.y_lo + 1;
   const int npx = (bw > 0 && bh > 0) ? bw * bh : 0;
-  const bool big = npx > kBigBox;
+  bool big = npx > kBigBox;
+  if (npx > kHugeBox) {  // needle-like or degenerate face with a (near) full-image box: defer
+    const unsigned slot = atomicAdd(&huge->count, 1u);
+    if (slot < (unsigned)kHugeCap) {
+      HugeEntry en = {b, fn, bx.x_lo, bx.y_lo, bw, npx, 0, 0};
+      huge->e[slot] = en;
+      big = false;
+      bx.y_hi = bx.y_lo - 1;  // nothing left to do here
+    }
+  }
   if (!big) {
     for (int yi = bx.y_lo; yi <= bx.y_hi; ++yi)
       for (int xi = bx.x_lo; xi <= bx.x_hi; ++xi) zbuf_try(zbuf, f, inv, b, fn, xi, yi, is, near_, far_);
@@ -201,6 +237,30 @@ k_raster_scatter(const float* __restrict__ faces_xyz, const float* __restrict__ 
     const int sb = __shfl_sync(0xffffffffu, b, src), sf = __shfl_sync(0xffffffffu, fn, src);
     for (int t = (int)lane; t < sn; t += 32)
       zbuf_try(zbuf, ff, fi, sb, sf, sx + t % sw, sy + t / sw, is, near_, far_);
+  }
+}
+
+// ---- pass 1b: the deferred huge boxes, each spread over kHugeChunks CTAs
+template <bool PROJECT>
+__global__ void __launch_bounds__(256)
+k_raster_huge(const float* __restrict__ faces_xyz, const float* __restrict__ cam, const float* __restrict__ verts,
+              const int* __restrict__ fidx, int V, int F, int is, float eye_z, float near_, float far_,
+              unsigned long long* __restrict__ zbuf, const HugeQueue* __restrict__ huge, int first) {
+  const unsigned count = min(huge->count, (unsigned)kHugeCap);
+  for (unsigned e = (unsigned)first + blockIdx.x; e < count; e += gridDim.x) {
+  const HugeEntry en = huge->e[e];
+  float f[9], inv[9], px[3], py[3];
+  if (PROJECT) {
+    load_face_projected(cam, verts, fidx, en.b, en.fn, V, eye_z, f);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = faces_xyz[((size_t)en.b * F + en.fn) * 9 + k];
+  }
+  face_setup(f, is, inv, px, py);
+  const int per = (en.npx + kHugeChunks - 1) / kHugeChunks;
+  const int t0 = blockIdx.y * per, t1 = min(en.npx, t0 + per);
+  for (int t = t0 + (int)threadIdx.x; t < t1; t += blockDim.x)
+    zbuf_try(zbuf, f, inv, en.b, en.fn, en.x_lo + t % en.bw, en.y_lo + t / en.bw, is, near_, far_);
   }
 }
 
@@ -300,6 +360,27 @@ k_flow_compose(const float* __restrict__ src_pts, int stride, int negate_y, cons
   reinterpret_cast<float2*>(T)[i] = make_float2(tx, ty);
 }
 
+size_t zbuf_bytes(int B, int is) { return ((size_t)B * is * is * sizeof(unsigned long long) + 255) & ~(size_t)255; }
+
+// pass 1 (+1b): clear the z-buffer and the huge-box queue, scatter the faces, spread the deferred boxes
+template <bool PROJECT>
+int run_pass1(const float* faces_xyz, const float* cam, const float* verts, const int* fidx, int B, int V, int F,
+              int is, float eye_z, float near_, float far_, void* workspace, float* faces_out, cudaStream_t st,
+              int* launches) {
+  auto* zb = static_cast<unsigned long long*>(workspace);
+  auto* hq = reinterpret_cast<HugeQueue*>(static_cast<char*>(workspace) + zbuf_bytes(B, is));
+  JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)B * is * is * 8, st));
+  JAF_CUDA(cudaMemsetAsync(hq, 0, 64, st));
+  if (F > 0) {
+    k_raster_scatter<PROJECT><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(faces_xyz, cam, verts, fidx, B, V, F, is,
+                                                                            eye_z, near_, far_, zb, faces_out, hq);
+    k_raster_huge<PROJECT><<<dim3(kHugeRun, kHugeChunks), 256, 0, st>>>(faces_xyz, cam, verts, fidx, V, F, is, eye_z,
+                                                                      near_, far_, zb, hq, 0);
+    *launches += 2;
+  }
+  return JAF_OK;
+}
+
 int check_raster_args(int B, int F, int is) {
   return B >= 0 && F >= 0 && is > 0 && is <= 16384;
 }
@@ -320,7 +401,7 @@ int jaf_project_gather(const float* cam, const float* verts, const int32_t* face
 
 size_t jaf_raster_workspace_bytes(int B, int image_size) {
   if (B <= 0 || image_size <= 0) return 0;
-  return (size_t)B * image_size * image_size * sizeof(unsigned long long);
+  return zbuf_bytes(B, image_size) + sizeof(HugeQueue);
 }
 
 int jaf_raster_fim_wim(const float* faces_xyz, int B, int F, int image_size, float near_, float far_,
@@ -331,12 +412,11 @@ int jaf_raster_fim_wim(const float* faces_xyz, int B, int F, int image_size, flo
   cudaStream_t st = jaf::as_stream(stream);
   auto* zb = static_cast<unsigned long long*>(workspace);
   const long npix = (long)B * image_size * image_size;
-  JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)npix * 8, st));
   int launches = 0;
-  if (F > 0) {
-    k_raster_scatter<false><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(
-        faces_xyz, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_, zb, nullptr);
-    ++launches;
+  {
+    const int st1 = run_pass1<false>(faces_xyz, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_,
+                                     workspace, nullptr, st, &launches);
+    if (st1 != JAF_OK) return st1;
   }
   k_raster_resolve<false, false><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
       zb, faces_xyz, nullptr, nullptr, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_, flip_rows,
@@ -353,12 +433,11 @@ int jaf_render_fim_wim(const float* cam, const float* verts, const int32_t* face
   cudaStream_t st = jaf::as_stream(stream);
   auto* zb = static_cast<unsigned long long*>(workspace);
   const long npix = (long)B * image_size * image_size;
-  JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)npix * 8, st));
   int launches = 0;
-  if (F > 0) {
-    k_raster_scatter<true><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(
-        nullptr, cam, verts, faces_idx, B, V, F, image_size, eye_z, near_, far_, zb, faces_xyz);
-    ++launches;
+  {
+    const int st1 = run_pass1<true>(nullptr, cam, verts, faces_idx, B, V, F, image_size, eye_z, near_, far_, workspace,
+                                    faces_xyz, st, &launches);
+    if (st1 != JAF_OK) return st1;
   }
   k_raster_resolve<true, false><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
       zb, nullptr, cam, verts, faces_idx, nullptr, nullptr, B, V, F, image_size, eye_z, near_, far_, 1, fim, wim,
@@ -389,12 +468,11 @@ int jaf_cal_flow(const float* src_cam, const float* src_verts, const float* tgt_
   cudaStream_t st = jaf::as_stream(stream);
   auto* zb = static_cast<unsigned long long*>(workspace);
   const long npix = (long)B * image_size * image_size;
-  JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)npix * 8, st));
   int launches = 0;
-  if (F > 0) {
-    k_raster_scatter<true><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(
-        nullptr, tgt_cam, tgt_verts, faces_idx, B, V, F, image_size, eye_z, near_, far_, zb, nullptr);
-    ++launches;
+  {
+    const int st1 = run_pass1<true>(nullptr, tgt_cam, tgt_verts, faces_idx, B, V, F, image_size, eye_z, near_, far_,
+                                    workspace, nullptr, st, &launches);
+    if (st1 != JAF_OK) return st1;
   }
   k_raster_resolve<true, true><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
       zb, nullptr, tgt_cam, tgt_verts, faces_idx, src_cam, src_verts, B, V, F, image_size, eye_z, near_, far_, 1,

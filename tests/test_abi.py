@@ -37,7 +37,7 @@ def test_version_and_error_reporting_without_gpu():
     assert "null params" in _lib.last_error()
     with pytest.raises(RuntimeError, match="null params"):
         _lib.check(lib.jaf_warp_fuse(None), "warp_fuse")
-    assert lib.jaf_raster_workspace_bytes(2, 256) == 2 * 256 * 256 * 8
+    assert lib.jaf_raster_workspace_bytes(2, 256) >= 2 * 256 * 256 * 8  # z-buffer keys + the deferred-box queue
     assert lib.jaf_convlstm_wpack_bytes(256, 256) == 9 * 1024 * 512 * 2
 
 
