@@ -105,6 +105,19 @@ int jaf_cal_flow(const float* src_cam, const float* src_verts, const float* tgt_
                  float* wim, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * a8 for K references: the transfer flows from K source poses into ONE target pose per frame.
+ * The reference calls float_estimate.cal_flow once per (source, target) pair and rasterises the
+ * target every time (src/cal_flow.py:33); here the target is rasterised once and composed K times.
+ * src_cam [B,K,3]; src_verts [B,K,V,3]; tgt_cam [B,3]; tgt_verts [B,V,3];
+ * T out [B,K,S,S,2] (the `grid` of jaf_warp_fuse); fim/wim out [B,S,S]/[B,S,S,3] may be NULL.
+ * T[b,k] is bit-identical to jaf_cal_flow(src[b,k], tgt[b]).
+ * --------------------------------------------------------------------------------- */
+int jaf_cal_flow_multi(const float* src_cam, const float* src_verts, const float* tgt_cam,
+                       const float* tgt_verts, const int32_t* faces_idx, int B, int K, int V, int F,
+                       int image_size, float eye_z, float near_, float far_, float* T, int32_t* fim,
+                       float* wim, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * row F  fused bilinear backward warp of K references + visibility/softmax fusion
  * replaces, in ONE pass over every input byte:
  *   float_estimate.warp_image = F.grid_sample(src, flow, padding_mode='border')

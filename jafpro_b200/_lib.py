@@ -40,6 +40,7 @@ SIGNATURES = {
     "jaf_render_fim_wim": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "jaf_flow_compose": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "jaf_cal_flow": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "jaf_cal_flow_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "jaf_warp_fuse": (_i, [C.POINTER(WarpFuseParams)]),
     "jaf_warp_fuse_host": (_i, [C.POINTER(WarpFuseParams), _i]),
     "jaf_warp_image": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

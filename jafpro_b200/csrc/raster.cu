@@ -273,7 +273,7 @@ k_raster_resolve(const unsigned long long* __restrict__ zbuf, const float* __res
                  const float* __restrict__ cam, const float* __restrict__ verts, const int* __restrict__ fidx,
                  const float* __restrict__ src_cam, const float* __restrict__ src_verts, int B, int V, int F,
                  int is, float eye_z, float near_, float far_, int flip_rows, int* __restrict__ fim,
-                 float* __restrict__ wim, float* __restrict__ depth, float* __restrict__ T) {
+                 float* __restrict__ wim, float* __restrict__ depth, float* __restrict__ T, int Ksrc) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)B * is * is) return;
   const int b = (int)(i / ((long)is * is));
@@ -305,20 +305,29 @@ k_raster_resolve(const unsigned long long* __restrict__ zbuf, const float* __res
   }
   if (depth) depth[o] = zp;
   if (COMPOSE) {
-    float tx = -2.0f, ty = -2.0f;  // src/nmr.py:627
+    // one target raster serves Ksrc source poses: T[b, ks] for ks < Ksrc (Ksrc == 1: float_estimate.cal_flow)
+    int vi[3] = {0, 0, 0};
     if (fn >= 0) {
-      const float s = src_cam[b * 3 + 0], ctx = src_cam[b * 3 + 1], cty = src_cam[b * 3 + 2];
-      float ax[3], ay[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float* p = src_verts + ((size_t)b * V + fidx[fn * 3 + k]) * 3;
-        ax[k] = __fmul_rn(s, __fadd_rn(p[0], ctx));
-        ay[k] = __fmul_rn(s, __fadd_rn(p[1], cty));  // -(-(s*(Y+ty))): raster flip then cal_flow.py:31
-      }
-      tx = __fadd_rn(__fadd_rn(__fmul_rn(ax[0], w[0]), __fmul_rn(ax[1], w[1])), __fmul_rn(ax[2], w[2]));
-      ty = __fadd_rn(__fadd_rn(__fmul_rn(ay[0], w[0]), __fmul_rn(ay[1], w[1])), __fmul_rn(ay[2], w[2]));
+      for (int k = 0; k < 3; ++k) vi[k] = fidx[fn * 3 + k];
     }
-    reinterpret_cast<float2*>(T)[o] = make_float2(tx, ty);
+    for (int ks = 0; ks < Ksrc; ++ks) {
+      float tx = -2.0f, ty = -2.0f;  // src/nmr.py:627
+      const size_t sb = (size_t)b * Ksrc + ks;
+      if (fn >= 0) {
+        const float s = src_cam[sb * 3 + 0], ctx = src_cam[sb * 3 + 1], cty = src_cam[sb * 3 + 2];
+        float ax[3], ay[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float* p = src_verts + (sb * V + vi[k]) * 3;
+          ax[k] = __fmul_rn(s, __fadd_rn(p[0], ctx));
+          ay[k] = __fmul_rn(s, __fadd_rn(p[1], cty));  // -(-(s*(Y+ty))): raster flip then cal_flow.py:31
+        }
+        tx = __fadd_rn(__fadd_rn(__fmul_rn(ax[0], w[0]), __fmul_rn(ax[1], w[1])), __fmul_rn(ax[2], w[2]));
+        ty = __fadd_rn(__fadd_rn(__fmul_rn(ay[0], w[0]), __fmul_rn(ay[1], w[1])), __fmul_rn(ay[2], w[2]));
+      }
+      reinterpret_cast<float2*>(T)[(sb * is + yo) * is + xi] = make_float2(tx, ty);
+    }
   }
 }
 
@@ -420,7 +429,7 @@ int jaf_raster_fim_wim(const float* faces_xyz, int B, int F, int image_size, flo
   }
   k_raster_resolve<false, false><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
       zb, faces_xyz, nullptr, nullptr, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_, flip_rows,
-      fim, wim, depth, nullptr);
+      fim, wim, depth, nullptr, 0);
   return jaf::finish_launch("jaf_raster_fim_wim", launches + 1);
 }
 
@@ -441,7 +450,7 @@ int jaf_render_fim_wim(const float* cam, const float* verts, const int32_t* face
   }
   k_raster_resolve<true, false><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
       zb, nullptr, cam, verts, faces_idx, nullptr, nullptr, B, V, F, image_size, eye_z, near_, far_, 1, fim, wim,
-      nullptr, nullptr);
+      nullptr, nullptr, 0);
   return jaf::finish_launch("jaf_render_fim_wim", launches + 1);
 }
 
@@ -458,11 +467,11 @@ int jaf_flow_compose(const float* src_pts, int stride, int negate_y, const int32
   return jaf::finish_launch("k_flow_compose");
 }
 
-int jaf_cal_flow(const float* src_cam, const float* src_verts, const float* tgt_cam, const float* tgt_verts,
-                 const int32_t* faces_idx, int B, int V, int F, int image_size, float eye_z, float near_,
-                 float far_, float* T, int32_t* fim, float* wim, void* workspace, void* stream) {
+int jaf_cal_flow_multi(const float* src_cam, const float* src_verts, const float* tgt_cam, const float* tgt_verts,
+                       const int32_t* faces_idx, int B, int K, int V, int F, int image_size, float eye_z, float near_,
+                       float far_, float* T, int32_t* fim, float* wim, void* workspace, void* stream) {
   JAF_REQUIRE(src_cam && src_verts && tgt_cam && tgt_verts && faces_idx && T && workspace, "null pointer");
-  JAF_REQUIRE(check_raster_args(B, F, image_size) && V > 0, "bad sizes");
+  JAF_REQUIRE(check_raster_args(B, F, image_size) && V > 0 && K >= 1, "bad sizes");
   JAF_REQUIRE((reinterpret_cast<uintptr_t>(T) & 7u) == 0, "T must be 8-byte aligned");
   if (B == 0) return JAF_OK;
   cudaStream_t st = jaf::as_stream(stream);
@@ -476,8 +485,15 @@ int jaf_cal_flow(const float* src_cam, const float* src_verts, const float* tgt_
   }
   k_raster_resolve<true, true><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
       zb, nullptr, tgt_cam, tgt_verts, faces_idx, src_cam, src_verts, B, V, F, image_size, eye_z, near_, far_, 1,
-      fim, wim, nullptr, T);
+      fim, wim, nullptr, T, K);
   return jaf::finish_launch("jaf_cal_flow", launches + 1);
+}
+
+int jaf_cal_flow(const float* src_cam, const float* src_verts, const float* tgt_cam, const float* tgt_verts,
+                 const int32_t* faces_idx, int B, int V, int F, int image_size, float eye_z, float near_,
+                 float far_, float* T, int32_t* fim, float* wim, void* workspace, void* stream) {
+  return jaf_cal_flow_multi(src_cam, src_verts, tgt_cam, tgt_verts, faces_idx, B, 1, V, F, image_size, eye_z, near_,
+                            far_, T, fim, wim, workspace, stream);
 }
 
 }  // extern "C"

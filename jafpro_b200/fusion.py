@@ -17,3 +17,18 @@ def softmax_fuse(x_con, mask_logits):
 def to_channels_last_5d(feat):
     """[R,K,C,H,W] -> same logical tensor with channels-last strides (dense [R,K,H,W,C] memory)."""
     return feat.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+
+
+def warp_fuse_from_poses(renderer, src_cams, src_vertices, tgt_cam, tgt_vertices, rgb=None, feat=None, *,
+                         logits=None, tgt_mask=None, ref_index=None, align_corners: bool = False):
+    """The whole hot path in two steps on the device: transfer flows of the K reference poses into the
+    target pose (one raster of the target, K composes) and the fused warp + fusion with the default
+    visibility `target pixel is on the body` (fim != -1).  `renderer` is a jafpro_b200.nmr.SMPLRenderer.
+    src_cams [B,K,3], src_vertices [B,K,V,3], tgt_cam [B,3], tgt_vertices [B,V,3]; references as in warp_fuse.
+    Returns (out_rgb, out_feat, T, fim)."""
+    T, fim, _ = ops.cal_flow_multi(src_cams.contiguous(), src_vertices.contiguous(), tgt_cam.contiguous(),
+                                   tgt_vertices.contiguous(), renderer.faces, renderer.image_size,
+                                   eye_z=renderer._eye_z)
+    out_rgb, out_feat = ops.warp_fuse(T, rgb=rgb, feat=feat, logits=logits, fim=fim, tgt_mask=tgt_mask,
+                                      ref_index=ref_index, align_corners=align_corners)
+    return out_rgb, out_feat, T, fim

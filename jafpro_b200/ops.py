@@ -403,3 +403,28 @@ def texture_warp(tex_parts, iuv, align_corners: bool = False):
         _lib.check(_lib.lib().jaf_texture_warp(_ptr(tex), P, Ht, Wt, _ptr(iuv), B, H, W, int(bool(align_corners)),
                                                _ptr(out), _stream()), "texture_warp")
     return out
+
+
+# ----------------------------------------------------------------------------- a8 for K references
+def cal_flow_multi(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx, image_size: int, eye_z: float = EYE_Z,
+                   near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR, return_maps: bool = True):
+    """Transfer flows from K source poses into one target pose per frame: the target is rasterised once,
+    composed K times.  src_cam [B,K,3], src_vertices [B,K,V,3], tgt_cam [B,3], tgt_vertices [B,V,3]
+    -> T [B,K,S,S,2] (+ fim [B,S,S], wim [B,S,S,3])."""
+    sc, sv = _check(src_cam, "src_cam", torch.float32), _check(src_vertices, "src_vertices", torch.float32)
+    tc, tv = _check(tgt_cam, "tgt_cam", torch.float32), _check(tgt_vertices, "tgt_vertices", torch.float32)
+    faces_idx = _check(faces_idx, "faces", torch.int32)
+    if sv.dim() != 4 or sc.dim() != 3 or sv.shape[:2] != sc.shape[:2] or sv.shape[0] != tv.shape[0]:
+        raise RuntimeError("expected src_cam [B,K,3], src_vertices [B,K,V,3], tgt_cam [B,3], tgt_vertices [B,V,3]")
+    B, K, V, _ = sv.shape
+    F = faces_idx.shape[-2]
+    dev = tv.device
+    T = torch.empty((B, K, image_size, image_size, 2), dtype=torch.float32, device=dev)
+    fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=dev) if return_maps else None
+    wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev) if return_maps else None
+    with _on(dev):
+        ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, image_size))
+        _lib.check(_lib.lib().jaf_cal_flow_multi(_ptr(sc), _ptr(sv), _ptr(tc), _ptr(tv), _ptr(faces_idx), B, K, V, F,
+                                                 image_size, eye_z, near, far, _ptr(T), _ptr(fim), _ptr(wim), _ptr(ws),
+                                                 _stream()), "cal_flow_multi")
+    return (T, fim, wim) if return_maps else T

@@ -545,3 +545,37 @@ def test_texture_warp_matches_reference_and_oracle(golden_dir, align_corners):
     iuv[..., 0] = rng.integers(0, 26, (4, 256, 256))  # includes an out-of-range part id (25)
     out = ops.texture_warp(_cu(tex), _cu(iuv), align_corners)
     assert np.array_equal(_bits(out), oracle.texture_warp(tex, iuv, align_corners).view(np.int32))
+
+
+def test_cal_flow_multi_equals_per_pair_cal_flow_and_feeds_warp_fuse():
+    """K source poses -> one target raster: bit-identical to the reference-shaped per-pair call, and the
+    two-step device pipeline (flows + fused warp) matches the oracle end to end."""
+    from jafpro_b200.fusion import warp_fuse_from_poses
+    _, faces_idx = load_smpl_template()
+    B, K, S = 2, 3, 96
+    cam, verts = synth.smpl_poses(B * (K + 1), seed=21)
+    tcam, tverts = cam[:B].contiguous(), verts[:B].contiguous()
+    scam = cam[B:].reshape(B, K, 3).contiguous()
+    sverts = verts[B:].reshape(B, K, -1, 3).contiguous()
+    f_idx = _cu(faces_idx)
+    T, fim, wim = ops.cal_flow_multi(scam.to(DEV), sverts.to(DEV), tcam.to(DEV), tverts.to(DEV), f_idx, S)
+    for k in range(K):
+        Tk, fk, wk = ops.cal_flow(scam[:, k].contiguous().to(DEV), sverts[:, k].contiguous().to(DEV), tcam.to(DEV),
+                                  tverts.to(DEV), f_idx, S, return_maps=True)
+        assert torch.equal(T[:, k], Tk) and torch.equal(fim, fk) and torch.equal(wim, wk)
+        oT, ofim, _ = oracle.cal_flow(scam[:, k].numpy(), sverts[:, k].numpy(), tcam.numpy(), tverts.numpy(), faces_idx, S)
+        assert np.array_equal(_bits(T[:, k]), oT.view(np.int32)) and np.array_equal(_np(fim), ofim)
+    rend = SMPLRenderer(image_size=S).to(DEV)
+    rgb, feat = synth.reference_sets(B, K, 64, S, S, seed=4, device=DEV)
+    logits = torch.randn(B, K, S, S, device=DEV)
+    out_rgb, out_feat, T2, fim2 = warp_fuse_from_poses(rend, scam.to(DEV), sverts.to(DEV), tcam.to(DEV), tverts.to(DEV),
+                                                       rgb=rgb, feat=feat, logits=logits)
+    assert torch.equal(T2, T) and torch.equal(fim2, fim)
+    fb = _bf16_bits(feat.permute(0, 1, 3, 4, 2).contiguous())
+    o = oracle.warp_fuse(_np(T), rgb=_np(rgb), feat=fb, feat_layout="nhwc", feat_bf16=True, logits=_np(logits),
+                         fim=_np(fim))
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 2e-6
+    ok, frac = _bf16_close(_bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
+    assert ok and frac < 2e-3
+    bg = _np(fim) == -1
+    assert float(np.abs(_np(out_rgb).transpose(0, 2, 3, 1)[bg]).max()) == 0.0  # background stays empty
