@@ -218,6 +218,25 @@ int jaf_convlstm_step_tc(const void* x, const void* h, const float* c, const voi
                          float* c_out, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * a13  G independent reference-sized cells in ONE launch, on the tensor cores with
+ * fp32-grade accuracy (split-bf16: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM).
+ * replaces: the 24 part-specific cells of one pyramid level of Accumulate_LSTM_no_loss
+ *           (src/networks.py:1304-1313,:1346-1355,:1641-1662 — 24 x ConvLSTMCell.forward,
+ *           src/convLSTM.py:41-56, each its own cuDNN conv + 11 elementwise launches).
+ * Reference layout and dtype throughout: x [G,B,Cin,H,W], h, c, h_out, c_out
+ * [G,B,Ch,H,W] f32; weight [G,4Ch,Cin+Ch,3,3] f32 repacked once by
+ * jaf_convlstm_gpack_weight into `wpack` (jaf_convlstm_gpack_bytes bytes); bias [G,4Ch]
+ * f32 or NULL.  3x3 kernel, pad 1.  G = 1 is the plain cell.  Requirements: Ch % 4 == 0
+ * (Ch % 8 == 0 above 64), Ch <= 128.
+ * --------------------------------------------------------------------------------- */
+size_t jaf_convlstm_gpack_bytes(int G, int Cin, int Ch);
+int jaf_convlstm_gpack_weight(const float* weight, int G, int Cin, int Ch, void* wpack,
+                              void* stream);
+int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, const void* wpack,
+                              const float* bias, int G, int B, int Cin, int Ch, int H, int W,
+                              float* h_out, float* c_out, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * SURVEY §8f rank 1  IUV texture lookup
  * replaces: texture_warp_pytorch (test/conv_pro_test.py:41-74; train/4.convLSTM_flowpro_interval.py:43-76):
  *           24 x (torch.where x2, grid build, F.grid_sample of one part texture with zero padding,

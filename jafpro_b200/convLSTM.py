@@ -110,3 +110,53 @@ class ConvLSTMCellTC(nn.Module):
     def forward(self, x_nhwc, prev_state):
         h, c = prev_state
         return ops.convlstm_step_tc(x_nhwc, h, c, self.wpack, self.bias, self.input_dim, self.hidden_dim)
+
+
+class ConvLSTMGrouped(nn.Module):
+    """G independent reference-sized ConvLSTM layers advanced together, one launch per recurrent step: the 24
+    part-specific ``ConvLSTM`` modules of one pyramid level of ``Downsampler_convLSTM`` inside
+    ``Accumulate_LSTM_no_loss`` (src/networks.py:1304-1313,:1346-1355,:1641-1662).  fp32 in / out in the reference
+    layout; tensor cores with split-bf16 arithmetic (abs. error ~3e-5, within the 1e-4 fp32 bound).
+    Build it from the G single-layer (reference or drop-in) ``ConvLSTM`` modules with ``from_lstms``; weights are
+    repacked once."""
+
+    def __init__(self, input_dim, hidden_dim, weight, bias):
+        super().__init__()
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
+        self.groups = weight.shape[0]
+        self.register_buffer('wpack', ops.convlstm_gpack_weight(weight.detach().float().contiguous(), input_dim,
+                                                                hidden_dim))
+        self.register_buffer('bias', None if bias is None else bias.detach().float().contiguous())
+
+    @classmethod
+    def from_lstms(cls, lstms):
+        cells = [m.cell_list[0] if hasattr(m, 'cell_list') else m for m in lstms]
+        c0 = cells[0]
+        if any(len(getattr(m, 'cell_list', [None])) != 1 for m in lstms):
+            raise ValueError('ConvLSTMGrouped groups single-layer ConvLSTM modules')
+        if any((c.input_dim, c.hidden_dim) != (c0.input_dim, c0.hidden_dim) or tuple(c.kernel_size) != (3, 3)
+               for c in cells):
+            raise ValueError('all grouped cells need the same channel counts and a 3x3 kernel')
+        weight = torch.stack([c.conv.weight for c in cells])
+        bias = None if c0.conv.bias is None else torch.stack([c.conv.bias for c in cells])
+        return cls(c0.input_dim, c0.hidden_dim, weight, bias)
+
+    def step(self, x, prev_state):
+        """x [G,B,Cin,H,W], (h, c) [G,B,Ch,H,W] -> (h_next, c_next)."""
+        h, c = prev_state
+        return ops.convlstm_step_grouped(x.contiguous(), h.contiguous(), c.contiguous(), self.wpack, self.bias,
+                                         self.input_dim, self.hidden_dim)
+
+    def forward(self, input, hidden_state=None):
+        """input [G,B,T,Cin,H,W] (the batch_first stacks x*_con of networks.py:1340-1344, one per part)
+        -> (outputs [G,B,T,Ch,H,W], (h_last, c_last)); zero initial state like ConvLSTM.forward."""
+        G, B, T, _, H, W = input.shape
+        if hidden_state is None:
+            z = torch.zeros(G, B, self.hidden_dim, H, W, device=input.device)
+            hidden_state = (z, z.clone())
+        h, c = hidden_state
+        outs = []
+        for t in range(T):
+            h, c = self.step(input[:, :, t], (h, c))
+            outs.append(h)
+        return torch.stack(outs, dim=2), (h, c)

@@ -1,0 +1,506 @@
+// Reference-sized ConvLSTM cells on the tensor cores, G independent cells per launch (row a13 at the shapes
+// the reference really runs: Accumulate_LSTM_no_loss builds 24 part-specific Downsampler_convLSTM stacks with
+// cells of 12/24/24/48/96 channels on 200^2 ... 13^2 maps, src/networks.py:1290-1355,:1641-1662; one cell
+// step is src/convLSTM.py:41-56).  fp32 in, fp32 out, reference (NCHW) layout, fp32-grade accuracy:
+//
+// * Split-bf16 arithmetic: every fp32 operand is written as hi + lo (two bf16 numbers, 16 mantissa bits
+//   together) and the product is accumulated as hi*hi + hi*lo + lo*hi in fp32 TMEM accumulators — three
+//   tcgen05.mma kind::f16 per k-step instead of one, relative error per product ~2^-17.
+// * Implicit GEMM without im2col by flattening the ZERO-PADDED image: with p = (y+1)*(W+2) + (x+1) a 3x3 tap
+//   is the constant row shift (ky-1)*(W+2) + (kx-1), so ONE shared-memory copy of the rows
+//   [p0 - (W+3), p0 + 128*MT + (W+3)) x channels serves all nine taps: the A descriptor of a tap is the same
+//   buffer with a different start address.  That needs rows at a uniform 16-byte pitch, i.e. the
+//   no-swizzle K-major canonical layout [channel chunk of 8][row][16 B] with SBO = 128 B and
+//   LBO = rows * 16 B.  Outputs computed for the two padding columns of each row are discarded.
+//   The batch is flattened into the same index (padded images stacked), so tiles may straddle images.
+// * The fp32 NCHW activations (x for channels < Cin, h above: the cat of :43 never exists) are read
+//   coalesced along x, split to hi/lo bf16 in registers and stored with conflict-free 16-byte stores.
+// * Weights are repacked once per model (jaf_convlstm_gpack_weight) into the exact shared-memory image of
+//   the B operand, hi and lo, in k-step order; stages of KS k-steps stream through a 3-slot ring with
+//   cp.async.bulk + mbarrier while the MMAs of the previous stage run.
+// * MT accumulator tiles (128 pixels x 4*Ch gate channels each) live in TMEM at once; the epilogue reads
+//   them with tcgen05.ld (thread = pixel, so global accesses are coalesced in NCHW), adds the bias and applies
+//   the gates (:46-54) without the 4*Ch pre-activation tensor ever reaching HBM.
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace jaf::tc;
+
+constexpr int kThreads = 1024;  // warp 0: weight stream + MMA issue; the other warps: staging + epilogue
+constexpr int kThreadsHalf = 512;  // two CTAs per SM (64 registers per thread either way)
+constexpr int kHalfSmem = 112 * 1024;
+constexpr int kRing = 3;        // weight stages in flight
+constexpr int kMaxSmem = 232448 - 1024;
+
+struct GArgs {
+  const float* x;
+  const float* h;
+  const float* c;
+  const float* bias;
+  const uint8_t* wpack;
+  float* h_out;
+  float* c_out;
+  int G, B, Cin, Ch, H, W;
+  int Wp, HpWp;      // padded row pitch, padded image size
+  long Q;            // B * HpWp flattened padded positions per group
+  int Ct, Ctp, N, nsplit, Nsub;
+  int MT, R;         // accumulator tiles per CTA, staged rows
+  int S, KS, nstages;
+  int tiles_per_group;
+  uint32_t idesc, a_half, stage_bytes, tmem_cols;
+};
+
+// no-swizzle K-major matrix descriptor: rows at a 16-byte pitch (SBO = 128 B per 8 rows), the two 8-element
+// K chunks of one k-step `lbo` bytes apart
+__device__ __forceinline__ uint64_t desc_noswz(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// Issued from warp-uniform code under elect_one(): ptxas then knows exactly one thread is active and moves the
+// operands to uniform registers directly.  (Under a plain divergent `if (lane == 0)` it wraps every UTCHMMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop, ~120 cycles per instruction — measured — which bounds small-N MMAs.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred px;\n"
+      "elect.sync _|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// The three split products of one k-step into one accumulator: hi*hi, hi*lo, lo*hi.  Only the low words of the
+// descriptors vary (start address >> 4); the high words are loop invariants, so the issuing thread moves five
+// values to uniform registers per group instead of twelve (R2UR latency is what bounds the issue rate).
+__device__ __forceinline__ void umma_split3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_top, uint32_t b_hi,
+                                            uint32_t b_lo, uint32_t b_top, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, t;\n"
+      ".reg .b64 dah, dal, dbh, dbl;\n"
+      "mov.b64 dah, {%1, %3};\n"
+      "mov.b64 dal, {%2, %3};\n"
+      "mov.b64 dbh, {%4, %6};\n"
+      "mov.b64 dbl, {%5, %6};\n"
+      "setp.ne.b32 p, %8, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %7, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %7, t;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %7, t;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_hi), "r"(a_lo), "r"(a_top), "r"(b_hi), "r"(b_lo), "r"(b_top), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(taddr));
+  v[0] = __uint_as_float(r0);
+  v[1] = __uint_as_float(r1);
+  v[2] = __uint_as_float(r2);
+  v[3] = __uint_as_float(r3);
+}
+// fp32 -> (hi, lo) bf16 pair; packs two consecutive channels per 32-bit word
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo = pack_bf16x2(ar, br);
+}
+
+#ifdef JAF_GROUPED_PROFILE
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PROF_STAMP(var) const unsigned long long var = gtime()
+#else
+#define PROF_STAMP(var)
+#endif
+
+// Warp 0: weight stream + MMA issue (one thread).  Warps 1..31: activation staging, then the gate epilogue
+// (warps 1..28: seven warps per TMEM lane quarter).
+__global__ void __launch_bounds__(kThreads, 1)
+k_convlstm_grouped(const GArgs a) {
+  PROF_STAMP(t_start);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* sA = smem;                       // [hi | lo] x [Ctp/8 chunks][R rows][16 B]
+  uint8_t* sB = smem + 2 * a.a_half;        // kRing x stage_bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kRing * a.stage_bytes);
+  uint64_t* full_bar = bars;                // [kRing]  bulk copy -> MMA
+  uint64_t* empty_bar = bars + kRing;       // [kRing]  MMA -> bulk copy
+  uint64_t* aready_bar = bars + 2 * kRing;  // staging -> MMA
+  uint64_t* tfull_bar = bars + 2 * kRing + 1;  // MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRing + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x / a.tiles_per_group, t = blockIdx.x % a.tiles_per_group;
+  const long p_end = a.Q - a.Wp - 1;                          // one past the last output position
+  const long p0 = (long)a.Wp + 1 + (long)t * a.MT * 128;      // first output position of this CTA
+  const int mt_here = (int)min((long)a.MT, (p_end - p0 + 127) / 128);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(aready_bar, blockDim.x - 32);
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(a.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);  // warp-uniform by construction
+
+  if (warp == 0) {
+    // ===================== weight stream + MMA issue (warp-uniform; lane 0 is the leader) =====================
+    // The issue rate of this single thread bounds the small-N MMAs, so everything is kept in descriptor
+    // units (16 B) and advanced with adds: a descriptor's low 14 bits are the start address >> 4.
+    {
+      const bool leader = lane == 0;  // == the lane elect.sync picks (lowest active), so commits track these MMAs
+      const uint8_t* wg = a.wpack + (size_t)g * a.S * 64 * a.N;
+      const uint32_t stage_bytes = a.stage_bytes;
+      const int nstages = a.nstages, KS = a.KS;
+      const int pre = min(kRing, nstages);
+      if (leader) {
+        for (int st = 0; st < pre; ++st) {
+          mbar_expect_tx(&full_bar[st], stage_bytes);
+          bulk_g2s(sB + (size_t)st * stage_bytes, wg + (size_t)st * stage_bytes, stage_bytes, &full_bar[st]);
+        }
+      }
+      const uint32_t N = (uint32_t)a.N, Nsub = (uint32_t)a.Nsub, R = (uint32_t)a.R, Wp = (uint32_t)a.Wp;
+      const uint32_t idesc = a.idesc;
+      const int nsplit = a.nsplit, spt = a.Ctp / 16;
+      const uint64_t ad0 = desc_noswz(smem_u32(sA), R * 16u), bd0 = desc_noswz(smem_u32(sB), N * 16u);
+      const uint32_t a_top = (uint32_t)(ad0 >> 32), b_top = (uint32_t)(bd0 >> 32);
+      const uint32_t a_hi0 = (uint32_t)ad0, a_lo_delta = a.a_half >> 4, b0 = (uint32_t)bd0;
+      const uint32_t stage_u = stage_bytes >> 4;
+      mbar_wait(aready_bar, 0);
+      tc_fence_after();
+      PROF_STAMP(t_aready);
+      int kc = 0, kx = 0, ky = 0;
+      uint32_t accf = 0;
+      for (int st = 0; st < nstages; ++st) {
+        const int slot = st % kRing;
+        mbar_wait(&full_bar[slot], (uint32_t)(st / kRing) & 1u);
+        tc_fence_after();
+        uint32_t bh = b0 + (uint32_t)slot * stage_u;
+        for (int j = 0; j < KS; ++j, bh += 4 * N) {
+          uint32_t ah = a_hi0 + (uint32_t)(kc * 2) * R + (uint32_t)ky * Wp + (uint32_t)kx;
+          uint32_t tm = tmem_base;
+          for (int m = 0; m < mt_here; ++m, ah += 128) {
+            uint32_t bhh = bh;
+            for (int hn = 0; hn < nsplit; ++hn, bhh += Nsub, tm += Nsub) {
+              if (elect_one()) umma_split3(tm, ah, ah + a_lo_delta, a_top, bhh, bhh + 2 * N, b_top, idesc, accf);
+            }
+          }
+          accf = 1u;
+          if (++kc == spt) {
+            kc = 0;
+            if (++kx == 3) {
+              kx = 0;
+              ++ky;
+            }
+          }
+        }
+        if (leader) umma_commit(&empty_bar[slot]);
+        // refill the slot of the PREVIOUS stage (its MMAs were issued a stage ago) with stage st-1+kRing
+        if (st >= 1 && st - 1 + kRing < nstages) {
+          const int ps = (st - 1) % kRing;
+          mbar_wait(&empty_bar[ps], (uint32_t)((st - 1) / kRing) & 1u);
+          if (leader) {
+            mbar_expect_tx(&full_bar[ps], stage_bytes);
+            bulk_g2s(sB + (size_t)ps * stage_bytes, wg + (size_t)(st - 1 + kRing) * stage_bytes, stage_bytes,
+                     &full_bar[ps]);
+          }
+        }
+      }
+      if (leader) umma_commit(tfull_bar);
+#ifdef JAF_GROUPED_PROFILE
+      PROF_STAMP(t_issued);
+      mbar_wait(tfull_bar, 0);
+      PROF_STAMP(t_done);
+      if (blockIdx.x == 0 && leader)
+        printf("cta %d: MT=%d R=%d KS=%d nstages=%d | staged at %llu ns, mma issued +%llu, mma done +%llu\n", blockIdx.x,
+               a.MT, a.R, a.KS, a.nstages, t_aready - t_start, t_issued - t_aready, t_done - t_aready);
+#endif
+    }
+  } else {
+    // ===================== stage the activation rows (31 warps) =====================
+    const size_t HW = (size_t)a.H * a.W;
+    {
+      const int wid = threadIdx.x - 32;
+      const long q0 = p0 - a.Wp - 1;
+      const int npairs = a.Ctp / 16;
+      const int items = a.R * npairs;  // (row, pair of 8-channel chunks): 16 independent loads in flight per thread
+      const int nworkers = (int)blockDim.x - 32;
+      for (int it = wid; it < items; it += nworkers) {
+        const int cp = it / a.R, i = it - cp * a.R;
+        const long q = q0 + i;
+        bool inside = q < a.Q;
+        size_t pix = 0;
+        int b = 0;
+        if (inside) {
+          b = (int)(q / a.HpWp);
+          const int rem = (int)(q - (long)b * a.HpWp);
+          const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
+          inside = xp >= 1 && xp <= a.W && yp >= 1 && yp <= a.H;
+          pix = (size_t)(yp - 1) * a.W + (size_t)(xp - 1);
+        }
+        const float* xb = a.x + ((size_t)g * a.B + b) * a.Cin * HW + pix;
+        const float* hb = a.h + ((size_t)g * a.B + b) * a.Ch * HW + pix;
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int ch = cp * 16 + e;
+          float val = 0.f;
+          if (inside && ch < a.Ct) val = ch < a.Cin ? __ldg(xb + (size_t)ch * HW) : __ldg(hb + (size_t)(ch - a.Cin) * HW);
+          v[e] = val;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint4 hi, lo;
+          split2(v[8 * u + 0], v[8 * u + 1], hi.x, lo.x);
+          split2(v[8 * u + 2], v[8 * u + 3], hi.y, lo.y);
+          split2(v[8 * u + 4], v[8 * u + 5], hi.z, lo.z);
+          split2(v[8 * u + 6], v[8 * u + 7], hi.w, lo.w);
+          uint8_t* dst = sA + ((size_t)(cp * 2 + u) * a.R + i) * 16;
+          *reinterpret_cast<uint4*>(dst) = hi;
+          *reinterpret_cast<uint4*>(dst + a.a_half) = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
+      mbar_arrive(aready_bar);
+    }
+    // ===================== epilogue: gates (thread = pixel; 7 warps per TMEM lane quarter) =====================
+    const int nsets = ((int)(blockDim.x >> 5) - 1) >> 2;  // epilogue warps per TMEM lane quarter (7 or 3)
+    if (warp <= 4 * nsets) {
+      const int qd = warp & 3, set = (warp - 1) >> 2;  // lane quarter this warp may read; which share of the items
+      const int nblk = a.Ch / 4;
+      const int nitems = mt_here * nblk;  // (accumulator tile, block of 4 hidden channels)
+      const float* bp = a.bias ? a.bias + (size_t)g * a.N : nullptr;
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      for (int it0 = set; it0 < nitems; it0 += 2 * nsets) {
+        // two items per pass so that two sets of TMEM / global loads overlap
+        float gi[2][4], gf[2][4], go[2][4], gg[2][4], cv[2][4];
+        size_t base[2];
+        bool valid[2];
+        int j0[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int it = it0 + nsets * u;
+          valid[u] = false;
+          base[u] = 0;
+          j0[u] = 0;
+          if (it < nitems) {  // warp-uniform
+            const int m = it / nblk;
+            j0[u] = (it - m * nblk) * 4;
+            const long p = p0 + (long)m * 128 + qd * 32 + lane;
+            bool ok = p < p_end;
+            if (ok) {
+              const int b = (int)(p / a.HpWp);
+              const int rem = (int)(p - (long)b * a.HpWp);
+              const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
+              ok = xp >= 1 && xp <= a.W && yp >= 1 && yp <= a.H;
+              base[u] = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)(xp - 1);
+            }
+            valid[u] = ok;
+            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(m * a.N + j0[u]);
+            tmem_ld4(taddr, gi[u]);
+            tmem_ld4(taddr + a.Ch, gf[u]);
+            tmem_ld4(taddr + 2 * a.Ch, go[u]);
+            tmem_ld4(taddr + 3 * a.Ch, gg[u]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cv[u][e] = ok ? __ldg(a.c + base[u] + (size_t)(j0[u] + e) * HW) : 0.f;
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!valid[u]) continue;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int ch = j0[u] + e;
+            float bi = 0.f, bf = 0.f, bo = 0.f, bg = 0.f;
+            if (bp) {
+              bi = __ldg(bp + ch);
+              bf = __ldg(bp + a.Ch + ch);
+              bo = __ldg(bp + 2 * a.Ch + ch);
+              bg = __ldg(bp + 3 * a.Ch + ch);
+            }
+            const float ig = sigmoid_f(gi[u][e] + bi), fg = sigmoid_f(gf[u][e] + bf), og = sigmoid_f(go[u][e] + bo);
+            const float g_ = tanh_f(gg[u][e] + bg);
+            const float cn = fg * cv[u][e] + ig * g_;  // src/convLSTM.py:53
+            const float hn = og * tanh_f(cn);          // :54
+            a.c_out[base[u] + (size_t)ch * HW] = cn;
+            a.h_out[base[u] + (size_t)ch * HW] = hn;
+          }
+        }
+      }
+    }
+  }
+
+#ifdef JAF_GROUPED_PROFILE
+  if (threadIdx.x == 32 && blockIdx.x == 0) {
+    PROF_STAMP(t_end);
+    printf("cta %d: epilogue warp 1 done at %llu ns after start\n", blockIdx.x, t_end - t_start);
+  }
+#endif
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
+  }
+}
+
+// weight [G][4Ch][Ct][3][3] f32 -> per group, per k-step (tap, 16 channels): [hi | lo] x [2 chunks][N rows][8 bf16]
+__global__ void __launch_bounds__(256)
+k_gpack_weight(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, int N, int Ct, int Ctp) {
+  const int spt = Ctp / 16, S = 9 * spt;
+  const size_t total = (size_t)G * S * 2 * N * 8;  // one thread per (g, step, chunk, n, e)
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int e = (int)(i % 8);
+  size_t r = i / 8;
+  const int n = (int)(r % N);
+  r /= N;
+  const int cc = (int)(r % 2);
+  r /= 2;
+  const int step = (int)(r % S);
+  const int g = (int)(r / S);
+  const int tap = step / spt, kc = step % spt;
+  const int ch = kc * 16 + cc * 8 + e;
+  const float v = ch < Ct ? w[(((size_t)g * N + n) * Ct + ch) * 9 + tap] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  uint8_t* stepb = wp + ((size_t)g * S + step) * 64 * N;
+  const size_t off = (size_t)cc * 16 * N + (size_t)n * 16 + (size_t)e * 2;
+  *reinterpret_cast<__nv_bfloat16*>(stepb + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(stepb + 32 * (size_t)N + off) = lo;
+}
+
+bool grouped_shape_ok(int Cin, int Ch) { return Cin > 0 && Ch > 0 && Ch % 4 == 0 && 4 * Ch <= 512 && ((4 * Ch <= 256) || (2 * Ch) % 16 == 0); }
+
+}  // namespace
+
+extern "C" {
+
+size_t jaf_convlstm_gpack_bytes(int G, int Cin, int Ch) {
+  if (G <= 0 || !grouped_shape_ok(Cin, Ch)) return 0;
+  const int Ctp = (Cin + Ch + 15) / 16 * 16;
+  return (size_t)G * 9 * (Ctp / 16) * 64 * (4 * Ch);
+}
+
+int jaf_convlstm_gpack_weight(const float* weight, int G, int Cin, int Ch, void* wpack, void* stream) {
+  JAF_REQUIRE(weight && wpack, "null pointer");
+  JAF_REQUIRE(G > 0 && grouped_shape_ok(Cin, Ch), "Ch must be a multiple of 4 and at most 128");
+  const int Ct = Cin + Ch, Ctp = (Ct + 15) / 16 * 16, N = 4 * Ch;
+  const size_t total = (size_t)G * 9 * (Ctp / 16) * 2 * N * 8;
+  k_gpack_weight<<<jaf::ceil_div((long)total, 256), 256, 0, jaf::as_stream(stream)>>>(
+      weight, static_cast<uint8_t*>(wpack), G, N, Ct, Ctp);
+  return jaf::finish_launch("k_gpack_weight");
+}
+
+int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, const void* wpack, const float* bias,
+                              int G, int B, int Cin, int Ch, int H, int W, float* h_out, float* c_out, void* stream) {
+  JAF_REQUIRE(x && h && c && wpack && h_out && c_out, "null pointer");
+  JAF_REQUIRE(G > 0 && B > 0 && H > 0 && W > 0, "bad sizes");
+  JAF_REQUIRE(grouped_shape_ok(Cin, Ch), "Ch must be a multiple of 4 and at most 128");
+  JAF_REQUIRE(((uintptr_t)wpack & 15) == 0, "wpack must be 16-byte aligned");
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    JAF_CUDA(cudaGetDevice(&dev));
+    JAF_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  }
+  GArgs a;
+  a.x = x; a.h = h; a.c = c; a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
+  a.h_out = h_out; a.c_out = c_out;
+  a.G = G; a.B = B; a.Cin = Cin; a.Ch = Ch; a.H = H; a.W = W;
+  a.Wp = W + 2;
+  a.HpWp = (H + 2) * (W + 2);
+  a.Q = (long)B * a.HpWp;
+  a.Ct = Cin + Ch;
+  a.Ctp = (a.Ct + 15) / 16 * 16;
+  a.N = 4 * Ch;
+  a.nsplit = a.N > 256 ? 2 : 1;
+  a.Nsub = a.N / a.nsplit;
+  a.S = 9 * (a.Ctp / 16);
+  // Two launch shapes.  "Half": 512 threads, <= 112 KB and <= 256 TMEM columns per CTA, so two CTAs share an SM and
+  // one stages / runs its epilogue while the other's MMAs execute.  "Full": 1024 threads, the whole SM, the largest
+  // MT (smallest halo overhead).  Half is used when it fits and the grid is more than one wave of it.
+  const long out_rows = a.Q - 2L * a.Wp - 2;
+  const int tiles_total = jaf::ceil_div(out_rows, 128);
+  auto plan = [&](long smem_cap, int col_cap, long stage_cap, int& KS, int& MT) {
+    KS = 1;
+    for (int ks = 1; ks <= a.S; ++ks)
+      if (a.S % ks == 0 && (long)ks * 64 * a.N <= stage_cap) KS = ks;
+    MT = 0;
+    for (int m = 1; m <= 8; ++m) {
+      const long R = (long)m * 128 + 2L * a.Wp + 2;
+      const long smem = 4L * a.Ctp * R + (long)kRing * KS * 64 * a.N + 256 + 128;
+      if ((long)m * a.N <= col_cap && smem <= smem_cap && m <= tiles_total) MT = m;
+    }
+  };
+  int ks_full, mt_full, ks_half, mt_half;
+  plan(kMaxSmem, 512, 28 * 1024, ks_full, mt_full);
+  plan(kHalfSmem, 256, 10 * 1024, ks_half, mt_half);
+  JAF_REQUIRE(mt_full >= 1, "cell does not fit shared memory (W or channel count too large)");
+  static const int forced_mode = [] {
+    const char* e = getenv("JAF_CG_MODE");
+    return e ? atoi(e) : 0;
+  }();
+  bool half = mt_half >= 1 && (long)G * jaf::ceil_div(tiles_total, mt_half) > sm_count;
+  if (forced_mode == 1) half = false;
+  if (forced_mode == 2 && mt_half >= 1) half = true;
+  int MT = half ? mt_half : mt_full;
+  a.KS = half ? ks_half : ks_full;
+  a.nstages = a.S / a.KS;
+  a.stage_bytes = (uint32_t)a.KS * 64u * (uint32_t)a.N;
+  // keep at least one CTA per SM
+  while (!half && MT > 1 && (long)G * jaf::ceil_div(tiles_total, MT) < sm_count) --MT;
+  a.MT = MT;
+  a.R = MT * 128 + 2 * a.Wp + 2;
+  a.a_half = (uint32_t)(a.Ctp / 8) * (uint32_t)a.R * 16u;
+  JAF_REQUIRE((uint32_t)a.R * 16u < (1u << 18), "row window too large for the descriptor");
+  a.tiles_per_group = jaf::ceil_div(tiles_total, MT);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(MT * a.N)) cols <<= 1;
+  a.tmem_cols = cols;
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Nsub >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const size_t smem = 2 * (size_t)a.a_half + (size_t)kRing * a.stage_bytes + 256 + 128;
+  const long grid = (long)G * a.tiles_per_group;
+  JAF_REQUIRE(grid < (1L << 31), "too many tiles");
+  k_convlstm_grouped<<<(unsigned)grid, half ? kThreadsHalf : kThreads, smem, jaf::as_stream(stream)>>>(a);
+  return jaf::finish_launch("k_convlstm_grouped");
+}
+
+}  // extern "C"

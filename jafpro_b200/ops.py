@@ -389,6 +389,39 @@ def convlstm_step_tc(x, h, c, wpack, bias, Cin: int, Ch: int):
     return h2, c2
 
 
+def convlstm_gpack_weight(weight, Cin: int, Ch: int):
+    """Repack G cell weights [G,4Ch,Cin+Ch,3,3] f32 (one-off) for `convlstm_step_grouped`."""
+    weight = _check(weight, "weight", torch.float32)
+    if weight.dim() != 5 or tuple(weight.shape[1:]) != (4 * Ch, Cin + Ch, 3, 3):
+        raise RuntimeError("expected weight [G,4Ch,Cin+Ch,3,3]")
+    G = weight.shape[0]
+    nbytes = _lib.lib().jaf_convlstm_gpack_bytes(G, Cin, Ch)
+    if nbytes == 0:
+        raise RuntimeError("grouped ConvLSTM: unsupported channel counts (Ch % 4 == 0, Ch <= 128)")
+    wpack = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    with _on(weight.device):
+        _lib.check(_lib.lib().jaf_convlstm_gpack_weight(_ptr(weight), G, Cin, Ch, _ptr(wpack), _stream()),
+                   "convlstm_gpack_weight")
+    return wpack
+
+
+def convlstm_step_grouped(x, h, c, wpack, bias, Cin: int, Ch: int):
+    """G independent ConvLSTM cells, one launch, tensor cores with split-bf16 (fp32-grade) arithmetic.
+    x [G,B,Cin,H,W], h, c [G,B,Ch,H,W] f32 (reference NCHW layout), bias [G,4Ch] or None -> (h_next, c_next)."""
+    x, h, c = _check(x, "x", torch.float32), _check(h, "h", torch.float32), _check(c, "c", torch.float32)
+    if bias is not None:
+        bias = _check(bias, "bias", torch.float32)
+    if x.dim() != 5 or h.shape != c.shape or x.shape[1] != h.shape[1] or x.shape[2] != Cin or h.shape[2] != Ch:
+        raise RuntimeError("expected x [G,B,Cin,H,W] and h, c [G,B,Ch,H,W]")
+    G, B, _, H, W = x.shape
+    h2, c2 = torch.empty_like(h), torch.empty_like(c)
+    with _on(x.device):
+        _lib.check(_lib.lib().jaf_convlstm_step_grouped(_ptr(x), _ptr(h), _ptr(c), _ptr(wpack), _ptr(bias), G, B, Cin,
+                                                        Ch, H, W, _ptr(h2), _ptr(c2), _stream()),
+                   "convlstm_step_grouped")
+    return h2, c2
+
+
 # ----------------------------------------------------------------------------- §8f rank 1
 def texture_warp(tex_parts, iuv, align_corners: bool = False):
     """IUV texture lookup (test/conv_pro_test.py:41-74).  tex_parts [P,3,Ht,Wt] f32, iuv [B,H,W,3] uint8

@@ -579,3 +579,51 @@ def test_cal_flow_multi_equals_per_pair_cal_flow_and_feeds_warp_fuse():
     assert ok and frac < 2e-3
     bg = _np(fim) == -1
     assert float(np.abs(_np(out_rgb).transpose(0, 2, 3, 1)[bg]).max()) == 0.0  # background stays empty
+
+
+# ------------------------------------------------------------------ a13: G reference-sized cells per launch (tcgen05, split-bf16)
+@pytest.mark.parametrize("G,B,Cin,Ch,H,W", [(1, 1, 12, 12, 20, 20), (3, 2, 12, 12, 50, 37), (2, 1, 24, 24, 100, 100),
+                                            (24, 1, 48, 48, 25, 25), (2, 3, 96, 96, 13, 13), (2, 1, 3, 12, 200, 200),
+                                            (1, 2, 20, 8, 9, 140)])
+def test_convlstm_grouped_cells_vs_fp64(G, B, Cin, Ch, H, W):
+    """Accumulate_LSTM_no_loss' per-part cells (src/networks.py:1304-1313: 12@200^2, 24@100^2, 24@50^2, 48@25^2,
+    96@13^2; 24 parts with their own weights) in one launch.  Tolerance: the fp32 bound of the north star, 1e-4."""
+    torch.manual_seed(G * 100 + Ch)
+    x, h, c = (torch.randn(G, B, n, H, W, device=DEV) for n in (Cin, Ch, Ch))
+    wgt = torch.randn(G, 4 * Ch, Cin + Ch, 3, 3, device=DEV) * (1.5 / (9 * (Cin + Ch)) ** 0.5)
+    bias = torch.randn(G, 4 * Ch, device=DEV)
+    wpack = ops.convlstm_gpack_weight(wgt, Cin, Ch)
+    for b_ in (bias, None):
+        h2, c2 = ops.convlstm_step_grouped(x, h, c, wpack, b_, Cin, Ch)
+        for g in range(G):
+            cc = F.conv2d(torch.cat((x[g], h[g]), 1).double(), wgt[g].double(), None if b_ is None else b_[g].double(), padding=1)
+            i, f, o, gg = torch.split(cc, Ch, dim=1)
+            c_r = torch.sigmoid(f) * c[g].double() + torch.sigmoid(i) * torch.tanh(gg)
+            h_r = torch.sigmoid(o) * torch.tanh(c_r)
+            ec, eh = float((c2[g].double() - c_r).abs().max()), float((h2[g].double() - h_r).abs().max())
+            assert ec <= 1e-4 and eh <= 1e-4, (g, ec, eh)
+    # the exact-fp32 CUDA-core cell agrees as well (same interface, G = 1 per call)
+    h3, c3 = ops.convlstm_step(x[0], h[0], c[0], wgt[0], None)
+    assert float((c3 - c2[0]).abs().max()) <= 1e-4 and float((h3 - h2[0]).abs().max()) <= 1e-4
+
+
+def test_convlstm_grouped_rejects_unsupported_shapes():
+    assert _lib.lib().jaf_convlstm_gpack_bytes(1, 12, 10) == 0   # Ch % 4
+    assert _lib.lib().jaf_convlstm_gpack_bytes(1, 12, 256) == 0  # 4*Ch > 512 TMEM columns
+    with pytest.raises(RuntimeError):
+        ops.convlstm_gpack_weight(torch.zeros(1, 40, 22, 3, 3, device=DEV), 12, 10)
+
+
+def test_convlstm_grouped_module_matches_per_part_lstms():
+    """24-part usage: ConvLSTMGrouped.from_lstms == running each part's ConvLSTM on its own (K = 3 steps)."""
+    from jafpro_b200.convLSTM import ConvLSTM, ConvLSTMGrouped
+    torch.manual_seed(5)
+    G, B, T, Ch, S = 4, 1, 3, 24, 50
+    lstms = [ConvLSTM((S, S), Ch, [Ch], [(3, 3)], 1, batch_first=True, bias=True).to(DEV) for _ in range(G)]
+    grouped = ConvLSTMGrouped.from_lstms(lstms)
+    x = torch.randn(G, B, T, Ch, S, S, device=DEV)
+    out, (h, c) = grouped(x)
+    for g in range(G):
+        o_ref, last = lstms[g](x[g])
+        assert float((out[g] - o_ref).abs().max()) <= 1e-4
+        assert float((h[g] - last[0][0]).abs().max()) <= 1e-4 and float((c[g] - last[0][1]).abs().max()) <= 1e-4
