@@ -202,6 +202,17 @@ int jaf_convlstm_step_f32(const float* x, const float* h, const float* c, const 
                           float* h_out, float* c_out, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * row F  per-reference visibility (optional `vis` input of jaf_warp_fuse)
+ * replaces: SMPLRenderer.get_vis_f2pts (src/nmr.py:507-546): faces absent from the SOURCE
+ *           pose's face-index map are invisible (the reference gives them the sentinel -2).
+ * fim_src [B,K,HW] i32 (face-index maps of the K reference poses), fim_tgt [B,HW] i32.
+ * seen [B,K,F] u8 (out): 1 if face f shows in fim_src[b,k].  vis [B,K,HW] f32 (out, optional
+ * together with fim_tgt): 1 where fim_tgt[b,p] >= 0 and that face is seen in reference k.
+ * --------------------------------------------------------------------------------- */
+int jaf_face_visibility(const int32_t* fim_src, const int32_t* fim_tgt, int B, int K, int HW, int F,
+                        uint8_t* seen, float* vis, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * a13  the same cell as a tensor-core implicit GEMM (tcgen05 + TMEM + TMA), for wide
  * cells (BASELINE config 4: Cin = Ch = 256, 64x64, B = 16).  3x3 kernel, pad 1.
  * Activations are channels-last bf16: x [B,H,W,Cin], h [B,H,W,Ch]; the cell state stays

@@ -47,6 +47,7 @@ SIGNATURES = {
     "jaf_mask_blend": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_softmax_fuse": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "jaf_convlstm_step_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "jaf_face_visibility": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_convlstm_wpack_bytes": (_sz, [_i, _i]),
     "jaf_convlstm_pack_weight": (_i, [_vp, _i, _i, _vp, _vp]),
     "jaf_convlstm_step_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

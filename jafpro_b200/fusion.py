@@ -19,16 +19,32 @@ def to_channels_last_5d(feat):
     return feat.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
 
 
+def reference_visibility(renderer, src_cams, src_vertices, fim_tgt):
+    """Per-reference visibility maps for `warp_fuse(vis=...)`: rasterise the K reference poses and apply the
+    reference's rule (get_vis_f2pts, src/nmr.py:507-546).  src_cams [B,K,3], src_vertices [B,K,V,3], fim_tgt [B,S,S]
+    -> vis [B,K,S,S] f32."""
+    B, K = src_cams.shape[:2]
+    S = renderer.image_size
+    _, fim_src, _ = ops.render_fim_wim(src_cams.reshape(B * K, 3).contiguous(),
+                                       src_vertices.reshape(B * K, -1, 3).contiguous(), renderer.faces, S,
+                                       eye_z=renderer._eye_z, return_faces=False)
+    _, vis = ops.face_visibility(fim_src.reshape(B, K, S, S), fim_tgt.contiguous(), renderer.faces.shape[-2])
+    return vis
+
+
 def warp_fuse_from_poses(renderer, src_cams, src_vertices, tgt_cam, tgt_vertices, rgb=None, feat=None, *,
-                         logits=None, tgt_mask=None, ref_index=None, align_corners: bool = False):
+                         logits=None, tgt_mask=None, ref_index=None, align_corners: bool = False,
+                         per_reference_visibility: bool = False):
     """The whole hot path in two steps on the device: transfer flows of the K reference poses into the
     target pose (one raster of the target, K composes) and the fused warp + fusion with the default
-    visibility `target pixel is on the body` (fim != -1).  `renderer` is a jafpro_b200.nmr.SMPLRenderer.
+    visibility `target pixel is on the body` (fim != -1), or with `per_reference_visibility` the reference's
+    get_vis_f2pts rule (the face under the target pixel must be visible in reference k).  `renderer` is a jafpro_b200.nmr.SMPLRenderer.
     src_cams [B,K,3], src_vertices [B,K,V,3], tgt_cam [B,3], tgt_vertices [B,V,3]; references as in warp_fuse.
     Returns (out_rgb, out_feat, T, fim)."""
     T, fim, _ = ops.cal_flow_multi(src_cams.contiguous(), src_vertices.contiguous(), tgt_cam.contiguous(),
                                    tgt_vertices.contiguous(), renderer.faces, renderer.image_size,
                                    eye_z=renderer._eye_z)
-    out_rgb, out_feat = ops.warp_fuse(T, rgb=rgb, feat=feat, logits=logits, fim=fim, tgt_mask=tgt_mask,
-                                      ref_index=ref_index, align_corners=align_corners)
+    vis = reference_visibility(renderer, src_cams, src_vertices, fim) if per_reference_visibility else None
+    out_rgb, out_feat = ops.warp_fuse(T, rgb=rgb, feat=feat, logits=logits, vis=vis, fim=None if vis is not None else fim,
+                                      tgt_mask=tgt_mask, ref_index=ref_index, align_corners=align_corners)
     return out_rgb, out_feat, T, fim

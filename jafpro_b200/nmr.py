@@ -77,6 +77,25 @@ class SMPLRenderer(nn.Module):
     def cal_bc_transform(self, src_f2pts, dst_fims, dst_wims):
         return ops.flow_compose(src_f2pts.contiguous(), dst_fims.contiguous(), dst_wims.contiguous())
 
+    # ---- src/nmr.py:507-546
+    @staticmethod
+    def get_vis_f2pts(f2pts, fims):
+        """Faces absent from `fims` get coordinates -2.  f2pts [bs,f,3,c] with fims [bs,H,W], or [f,3,c] with [H,W].
+        Like the reference, which drops the FIRST unique value of the fim assuming it is the background -1
+        (`fim.unique()[1:]`), an item without any background pixel also loses its lowest visible face."""
+        single = f2pts.dim() == 3
+        f2 = f2pts.unsqueeze(0) if single else f2pts
+        fm = (fims.unsqueeze(0) if single else fims).to(torch.int32).contiguous()
+        bs, nf = f2.shape[0], f2.shape[1]
+        seen, _ = ops.face_visibility(fm.unsqueeze(1), None, nf)
+        seen = seen[:, 0].bool()
+        no_bg = ~(fm == -1).flatten(1).any(1)
+        first = seen.int().argmax(1)  # lowest visible face
+        drop = no_bg & seen.any(1)
+        seen[torch.arange(bs, device=seen.device)[drop], first[drop]] = False
+        out = torch.where(seen[:, :, None, None], f2, torch.full_like(f2, -2.0))
+        return out[0] if single else out
+
     # ---- src/cal_flow.py:28-35 as one fused call (no source raster, no [B,F,3,3] round trip)
     def cal_flow(self, src_cam, src_vertices, tgt_cam, tgt_vertices, return_maps=False):
         return ops.cal_flow(src_cam.contiguous(), src_vertices.contiguous(), tgt_cam.contiguous(),

@@ -461,3 +461,26 @@ def cal_flow_multi(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx, imag
                                                  image_size, eye_z, near, far, _ptr(T), _ptr(fim), _ptr(wim), _ptr(ws),
                                                  _stream()), "cal_flow_multi")
     return (T, fim, wim) if return_maps else T
+
+
+# ----------------------------------------------------------------------------- row F: per-reference visibility
+def face_visibility(fim_src, fim_tgt, num_faces: int):
+    """The reference's visibility rule (SMPLRenderer.get_vis_f2pts, src/nmr.py:507-546) as data for `warp_fuse`:
+    fim_src [B,K,H,W] int32 (face-index maps of the K reference poses), fim_tgt [B,H,W] int32 or None
+    -> (seen [B,K,F] uint8, vis [B,K,H,W] f32 or None) with vis = 1 where the face shown by the target pixel is
+    visible in reference k."""
+    fim_src = _check(fim_src, "fim_src", torch.int32)
+    if fim_src.dim() != 4:
+        raise RuntimeError("expected fim_src [B,K,H,W]")
+    B, K, H, W = fim_src.shape
+    vis = None
+    if fim_tgt is not None:
+        fim_tgt = _check(fim_tgt, "fim_tgt", torch.int32)
+        if tuple(fim_tgt.shape) != (B, H, W):
+            raise RuntimeError("expected fim_tgt [B,H,W]")
+        vis = torch.empty((B, K, H, W), dtype=torch.float32, device=fim_src.device)
+    seen = torch.empty((B, K, num_faces), dtype=torch.uint8, device=fim_src.device)
+    with _on(fim_src.device):
+        _lib.check(_lib.lib().jaf_face_visibility(_ptr(fim_src), _ptr(fim_tgt), B, K, H * W, num_faces, _ptr(seen),
+                                                  _ptr(vis), _stream()), "face_visibility")
+    return seen, vis

@@ -316,3 +316,37 @@ def texture_warp(tex_parts, iuv, align_corners: bool = False):
     out = np.empty((B, 3, H, W), np.float32)
     lib().orc_texture_warp(_p(tex), P, Ht, Wt, _p(iuv), B, H, W, int(bool(align_corners)), _p(out))
     return out[0] if single else out
+
+
+def face_visibility(fim_src, fim_tgt, num_faces: int):
+    """Row F per-reference visibility, numpy restatement of the rule behind SMPLRenderer.get_vis_f2pts
+    (src/nmr.py:507-546): seen[b,k,f] = f in fim_src[b,k]; vis[b,k,p] = fim_tgt[b,p] >= 0 and seen[b,k,fim_tgt[b,p]]."""
+    fim_src = np.asarray(fim_src)
+    B, K = fim_src.shape[:2]
+    seen = np.zeros((B, K, num_faces), np.uint8)
+    for b in range(B):
+        for k in range(K):
+            ids = np.unique(fim_src[b, k])
+            ids = ids[(ids >= 0) & (ids < num_faces)]
+            seen[b, k, ids] = 1
+    if fim_tgt is None:
+        return seen, None
+    fim_tgt = np.asarray(fim_tgt)
+    vis = np.zeros(fim_src.shape, np.float32)
+    for b in range(B):
+        t = fim_tgt[b]
+        ok = (t >= 0) & (t < num_faces)
+        for k in range(K):
+            vis[b, k][ok] = seen[b, k][t[ok]]
+    return seen, vis
+
+
+def get_vis_f2pts(f2pts, fims):
+    """SMPLRenderer.get_vis_f2pts (src/nmr.py:507-546), including `fim.unique()[1:]` (:529): the FIRST unique value
+    is dropped whatever it is."""
+    f2pts, fims = np.asarray(f2pts, np.float32), np.asarray(fims)
+    out = np.full_like(f2pts, -2.0)
+    for b in range(f2pts.shape[0]):
+        ids = np.unique(fims[b])[1:]
+        out[b, ids] = f2pts[b, ids]
+    return out

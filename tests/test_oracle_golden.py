@@ -223,3 +223,17 @@ def test_texture_warp_matches_reference_function(golden_dir):
     # batched call == per-frame calls
     both = oracle.texture_warp(d["tex"], np.stack([d["iuv"], d["iuv"][::-1].copy()]))
     assert np.array_equal(both[0], out)
+
+
+def test_get_vis_f2pts_restatement_matches_the_reference_function(golden_dir):
+    """Fixture = SMPLRenderer.get_vis_f2pts (src/nmr.py:507-546) executed by tools/make_golden.py, one item with and
+    one without background pixels; the per-reference visibility rule of row F is derived from it."""
+    d = np.load(os.path.join(golden_dir, "vis_f2pts.npz"))
+    out = oracle.get_vis_f2pts(d["f2pts"], d["fim"])
+    assert np.array_equal(out, d["out"])
+    F = d["f2pts"].shape[1]
+    seen, vis = oracle.face_visibility(d["fim"][:, None], d["fim"], F)
+    # item 0 (has background): invisible faces <=> -2 rows of the reference output
+    assert np.array_equal(seen[0, 0] == 0, d["out"][0, :, 0, 0] == -2)
+    # every non-background target pixel of a pose is visible from the same pose
+    assert np.array_equal(vis[:, 0] == 1, d["fim"] >= 0)

@@ -20,6 +20,7 @@ Fixtures (all small, float32 unless noted):
   render_faces.npz     cam, verts -> `faces` exactly as SMPLRenderer.render_fim_wim builds them
                        (src/nmr.py:263-276, rasteriser stubbed out).
   bc_transform.npz     SMPLRenderer.cal_bc_transform (src/nmr.py:617-659) on a random fim/wim.
+  vis_f2pts.npz        SMPLRenderer.get_vis_f2pts (src/nmr.py:507-546) on random fims (with / without background).
   convlstm.npz         src/convLSTM.py ConvLSTMCell.forward and a 3-step ConvLSTM.forward.
   softmax_fuse.npz     src/networks.py Downsampler_mask.forward K-reduction (:1259-1286), captured
                        with forward hooks at the first scale.
@@ -222,6 +223,19 @@ def texture_warp():
     print("texture_warp:", tuple(out.shape))
 
 
+def vis_f2pts(nmr):
+    """SMPLRenderer.get_vis_f2pts (src/nmr.py:507-546): faces absent from a fim get coordinates -2.  Item 0 has
+    background pixels, item 1 has none (then `unique()[1:]` also drops the lowest visible face: a quirk we restate)."""
+    rng = np.random.default_rng(6)
+    B, F, S = 2, 60, 12
+    f2pts = rng.normal(0, 0.5, (B, F, 3, 2)).astype(np.float32)
+    fim = rng.integers(-1, F // 2, (B, S, S)).astype(np.int32)
+    fim[1][fim[1] == -1] = 7
+    out = nmr.SMPLRenderer.get_vis_f2pts(torch.from_numpy(f2pts), torch.from_numpy(fim))
+    np.savez_compressed(os.path.join(GOLD, "vis_f2pts.npz"), f2pts=f2pts, fim=fim, out=out.numpy())
+    print("vis_f2pts:", out.shape, "invisible faces:", int((out[..., 0, 0] == -2).sum()))
+
+
 def smpl_template():
     """mapper.txt `v` lines (6890 T-pose vertices) + smpl_faces.npy -> jafpro_b200/data/."""
     vs = []
@@ -246,6 +260,7 @@ if __name__ == "__main__":
     look_at(nr)
     nmr = render_faces(nr, v, f)
     bc_transform(nmr)
+    vis_f2pts(nmr)
     convlstm()
     softmax_fuse()
     mask_blend()
