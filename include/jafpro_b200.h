@@ -248,6 +248,19 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
                               float* h_out, float* c_out, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * SURVEY §8f rank 3  bidirectional multi-scale feature warp of SpatioTempoCRN
+ * replaces, per pyramid level (src/crn_model.py:457-566):
+ *   flow_s = F.interpolate(flow, size, mode='nearest')
+ *   out_fwd = F.grid_sample(feat_fwd, (grid + flow_s).permute(0,2,3,1), padding_mode='border')
+ *   out_bwd = F.grid_sample(feat_bwd, (grid - flow_s).permute(0,2,3,1), padding_mode='border')
+ * feat_fwd / feat_bwd / out_* [B,C,h,w] f32 (either pair may be NULL); base_grid [B,2,h,w]
+ * (channel 0 = x, 1 = y, the `grid_list[i]` input); flow [B,2,H,W] at full resolution.
+ * --------------------------------------------------------------------------------- */
+int jaf_flow_warp_pair(const float* feat_fwd, const float* feat_bwd, const float* base_grid,
+                       const float* flow, int B, int C, int h, int w, int H, int W, int align_corners,
+                       float* out_fwd, float* out_bwd, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * SURVEY §8f rank 1  IUV texture lookup
  * replaces: texture_warp_pytorch (test/conv_pro_test.py:41-74; train/4.convLSTM_flowpro_interval.py:43-76):
  *           24 x (torch.where x2, grid build, F.grid_sample of one part texture with zero padding,

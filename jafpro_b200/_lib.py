@@ -54,6 +54,7 @@ SIGNATURES = {
     "jaf_convlstm_gpack_bytes": (_sz, [_i, _i, _i]),
     "jaf_convlstm_gpack_weight": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "jaf_convlstm_step_grouped": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "jaf_flow_warp_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_texture_warp": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
 

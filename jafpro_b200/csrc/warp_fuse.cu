@@ -574,6 +574,65 @@ k_warp_fuse_generic(const WFArgs a) {
   }
 }
 
+// =====================================================================================
+// the bidirectional multi-scale feature warps of SpatioTempoCRN.forward
+// (src/crn_model.py:457-566).  Per pyramid level the reference runs
+//   flow_s = F.interpolate(flow, size, mode='nearest');  a = grid_sample(prev_pool, (grid + flow_s).permute(0,2,3,1), border)
+//                                                        b = grid_sample(pool,      (grid - flow_s).permute(0,2,3,1), border)
+// i.e. interpolate + 2 adds + 2 permutes + 2 grid_samples; here one thread per (pixel, channel slice) reads the
+// base grid and the full-resolution flow once (nearest index floor(dst * in/out), ATen's
+// nearest_neighbor_compute_source_index) and writes both warps.
+// =====================================================================================
+struct PairArgs {
+  const float* feat_fwd;  // warped with grid + flow
+  const float* feat_bwd;  // warped with grid - flow
+  const float* base_grid; // [B,2,h,w]  channel 0 = x, 1 = y
+  const float* flow;      // [B,2,H,W]
+  float* out_fwd;
+  float* out_bwd;
+  int B, C, h, w, H, W, align_corners, c_chunk;
+  float scale_y, scale_x;
+};
+
+__global__ void __launch_bounds__(256)
+k_flow_warp_pair(const PairArgs a) {
+  const long hw = (long)a.h * a.w, HWf = (long)a.H * a.W;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)a.B * hw) return;
+  const int b = (int)(i / hw);
+  const int pix = (int)(i - (long)b * hw);
+  const int y = pix / a.w, x = pix - y * a.w;
+  // nearest source index: min(floor(dst * scale), in - 1) with scale = in / out in fp32
+  const int ys = min((int)floorf(__fmul_rn((float)y, a.scale_y)), a.H - 1);
+  const int xs = min((int)floorf(__fmul_rn((float)x, a.scale_x)), a.W - 1);
+  const float fx = ld_stream_f32(a.flow + ((long)b * 2 + 0) * HWf + (long)ys * a.W + xs);
+  const float fy = ld_stream_f32(a.flow + ((long)b * 2 + 1) * HWf + (long)ys * a.W + xs);
+  const float gx = ld_stream_f32(a.base_grid + ((long)b * 2 + 0) * hw + pix);
+  const float gy = ld_stream_f32(a.base_grid + ((long)b * 2 + 1) * hw + pix);
+  const Tap tf = make_tap(__fadd_rn(gx, fx), __fadd_rn(gy, fy), a.w, a.h, a.align_corners);
+  const Tap tb = make_tap(__fsub_rn(gx, fx), __fsub_rn(gy, fy), a.w, a.h, a.align_corners);
+  const int c0 = (int)blockIdx.y * a.c_chunk, c1 = min(a.C, c0 + a.c_chunk);
+  for (int c = c0; c < c1; ++c) {
+    const long plane = ((long)b * a.C + c) * hw;
+    if (a.feat_fwd) {
+      const float* p = a.feat_fwd + plane + tf.off;
+      float s = fmaf(__ldg(p), tf.nw, 0.f);
+      s = fmaf(__ldg(p + tf.dx), tf.ne, s);
+      s = fmaf(__ldg(p + tf.dy), tf.sw, s);
+      s = fmaf(__ldg(p + tf.dy + tf.dx), tf.se, s);
+      st_stream_f32(a.out_fwd + plane + pix, s);
+    }
+    if (a.feat_bwd) {
+      const float* p = a.feat_bwd + plane + tb.off;
+      float s = fmaf(__ldg(p), tb.nw, 0.f);
+      s = fmaf(__ldg(p + tb.dx), tb.ne, s);
+      s = fmaf(__ldg(p + tb.dy), tb.sw, s);
+      s = fmaf(__ldg(p + tb.dy + tb.dx), tb.se, s);
+      st_stream_f32(a.out_bwd + plane + pix, s);
+    }
+  }
+}
+
 int wf_env(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -749,4 +808,29 @@ extern "C" int jaf_warp_image(const float* src, const float* grid, int N, int C,
   }
   p.stream = stream;
   return jaf_warp_fuse(&p);
+}
+
+
+extern "C" int jaf_flow_warp_pair(const float* feat_fwd, const float* feat_bwd, const float* base_grid, const float* flow,
+                                  int B, int C, int h, int w, int H, int W, int align_corners, float* out_fwd,
+                                  float* out_bwd, void* stream) {
+  JAF_REQUIRE(base_grid && flow, "null pointer");
+  JAF_REQUIRE((feat_fwd == nullptr) == (out_fwd == nullptr) && (feat_bwd == nullptr) == (out_bwd == nullptr),
+              "each feature tensor needs its output");
+  JAF_REQUIRE(feat_fwd || feat_bwd, "nothing to warp");
+  JAF_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "bad sizes");
+  PairArgs a;
+  a.feat_fwd = feat_fwd; a.feat_bwd = feat_bwd; a.base_grid = base_grid; a.flow = flow;
+  a.out_fwd = out_fwd; a.out_bwd = out_bwd;
+  a.B = B; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.align_corners = align_corners;
+  a.scale_y = (float)H / (float)h;  // ATen compute_scales_value for mode='nearest' with an explicit size
+  a.scale_x = (float)W / (float)w;
+  // small maps with many channels: slice the channels over blockIdx.y so the grid still fills the GPU
+  const long pixels = (long)B * h * w;
+  int slices = 1;
+  while (slices < C && pixels * slices < 148L * 2048 && slices < 64) slices *= 2;
+  a.c_chunk = jaf::ceil_div(C, slices);
+  dim3 grid(jaf::ceil_div(pixels, 256), jaf::ceil_div(C, a.c_chunk));
+  k_flow_warp_pair<<<grid, 256, 0, jaf::as_stream(stream)>>>(a);
+  return jaf::finish_launch("k_flow_warp_pair");
 }

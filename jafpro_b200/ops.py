@@ -484,3 +484,30 @@ def face_visibility(fim_src, fim_tgt, num_faces: int):
         _lib.check(_lib.lib().jaf_face_visibility(_ptr(fim_src), _ptr(fim_tgt), B, K, H * W, num_faces, _ptr(seen),
                                                   _ptr(vis), _stream()), "face_visibility")
     return seen, vis
+
+
+# ----------------------------------------------------------------------------- §8f rank 3
+def flow_warp_pair(feat_fwd, feat_bwd, base_grid, flow, align_corners: bool = False):
+    """One pyramid level of SpatioTempoCRN.forward (src/crn_model.py:457-566): nearest-downsample `flow` [B,2,H,W]
+    to the feature resolution, warp `feat_fwd` with (grid + flow) and `feat_bwd` with (grid - flow), border padding.
+    feats [B,C,h,w] f32 (either may be None), base_grid [B,2,h,w] -> (out_fwd, out_bwd)."""
+    base_grid, flow = _check(base_grid, "grid", torch.float32), _check(flow, "flow", torch.float32)
+    ref = feat_fwd if feat_fwd is not None else feat_bwd
+    if ref is None:
+        raise RuntimeError("nothing to warp")
+    B, C, h, w = ref.shape
+    if tuple(base_grid.shape) != (B, 2, h, w) or flow.dim() != 4 or flow.shape[:2] != (B, 2):
+        raise RuntimeError("expected base_grid [B,2,h,w] and flow [B,2,H,W]")
+    outs = []
+    for f in (feat_fwd, feat_bwd):
+        if f is not None:
+            f = _check(f, "feat", torch.float32)
+            if tuple(f.shape) != (B, C, h, w):
+                raise RuntimeError("feature maps must share their shape")
+        outs.append(None if f is None else torch.empty_like(f))
+    H, W = flow.shape[2:]
+    with _on(ref.device):
+        _lib.check(_lib.lib().jaf_flow_warp_pair(_ptr(feat_fwd), _ptr(feat_bwd), _ptr(base_grid), _ptr(flow), B, C, h, w,
+                                                 H, W, int(bool(align_corners)), _ptr(outs[0]), _ptr(outs[1]),
+                                                 _stream()), "flow_warp_pair")
+    return outs[0], outs[1]

@@ -350,3 +350,25 @@ def get_vis_f2pts(f2pts, fims):
         ids = np.unique(fims[b])[1:]
         out[b, ids] = f2pts[b, ids]
     return out
+
+
+def flow_warp_pair(feat_fwd, feat_bwd, base_grid, flow, align_corners: bool = False):
+    """One level of SpatioTempoCRN.forward's warps (src/crn_model.py:457-466): F.interpolate(flow, size, 'nearest')
+    [source index min(floor(dst * float32(in/out)), in-1), ATen UpSample.h nearest_neighbor_compute_source_index],
+    grid +/- flow in fp32, permute, grid_sample border."""
+    base_grid, flow = np.asarray(base_grid, np.float32), np.asarray(flow, np.float32)
+    B, _, h, w = base_grid.shape
+    H, W = flow.shape[2:]
+    sy, sx = np.float32(H) / np.float32(h), np.float32(W) / np.float32(w)
+    ys = np.minimum(np.floor(np.arange(h, dtype=np.float32) * sy).astype(np.int64), H - 1)
+    xs = np.minimum(np.floor(np.arange(w, dtype=np.float32) * sx).astype(np.int64), W - 1)
+    flow_s = flow[:, :, ys][:, :, :, xs]
+    outs = []
+    for feat, sign in ((feat_fwd, 1.0), (feat_bwd, -1.0)):
+        if feat is None:
+            outs.append(None)
+            continue
+        g = (base_grid + np.float32(sign) * flow_s).astype(np.float32)
+        outs.append(grid_sample_border(np.asarray(feat, np.float32), np.ascontiguousarray(g.transpose(0, 2, 3, 1)),
+                                       align_corners))
+    return outs[0], outs[1]

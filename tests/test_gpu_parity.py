@@ -670,3 +670,25 @@ def test_warp_fuse_from_poses_with_per_reference_visibility():
     assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 2e-6
     ok, frac_bad = _bf16_close(_bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
     assert ok and frac_bad < 2e-3
+
+
+# ------------------------------------------------------------------ §8f rank 3: SpatioTempoCRN multi-scale warps
+@pytest.mark.parametrize("C,h,w,H,W,ac", [(64, 128, 128, 256, 256, False), (512, 16, 16, 256, 256, False),
+                                          (5, 13, 7, 50, 30, True), (3, 4, 4, 256, 256, False)])
+def test_flow_warp_pair_matches_oracle_and_torch(C, h, w, H, W, ac):
+    from jafpro_b200.crn_model import warp_level
+    torch.manual_seed(C + h)
+    B = 2
+    prev_pool, pool = torch.randn(B, C, h, w, device=DEV), torch.randn(B, C, h, w, device=DEV)
+    flow = torch.randn(B, 2, H, W, device=DEV) * 0.2
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, h, device=DEV), torch.linspace(-1, 1, w, device=DEV), indexing="ij")
+    grid = torch.stack([xs, ys])[None].expand(B, 2, h, w).contiguous()
+    w_prev, w_cur = warp_level(prev_pool, pool, grid, flow, align_corners=ac)
+    o_prev, o_cur = oracle.flow_warp_pair(_np(prev_pool), _np(pool), _np(grid), _np(flow), ac)
+    assert np.array_equal(_bits(w_prev), o_prev.view(np.int32)) and np.array_equal(_bits(w_cur), o_cur.view(np.int32))
+    fs = F.interpolate(flow, (h, w), mode="nearest")  # the reference's sequence on the GPU
+    t_prev = F.grid_sample(prev_pool, (grid + fs).permute(0, 2, 3, 1), padding_mode="border", align_corners=ac)
+    t_cur = F.grid_sample(pool, (grid - fs).permute(0, 2, 3, 1), padding_mode="border", align_corners=ac)
+    assert float((w_prev - t_prev).abs().max()) <= 1e-5 and float((w_cur - t_cur).abs().max()) <= 1e-5
+    only, none = warp_level(prev_pool, None, grid, flow, align_corners=ac)
+    assert none is None and torch.equal(only, w_prev)

@@ -237,3 +237,24 @@ def test_get_vis_f2pts_restatement_matches_the_reference_function(golden_dir):
     assert np.array_equal(seen[0, 0] == 0, d["out"][0, :, 0, 0] == -2)
     # every non-background target pixel of a pose is visible from the same pose
     assert np.array_equal(vis[:, 0] == 1, d["fim"] >= 0)
+
+
+@pytest.mark.parametrize("h,w,H,W", [(8, 8, 64, 64), (13, 7, 50, 30), (5, 9, 17, 40)])
+def test_flow_warp_pair_oracle_matches_torch_composition(h, w, H, W):
+    """The oracle of §8f rank 3 against the reference's own op sequence (src/crn_model.py:457-466) in torch on CPU:
+    the nearest-neighbour index must agree exactly (odd ratios included), the warp within grid_sample's 1e-5."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(h * w)
+    B, C = 2, 3
+    a, b = rng.normal(size=(2, B, C, h, w)).astype(np.float32)
+    flow = (rng.normal(size=(B, 2, H, W)) * 0.3).astype(np.float32)
+    ys, xs = np.meshgrid(np.linspace(-1, 1, h, dtype=np.float32), np.linspace(-1, 1, w, dtype=np.float32), indexing="ij")
+    grid = np.broadcast_to(np.stack([xs, ys])[None], (B, 2, h, w)).copy()
+    o_f, o_b = oracle.flow_warp_pair(a, b, grid, flow)
+    fs = F.interpolate(torch.from_numpy(flow), (h, w), mode="nearest")
+    t_f = F.grid_sample(torch.from_numpy(a), (torch.from_numpy(grid) + fs).permute(0, 2, 3, 1), padding_mode="border",
+                        align_corners=False)
+    t_b = F.grid_sample(torch.from_numpy(b), (torch.from_numpy(grid) - fs).permute(0, 2, 3, 1), padding_mode="border",
+                        align_corners=False)
+    assert float(np.abs(o_f - t_f.numpy()).max()) <= 1e-5 and float(np.abs(o_b - t_b.numpy()).max()) <= 1e-5
