@@ -272,6 +272,26 @@ int jaf_flow_warp_pair(const float* feat_fwd, const float* feat_bwd, const float
 int jaf_texture_warp(const float* tex_parts, int P, int Ht, int Wt, const uint8_t* iuv, int B, int H, int W,
                      int align_corners, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * SURVEY §8f rank 2  texture-space assembly around the ConvLSTM accumulation
+ * replaces: the part / reference slicing loops of test/conv_pro_test.py:209-217
+ *           (train/4.convLSTM_flowpro_interval.py:269-277), the common-area OR + masking of
+ *           :221-236, and the atlas re-assembly of src/networks.py:1685-1691.
+ * The atlas is rows x cols parts of ph x pw pixels (reference: 4 x 6 x 200 x 200 = 800 x 1200).
+ *   gather : atlas [B,Kmax,C,rows*ph,cols*pw], ref_index [K] i32 (the `random_index` frames)
+ *            -> out [rows*cols, K, B, C, ph, pw]  (per part = torch.cat(x_in[part], dim=0))
+ *   common_mask : parts [rows*cols, B, C, ph, pw] *= float(OR_z uint8(mask[b, ref[z]])) in place;
+ *            mask [B,Kmax,rows*ph,cols*pw] f32
+ *   scatter: parts [rows*cols, B, C, ph, pw] -> atlas [B, C, rows*ph, cols*pw]
+ * --------------------------------------------------------------------------------- */
+int jaf_texture_parts_gather(const float* atlas, const int32_t* ref_index, int B, int Kmax, int K, int C,
+                             int rows, int cols, int ph, int pw, float* out, void* stream);
+int jaf_texture_parts_common_mask(float* parts, const float* mask, const int32_t* ref_index, int B,
+                                  int Kmax, int K, int C, int rows, int cols, int ph, int pw,
+                                  void* stream);
+int jaf_texture_parts_scatter(const float* parts, int B, int C, int rows, int cols, int ph, int pw,
+                              float* atlas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

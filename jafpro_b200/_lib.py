@@ -56,6 +56,9 @@ SIGNATURES = {
     "jaf_convlstm_step_grouped": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_flow_warp_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_texture_warp": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "jaf_texture_parts_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "jaf_texture_parts_common_mask": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "jaf_texture_parts_scatter": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

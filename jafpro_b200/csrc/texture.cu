@@ -47,7 +47,110 @@ k_texture_warp(const float* __restrict__ tex, int P, int Ht, int Wt, const unsig
   for (int c = 0; c < 3; ++c) st_stream_f32(out + ((long)b * 3 + c) * HW + p, r[c]);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// texture-space assembly around Accumulate_LSTM_no_loss (test/conv_pro_test.py:209-239;
+// train/4.convLSTM_flowpro_interval.py:269-298).  The atlas is rows x cols parts of ph x pw pixels (4 x 6 x 200 x 200).
+//   gather : src_texture_im[:, ref[z], :, i*ph:(i+1)*ph, j*pw:(j+1)*pw] for every part and selected reference,
+//            already in the [K*B, C, ph, pw] order Downsampler_convLSTM's torch.cat(x, dim=0) builds
+//            (src/networks.py:1316) -> out [parts, K, B, C, ph, pw]                       (:209-217)
+//   mask   : common = OR_z uint8(src_mask_im[:, ref[z]]) as float, parts[p] *= common     (:221-236)
+//   scatter: texture_image[:, :, i*ph:.., j*pw:..] = parts[i*cols+j]                       (src/networks.py:1685-1691)
+// One thread per output element, x fastest: reads and writes are coalesced part-row segments.
+// ---------------------------------------------------------------------------------------------------
+struct AtlasGeom {
+  int B, Kmax, K, C, rows, cols, ph, pw;
+};
+
+__global__ void __launch_bounds__(256)
+k_parts_gather(const float* __restrict__ atlas, const int* __restrict__ ref, AtlasGeom g, long n, float* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long r = i;
+  const int x = (int)(r % g.pw); r /= g.pw;
+  const int y = (int)(r % g.ph); r /= g.ph;
+  const int c = (int)(r % g.C); r /= g.C;
+  const int b = (int)(r % g.B); r /= g.B;
+  const int z = (int)(r % g.K);
+  const int part = (int)(r / g.K);
+  const int pi = part / g.cols, pj = part % g.cols;
+  const long AW = (long)g.cols * g.pw, AH = (long)g.rows * g.ph;
+  const long src = ((((long)b * g.Kmax + __ldg(ref + z)) * g.C + c) * AH + (long)pi * g.ph + y) * AW + (long)pj * g.pw + x;
+  st_stream_f32(out + i, ld_stream_f32(atlas + src));
+}
+
+__global__ void __launch_bounds__(256)
+k_parts_common_mask(float* __restrict__ parts, const float* __restrict__ mask, const int* __restrict__ ref, AtlasGeom g,
+                    long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over [parts, B, ph, pw]: one mask value serves C channels
+  if (i >= n) return;
+  long r = i;
+  const int x = (int)(r % g.pw); r /= g.pw;
+  const int y = (int)(r % g.ph); r /= g.ph;
+  const int b = (int)(r % g.B);
+  const int part = (int)(r / g.B);
+  const int pi = part / g.cols, pj = part % g.cols;
+  const long AW = (long)g.cols * g.pw, AH = (long)g.rows * g.ph;
+  unsigned common = 0;
+  for (int z = 0; z < g.K; ++z) {
+    const float m = ld_stream_f32(mask + (((long)b * g.Kmax + __ldg(ref + z)) * AH + (long)pi * g.ph + y) * AW + (long)pj * g.pw + x);
+    common |= (unsigned)(unsigned char)(int)m;  // .byte(): truncate toward zero, keep the low 8 bits
+  }
+  const float cf = (float)common;
+  const long plane = (long)g.ph * g.pw;
+  float* p = parts + (((long)part * g.B + b) * g.C) * plane + (long)y * g.pw + x;
+  for (int c = 0; c < g.C; ++c) p[c * plane] *= cf;
+}
+
+__global__ void __launch_bounds__(256)
+k_parts_scatter(const float* __restrict__ parts, AtlasGeom g, long n, float* __restrict__ atlas) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over the atlas [B, C, AH, AW]
+  if (i >= n) return;
+  const long AW = (long)g.cols * g.pw, AH = (long)g.rows * g.ph;
+  long r = i;
+  const int ax = (int)(r % AW); r /= AW;
+  const int ay = (int)(r % AH); r /= AH;
+  const int c = (int)(r % g.C);
+  const int b = (int)(r / g.C);
+  const int part = (ay / g.ph) * g.cols + ax / g.pw;
+  const long src = ((((long)part * g.B + b) * g.C + c) * g.ph + ay % g.ph) * g.pw + ax % g.pw;
+  st_stream_f32(atlas + i, ld_stream_f32(parts + src));
+}
+
+bool geom_ok(const AtlasGeom& g) {
+  return g.B > 0 && g.Kmax > 0 && g.K > 0 && g.C > 0 && g.rows > 0 && g.cols > 0 && g.ph > 0 && g.pw > 0;
+}
+
 }  // namespace
+
+extern "C" int jaf_texture_parts_gather(const float* atlas, const int32_t* ref_index, int B, int Kmax, int K, int C,
+                                        int rows, int cols, int ph, int pw, float* out, void* stream) {
+  JAF_REQUIRE(atlas && ref_index && out, "null pointer");
+  const AtlasGeom g{B, Kmax, K, C, rows, cols, ph, pw};
+  JAF_REQUIRE(geom_ok(g), "bad sizes");
+  const long n = (long)rows * cols * K * B * C * ph * pw;
+  k_parts_gather<<<jaf::ceil_div(n, 256), 256, 0, jaf::as_stream(stream)>>>(atlas, ref_index, g, n, out);
+  return jaf::finish_launch("k_parts_gather");
+}
+
+extern "C" int jaf_texture_parts_common_mask(float* parts, const float* mask, const int32_t* ref_index, int B, int Kmax,
+                                             int K, int C, int rows, int cols, int ph, int pw, void* stream) {
+  JAF_REQUIRE(parts && mask && ref_index, "null pointer");
+  const AtlasGeom g{B, Kmax, K, C, rows, cols, ph, pw};
+  JAF_REQUIRE(geom_ok(g), "bad sizes");
+  const long n = (long)rows * cols * B * ph * pw;
+  k_parts_common_mask<<<jaf::ceil_div(n, 256), 256, 0, jaf::as_stream(stream)>>>(parts, mask, ref_index, g, n);
+  return jaf::finish_launch("k_parts_common_mask");
+}
+
+extern "C" int jaf_texture_parts_scatter(const float* parts, int B, int C, int rows, int cols, int ph, int pw,
+                                         float* atlas, void* stream) {
+  JAF_REQUIRE(parts && atlas, "null pointer");
+  const AtlasGeom g{B, 1, 1, C, rows, cols, ph, pw};
+  JAF_REQUIRE(geom_ok(g), "bad sizes");
+  const long n = (long)B * C * rows * ph * cols * pw;
+  k_parts_scatter<<<jaf::ceil_div(n, 256), 256, 0, jaf::as_stream(stream)>>>(parts, g, n, atlas);
+  return jaf::finish_launch("k_parts_scatter");
+}
 
 extern "C" int jaf_texture_warp(const float* tex_parts, int P, int Ht, int Wt, const uint8_t* iuv, int B, int H, int W,
                                 int align_corners, float* out, void* stream) {

@@ -511,3 +511,50 @@ def flow_warp_pair(feat_fwd, feat_bwd, base_grid, flow, align_corners: bool = Fa
                                                  H, W, int(bool(align_corners)), _ptr(outs[0]), _ptr(outs[1]),
                                                  _stream()), "flow_warp_pair")
     return outs[0], outs[1]
+
+
+# ----------------------------------------------------------------------------- §8f rank 2
+def _atlas_geom(AH, AW, rows, cols):
+    if AH % rows or AW % cols:
+        raise RuntimeError("atlas size must be a multiple of the part grid")
+    return AH // rows, AW // cols
+
+
+def texture_parts_gather(atlas, ref_index, rows: int = 4, cols: int = 6):
+    """atlas [B,Kmax,C,AH,AW] f32, ref_index [K] int32 -> [rows*cols, K, B, C, ph, pw] (test/conv_pro_test.py:209-217)."""
+    atlas, ref_index = _check(atlas, "atlas", torch.float32), _check(ref_index, "ref_index", torch.int32)
+    B, Kmax, C, AH, AW = atlas.shape
+    ph, pw = _atlas_geom(AH, AW, rows, cols)
+    K = ref_index.numel()
+    out = torch.empty((rows * cols, K, B, C, ph, pw), dtype=torch.float32, device=atlas.device)
+    with _on(atlas.device):
+        _lib.check(_lib.lib().jaf_texture_parts_gather(_ptr(atlas), _ptr(ref_index), B, Kmax, K, C, rows, cols, ph, pw,
+                                                       _ptr(out), _stream()), "texture_parts_gather")
+    return out
+
+
+def texture_parts_common_mask_(parts, mask, ref_index, rows: int = 4, cols: int = 6):
+    """In place: parts [rows*cols,B,C,ph,pw] *= float(OR_z uint8(mask[:, ref_index[z]])) (conv_pro_test.py:221-236)."""
+    parts, mask = _check(parts, "parts", torch.float32), _check(mask, "mask", torch.float32)
+    ref_index = _check(ref_index, "ref_index", torch.int32)
+    P, B, C, ph, pw = parts.shape
+    if P != rows * cols or tuple(mask.shape) != (B, mask.shape[1], rows * ph, cols * pw):
+        raise RuntimeError("expected parts [rows*cols,B,C,ph,pw] and mask [B,Kmax,rows*ph,cols*pw]")
+    with _on(parts.device):
+        _lib.check(_lib.lib().jaf_texture_parts_common_mask(_ptr(parts), _ptr(mask), _ptr(ref_index), B, mask.shape[1],
+                                                            ref_index.numel(), C, rows, cols, ph, pw, _stream()),
+                   "texture_parts_common_mask")
+    return parts
+
+
+def texture_parts_scatter(parts, rows: int = 4, cols: int = 6):
+    """parts [rows*cols,B,C,ph,pw] -> atlas [B,C,rows*ph,cols*pw] (src/networks.py:1685-1691)."""
+    parts = _check(parts, "parts", torch.float32)
+    P, B, C, ph, pw = parts.shape
+    if P != rows * cols:
+        raise RuntimeError("expected rows*cols parts")
+    atlas = torch.empty((B, C, rows * ph, cols * pw), dtype=torch.float32, device=parts.device)
+    with _on(parts.device):
+        _lib.check(_lib.lib().jaf_texture_parts_scatter(_ptr(parts), B, C, rows, cols, ph, pw, _ptr(atlas), _stream()),
+                   "texture_parts_scatter")
+    return atlas

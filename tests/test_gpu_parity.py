@@ -692,3 +692,49 @@ def test_flow_warp_pair_matches_oracle_and_torch(C, h, w, H, W, ac):
     assert float((w_prev - t_prev).abs().max()) <= 1e-5 and float((w_cur - t_cur).abs().max()) <= 1e-5
     only, none = warp_level(prev_pool, None, grid, flow, align_corners=ac)
     assert none is None and torch.equal(only, w_prev)
+
+
+# ------------------------------------------------------------------ §8f rank 2: texture-space assembly
+def test_texture_space_assembly_matches_the_reference_loops():
+    """The slicing / OR / masking / re-assembly loops of test/conv_pro_test.py:209-236 and src/networks.py:1685-1691,
+    written here exactly as the reference writes them (torch slicing), against the one-launch kernels."""
+    from jafpro_b200.texture import assemble_atlas, gather_parts, mask_common_area_
+    torch.manual_seed(2)
+    B, Kmax, ph, pw = 2, 5, 20, 12  # the reference: B=1, Kmax=5, 200x200 parts; smaller parts keep the test quick
+    src_texture_im = torch.randn(B, Kmax, 3, 4 * ph, 6 * pw, device=DEV)
+    src_mask_im = (torch.rand(B, Kmax, 4 * ph, 6 * pw, device=DEV) > 0.7).float()
+    random_index = np.array([0, 2, 3])
+    # :209-217
+    ref_in = []
+    for i in range(4):
+        for j in range(6):
+            ref_in.append([src_texture_im[:, random_index[z], :, i * ph:(i + 1) * ph, j * pw:(j + 1) * pw].squeeze(1)
+                           for z in range(random_index.shape[0])])
+    got = gather_parts(src_texture_im, random_index)
+    assert tuple(got.shape) == (24, 3, B, 3, ph, pw)
+    for p in range(24):
+        assert torch.equal(got[p].flatten(0, 1), torch.cat(ref_in[p], dim=0))  # src/networks.py:1316
+    # :221-236 (unused frames zeroed, OR over all Kmax as bytes, float, repeat to 3 channels, multiply per part)
+    mask = src_mask_im.clone()
+    for i in range(Kmax):
+        if i not in list(random_index):
+            mask[:, i] = mask[:, i] * 0
+    common = (mask[:, 0] * 0).byte()
+    for i in range(Kmax):
+        common = common | mask[:, i].byte()
+    common = common.float().unsqueeze(1).repeat(1, 3, 1, 1)
+    accu_out = [torch.randn(B, 3, ph, pw, device=DEV) for _ in range(24)]
+    ref_masked = [accu_out[i * 6 + j] * common[:, :, i * ph:(i + 1) * ph, j * pw:(j + 1) * pw] for i in range(4) for j in range(6)]
+    parts = mask_common_area_(torch.stack(accu_out, 0), src_mask_im, random_index)
+    for p in range(24):
+        assert torch.equal(parts[p], ref_masked[p])
+    # src/networks.py:1685-1691
+    tex = torch.empty(B, 3, 4 * ph, 6 * pw, device=DEV)
+    for i in range(4):
+        for j in range(6):
+            tex[:, :, i * ph:(i + 1) * ph, j * pw:(j + 1) * pw] = ref_masked[i * 6 + j]
+    assert torch.equal(assemble_atlas(parts), tex) and torch.equal(assemble_atlas(ref_masked), tex)
+    # full-size shapes once
+    big = torch.randn(1, 5, 3, 800, 1200, device=DEV)
+    g = gather_parts(big, [1, 4])
+    assert torch.equal(g[7, 1, 0], big[0, 4, :, 200:400, 200:400])
