@@ -292,6 +292,22 @@ int jaf_texture_parts_common_mask(float* parts, const float* mask, const int32_t
 int jaf_texture_parts_scatter(const float* parts, int B, int C, int rows, int cols, int ph, int pw,
                               float* atlas, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * SURVEY §8f rank 4  per-frame IUV preprocessing of the data loader
+ * jaf_transfer_texture replaces TransferTexture (src/utils.py:369-394; three calls per frame at
+ *   src/data.py:102-113): nearest texel of the atlas at U = rint(IUV[1]/255.*(ps-1)), V likewise,
+ *   row i*ps + U, column j*ps + (ps-1-V) of part 6*i+j+1; output channels that come out 0 take `im`
+ *   when it is given.  tex [rows*ps, cols*ps, 3] u8 (or one per frame when tex_batched); iuv, im, out
+ *   [B,H,W,3] u8.  The reference hard-codes rows=4, cols=6, ps=200, H=W=256.
+ * jaf_iuv_part_stats feeds compute_angle (src/computer_angle.py:4-39; src/data.py:504):
+ *   counts [B,32] i32 = pixels of each part id < 32, sumx [B,32] i64 = sum of their column index.
+ * --------------------------------------------------------------------------------- */
+int jaf_transfer_texture(const uint8_t* tex, int tex_batched, int rows, int cols, int part_size,
+                         const uint8_t* iuv, const uint8_t* im, int B, int H, int W, uint8_t* out,
+                         void* stream);
+int jaf_iuv_part_stats(const uint8_t* iuv, int B, int H, int W, int32_t* counts, int64_t* sumx,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,8 @@ SIGNATURES = {
     "jaf_texture_parts_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "jaf_texture_parts_common_mask": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "jaf_texture_parts_scatter": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "jaf_transfer_texture": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "jaf_iuv_part_stats": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -116,6 +116,67 @@ k_parts_scatter(const float* __restrict__ parts, AtlasGeom g, long n, float* __r
   st_stream_f32(atlas + i, ld_stream_f32(parts + src));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// per-frame IUV preprocessing of the reference's data loader (src/data.py:102-113,:504).
+//   TransferTexture (src/utils.py:369-394): nearest texel lookup  U = rint(IUV[1]/255.*199.), V likewise,
+//       out = tex[i*200 + U, j*200 + (199 - V)] for part 6*i + j + 1; channels that come out 0 take `im`.
+//   compute_angle (src/computer_angle.py:4-39): needs the pixel count of every part and the sum of x of
+//       parts 1 and 2 — a per-frame histogram; the scalar formula stays on the host in float64.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_transfer_texture(const unsigned char* __restrict__ tex, long tex_stride, int cols, int nparts, int ps,
+                   const unsigned char* __restrict__ iuv, const unsigned char* __restrict__ im, long HW, long n,
+                   unsigned char* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = (int)(i / HW);
+  const int part = iuv[i * 3 + 0];
+  unsigned char r[3] = {0, 0, 0};
+  if (part >= 1 && part <= nparts) {
+    // float64 like numpy: uint8 / 255. * 199. then round-half-even, then the uint8 cast
+    const double last = (double)(ps - 1);
+    const int u = (int)(unsigned char)rint((double)iuv[i * 3 + 1] / 255.0 * last);
+    const int v = (int)(unsigned char)rint((double)iuv[i * 3 + 2] / 255.0 * last);
+    const int ic = (part - 1) / cols, jc = part - ic * cols - 1;
+    const long AW = (long)cols * ps;
+    const unsigned char* t = tex + b * tex_stride + (((long)ic * ps + u) * AW + (long)jc * ps + (ps - 1 - v)) * 3;
+    r[0] = __ldg(t);
+    r[1] = __ldg(t + 1);
+    r[2] = __ldg(t + 2);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    unsigned char o = r[c];
+    if (im != nullptr && o == 0) o = im[i * 3 + c];  // BG_MASK = output_img == 0, per channel (:390-391)
+    out[i * 3 + c] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_iuv_part_stats(const unsigned char* __restrict__ iuv, int W, long HW, int* __restrict__ counts,
+                 long long* __restrict__ sumx) {
+  __shared__ int s_cnt[32];
+  __shared__ unsigned long long s_sx[32];
+  if (threadIdx.x < 32) {
+    s_cnt[threadIdx.x] = 0;
+    s_sx[threadIdx.x] = 0ull;
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long)gridDim.x * blockDim.x) {
+    const int part = iuv[((long)b * HW + p) * 3];
+    if (part >= 1 && part < 32) {
+      atomicAdd(&s_cnt[part], 1);
+      atomicAdd(&s_sx[part], (unsigned long long)(p % W));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && s_cnt[threadIdx.x] != 0) {
+    atomicAdd(&counts[b * 32 + threadIdx.x], s_cnt[threadIdx.x]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&sumx[b * 32 + threadIdx.x]), s_sx[threadIdx.x]);
+  }
+}
+
 bool geom_ok(const AtlasGeom& g) {
   return g.B > 0 && g.Kmax > 0 && g.K > 0 && g.C > 0 && g.rows > 0 && g.cols > 0 && g.ph > 0 && g.pw > 0;
 }
@@ -150,6 +211,32 @@ extern "C" int jaf_texture_parts_scatter(const float* parts, int B, int C, int r
   const long n = (long)B * C * rows * ph * cols * pw;
   k_parts_scatter<<<jaf::ceil_div(n, 256), 256, 0, jaf::as_stream(stream)>>>(parts, g, n, atlas);
   return jaf::finish_launch("k_parts_scatter");
+}
+
+extern "C" int jaf_transfer_texture(const uint8_t* tex, int tex_batched, int rows, int cols, int part_size,
+                                    const uint8_t* iuv, const uint8_t* im, int B, int H, int W, uint8_t* out,
+                                    void* stream) {
+  JAF_REQUIRE(tex && iuv && out, "null pointer");
+  JAF_REQUIRE(rows > 0 && cols > 0 && part_size > 0 && part_size <= 256 && rows * cols <= 255 && B > 0 && H > 0 && W > 0,
+              "bad sizes");
+  const long n = (long)B * H * W;
+  const long tex_stride = tex_batched ? (long)rows * part_size * cols * part_size * 3 : 0;
+  k_transfer_texture<<<jaf::ceil_div(n, 256), 256, 0, jaf::as_stream(stream)>>>(tex, tex_stride, cols, rows * cols,
+                                                                               part_size, iuv, im, (long)H * W, n, out);
+  return jaf::finish_launch("k_transfer_texture");
+}
+
+extern "C" int jaf_iuv_part_stats(const uint8_t* iuv, int B, int H, int W, int32_t* counts, int64_t* sumx, void* stream) {
+  JAF_REQUIRE(iuv && counts && sumx, "null pointer");
+  JAF_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "bad sizes");
+  cudaStream_t st = jaf::as_stream(stream);
+  JAF_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * 32 * sizeof(int32_t), st));
+  JAF_CUDA(cudaMemsetAsync(sumx, 0, (size_t)B * 32 * sizeof(int64_t), st));
+  const long HW = (long)H * W;
+  int bx = jaf::ceil_div(HW, 256 * 8);
+  if (bx > 64) bx = 64;
+  k_iuv_part_stats<<<dim3(bx, B), 256, 0, st>>>(iuv, W, HW, counts, reinterpret_cast<long long*>(sumx));
+  return jaf::finish_launch("k_iuv_part_stats");
 }
 
 extern "C" int jaf_texture_warp(const float* tex_parts, int P, int Ht, int Wt, const uint8_t* iuv, int B, int H, int W,

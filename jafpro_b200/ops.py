@@ -558,3 +558,35 @@ def texture_parts_scatter(parts, rows: int = 4, cols: int = 6):
         _lib.check(_lib.lib().jaf_texture_parts_scatter(_ptr(parts), B, C, rows, cols, ph, pw, _ptr(atlas), _stream()),
                    "texture_parts_scatter")
     return atlas
+
+
+# ----------------------------------------------------------------------------- §8f rank 4
+def transfer_texture(tex, iuv, im=None, rows: int = 4, cols: int = 6):
+    """TransferTexture (src/utils.py:369-394) for a batch: tex [rows*ps, cols*ps, 3] uint8 (or [B,...] one atlas per
+    frame), iuv [B,H,W,3] uint8, im [B,H,W,3] uint8 or None -> [B,H,W,3] uint8."""
+    tex, iuv = _check(tex, "TextureIm", torch.uint8), _check(iuv, "IUV", torch.uint8)
+    if im is not None:
+        im = _check(im, "im", torch.uint8)
+    batched = tex.dim() == 4
+    AH, AW = tex.shape[-3], tex.shape[-2]
+    if tex.shape[-1] != 3 or AH % rows or AW % cols or AH // rows != AW // cols or iuv.dim() != 4 or iuv.shape[-1] != 3:
+        raise RuntimeError("expected tex [rows*ps, cols*ps, 3] and IUV [B,H,W,3]")
+    B, H, W, _ = iuv.shape
+    if (batched and tex.shape[0] != B) or (im is not None and im.shape != iuv.shape):
+        raise RuntimeError("batch / image shapes do not match")
+    out = torch.empty_like(iuv)
+    with _on(iuv.device):
+        _lib.check(_lib.lib().jaf_transfer_texture(_ptr(tex), int(batched), rows, cols, AH // rows, _ptr(iuv), _ptr(im), B, H,
+                                                   W, _ptr(out), _stream()), "transfer_texture")
+    return out
+
+
+def iuv_part_stats(iuv):
+    """iuv [B,H,W,3] uint8 -> (counts [B,32] int32, sumx [B,32] int64): pixels per part id and the sum of their x."""
+    iuv = _check(iuv, "IUV", torch.uint8)
+    B, H, W, _ = iuv.shape
+    counts = torch.empty((B, 32), dtype=torch.int32, device=iuv.device)
+    sumx = torch.empty((B, 32), dtype=torch.int64, device=iuv.device)
+    with _on(iuv.device):
+        _lib.check(_lib.lib().jaf_iuv_part_stats(_ptr(iuv), B, H, W, _ptr(counts), _ptr(sumx), _stream()), "iuv_part_stats")
+    return counts, sumx

@@ -738,3 +738,26 @@ def test_texture_space_assembly_matches_the_reference_loops():
     big = torch.randn(1, 5, 3, 800, 1200, device=DEV)
     g = gather_parts(big, [1, 4])
     assert torch.equal(g[7, 1, 0], big[0, 4, :, 200:400, 200:400])
+
+
+# ------------------------------------------------------------------ §8f rank 4: IUV preprocessing of the data loader
+def test_transfer_texture_and_compute_angle_match_the_reference_functions(golden_dir):
+    """Fixture = TransferTexture (src/utils.py:369-394) and compute_angle (src/computer_angle.py:4-39) executed
+    unmodified by tools/make_golden.py on oracle.inputs.iuv_preprocessing_inputs()."""
+    from jafpro_b200.computer_angle import compute_angle, compute_angles
+    from jafpro_b200.utils import TransferTexture
+    from oracle.inputs import iuv_preprocessing_inputs
+    d = _load(golden_dir, "iuv_preprocessing.npz")
+    iuv, tex, im = iuv_preprocessing_inputs()
+    n = iuv.shape[0]
+    out_bg = TransferTexture(_cu(tex), _cu(iuv), _cu(im))         # batched, on the GPU
+    assert np.array_equal(_np(out_bg), d["out_bg"])
+    assert np.array_equal(TransferTexture(tex, iuv[1]), d["out_nobg"][1])  # the reference's numpy call form
+    ones = TransferTexture(_cu(np.ones((800, 1200, 3), np.uint8)), _cu(iuv))   # src/data.py:108
+    packed = np.unpackbits(d["ones"])[: n * 256 * 256].reshape(n, 256, 256)
+    assert np.array_equal(_np(ones)[..., 0], packed) and np.array_equal(_np(ones)[..., 2], packed)
+    batched_tex = TransferTexture(_cu(np.stack([tex] * n)), _cu(iuv))
+    assert np.array_equal(_np(batched_tex), d["out_nobg"])
+    angles = compute_angles(_cu(iuv))
+    assert [float(a) for a in angles] == [float(a) for a in d["angles"]]   # bit-identical float64
+    assert float(compute_angle(iuv[2])) == float(d["angles"][2])

@@ -84,3 +84,19 @@ def test_world_size_2_gloo_sharding_and_reduction(tmp_path):
     assert res.returncode == 0, res.stderr[-2000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("RESULT")][0]
     assert "20.0 180.0 [[0, 2, 4], [1, 3, 5]]" in line
+
+
+def test_compute_angle_host_formula_matches_reference_fixture(golden_dir):
+    """The float64 tail of compute_angle (src/computer_angle.py:20-39) restated on top of per-part (count, sum x)
+    statistics — the GPU kernel only supplies those integers.  Fixture: the reference function's own output."""
+    import numpy as np
+    from jafpro_b200.computer_angle import _angle_from_stats
+    from oracle.inputs import iuv_preprocessing_inputs
+    iuv, _, _ = iuv_preprocessing_inputs()
+    d = np.load(os.path.join(golden_dir, "iuv_preprocessing.npz"))
+    for i in range(iuv.shape[0]):
+        part = iuv[i, :, :, 0]
+        counts = np.bincount(part.ravel(), minlength=32)[:32]
+        xs = np.broadcast_to(np.arange(part.shape[1])[None], part.shape)
+        sumx = np.array([xs[part == p].sum() for p in range(32)])
+        assert float(_angle_from_stats(counts, sumx)) == float(d["angles"][i])

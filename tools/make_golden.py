@@ -20,6 +20,7 @@ Fixtures (all small, float32 unless noted):
   render_faces.npz     cam, verts -> `faces` exactly as SMPLRenderer.render_fim_wim builds them
                        (src/nmr.py:263-276, rasteriser stubbed out).
   bc_transform.npz     SMPLRenderer.cal_bc_transform (src/nmr.py:617-659) on a random fim/wim.
+  iuv_preprocessing.npz  TransferTexture (src/utils.py:369-394) and compute_angle (src/computer_angle.py:4-39) on synthetic IUV maps.
   vis_f2pts.npz        SMPLRenderer.get_vis_f2pts (src/nmr.py:507-546) on random fims (with / without background).
   convlstm.npz         src/convLSTM.py ConvLSTMCell.forward and a 3-step ConvLSTM.forward.
   softmax_fuse.npz     src/networks.py Downsampler_mask.forward K-reduction (:1259-1286), captured
@@ -236,6 +237,36 @@ def vis_f2pts(nmr):
     print("vis_f2pts:", out.shape, "invisible faces:", int((out[..., 0, 0] == -2).sum()))
 
 
+def iuv_preprocessing():
+    """The per-frame IUV preprocessing of src/data.py (§8f rank 4): TransferTexture (src/utils.py:369-394, called three
+    times per frame at src/data.py:102-113) and compute_angle (src/computer_angle.py:4-39, src/data.py:504).  Both are
+    numpy-only; the modules' unrelated imports (matplotlib, tensorflow, cv2, moviepy) are absent here and are stubbed."""
+    for name in ("matplotlib", "matplotlib.pyplot", "tensorflow", "cv2", "moviepy", "moviepy.editor"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__getattr__ = lambda attr: None
+            m.__path__ = []
+            sys.modules[name] = m
+    from src.computer_angle import compute_angle
+    from src.utils import TransferTexture
+    sys.path.insert(0, ROOT)
+    from oracle.inputs import iuv_preprocessing_inputs
+    iuv, tex, im = iuv_preprocessing_inputs()
+    n = iuv.shape[0]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        angles = np.array([compute_angle(iuv[i]) for i in range(n)], np.float64)
+    out_bg = np.stack([TransferTexture(tex, iuv[i], im[i]) for i in range(n)])
+    out_nobg = np.stack([TransferTexture(tex, iuv[i]) for i in range(n)])
+    ones = np.stack([TransferTexture(np.ones((800, 1200, 3), np.uint8), iuv[i]) for i in range(n)])  # src/data.py:108
+    # inputs are regenerated by iuv_preprocessing_inputs() in the tests; only the reference's outputs are stored
+    np.savez_compressed(os.path.join(GOLD, "iuv_preprocessing.npz"), angles=angles, out_bg=out_bg, out_nobg=out_nobg,
+                        ones=np.packbits(ones[..., 0] != 0))
+    assert all(np.array_equal(ones[..., 0], ones[..., c]) for c in (1, 2)) and set(np.unique(ones)) <= {0, 1}
+    print("iuv_preprocessing: angles", np.round(angles, 3))
+
+
 def smpl_template():
     """mapper.txt `v` lines (6890 T-pose vertices) + smpl_faces.npy -> jafpro_b200/data/."""
     vs = []
@@ -265,3 +296,4 @@ if __name__ == "__main__":
     softmax_fuse()
     mask_blend()
     texture_warp()
+    iuv_preprocessing()
