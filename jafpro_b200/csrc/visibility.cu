@@ -10,9 +10,13 @@ namespace {
 __global__ void __launch_bounds__(256)
 k_mark_faces(const int* __restrict__ fim_src, long n, int HW, int F, uint8_t* __restrict__ seen) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int f = ld_stream_s32(fim_src + i);
-  if (f >= 0 && f < F) seen[(i / HW) * F + f] = 1;  // racing stores all write 1
+  const int f = i < n ? ld_stream_s32(fim_src + i) : -1;
+  const long img = i < n ? i / HW : -1;
+  // face-index maps are piecewise constant along x: only the first pixel of a run inside the warp stores
+  const int fl = __shfl_up_sync(0xffffffffu, f, 1);
+  const long il = __shfl_up_sync(0xffffffffu, img, 1);
+  const bool first = (threadIdx.x & 31) == 0 || fl != f || il != img;
+  if (first && f >= 0 && f < F) seen[img * F + f] = 1;  // racing stores all write 1
 }
 
 __global__ void __launch_bounds__(256)

@@ -121,6 +121,60 @@ def main():
     savg, _, _ = timeit(lambda: ops.softmax_fuse(fc, lg), n=30)
     sb = 64 * 10000 * 4 * (72 + 3 + 24)
     out.append({"config": "a12 softmax fuse K=3 C=24 @100^2 x64", "ms_avg": round(savg, 4), "GBps": round(sb / savg / 1e6, 1), "frac_of_hbm": round(sb / savg / 1e6 / hbm, 3)})
+    # ---- K-source transfer flows: one target raster, K composes
+    Bm, Km = 30, 4
+    cam5, verts5 = synth.smpl_poses(Bm * (Km + 1), seed=5, device=DEV)
+    tcm, tvm = cam5[:Bm].contiguous(), verts5[:Bm].contiguous()
+    scm, svm = cam5[Bm:].reshape(Bm, Km, 3).contiguous(), verts5[Bm:].reshape(Bm, Km, -1, 3).contiguous()
+    mavg, _, _ = timeit(lambda: ops.cal_flow_multi(scm, svm, tcm, tvm, f_idx, 256), n=50)
+    pavg, _, _ = timeit(lambda: [ops.cal_flow(scm[:, k].contiguous(), svm[:, k].contiguous(), tcm, tvm, f_idx, 256) for k in range(Km)], n=20)
+    out.append({"config": "a8 x K: cal_flow_multi, 30 target frames x 4 source poses", "ms_avg": round(mavg, 4),
+                "flows_per_s": round(Bm * Km / mavg * 1e3, 1), "four_cal_flow_calls_ms": round(pavg, 4)})
+    # ---- row F per-reference visibility
+    fim30 = ops.render_fim_wim(tc, tv, f_idx, 256, return_faces=False)[1]  # real face-index maps (~10 % foreground)
+    ftgt = fim30.repeat(8, 1, 1).contiguous()
+    fsrc = torch.stack([torch.roll(ftgt, k + 1, 0) for k in range(4)], 1).contiguous()
+    vavg, _, _ = timeit(lambda: ops.face_visibility(fsrc, ftgt, 13776), n=30)
+    frnd = torch.randint(-1, 13776, (240, 4, 256, 256), device=DEV, dtype=torch.int32)
+    ravg, _, _ = timeit(lambda: ops.face_visibility(frnd, ftgt, 13776), n=10)
+    vb = 240 * 65536 * (4 * 4 + 4 + 4 * 4)
+    out.append({"config": "F per-reference visibility 240 frames x K=4 @256^2 (SMPL face-index maps)", "ms_avg": round(vavg, 4),
+                "GBps": round(vb / vavg / 1e6, 1), "worst_case_random_fim_ms": round(ravg, 4)})
+    # ---- §8f rank 3: bidirectional feature warp per SpatioTempoCRN level (B=8) vs the reference's op sequence in torch
+    flow8 = torch.randn(8, 2, 256, 256, device=DEV) * 0.1
+    tot_j = tot_t = 0.0
+    for C_, s_ in ((64, 128), (128, 64), (256, 32), (512, 16), (512, 8), (512, 4)):
+        pp, pl = torch.randn(8, C_, s_, s_, device=DEV), torch.randn(8, C_, s_, s_, device=DEV)
+        ys, xs_ = torch.meshgrid(torch.linspace(-1, 1, s_, device=DEV), torch.linspace(-1, 1, s_, device=DEV), indexing="ij")
+        g_ = torch.stack([xs_, ys])[None].expand(8, 2, s_, s_).contiguous()
+        ja, _, _ = timeit(lambda: ops.flow_warp_pair(pp, pl, g_, flow8), n=50)
+
+        def ref_level():
+            fs = F.interpolate(flow8, (s_, s_), mode="nearest")
+            a_ = F.grid_sample(pp, (g_ + fs).permute(0, 2, 3, 1), padding_mode="border", align_corners=False)
+            b_ = F.grid_sample(pl, (g_ - fs).permute(0, 2, 3, 1), padding_mode="border", align_corners=False)
+            return a_, b_
+        ta, _, _ = timeit(ref_level, n=50)
+        tot_j += ja
+        tot_t += ta
+    out.append({"config": "rank 3: 6-level bidirectional feature warp pyramid, B=8 (64ch@128^2 ... 512ch@4^2)",
+                "ms_total": round(tot_j, 4), "torch_ref_ops_ms_total": round(tot_t, 4), "launches": 6, "torch_launches": 42})
+    # ---- §8f rank 2 / 4: texture-space assembly and IUV preprocessing
+    atlas = torch.randn(1, 5, 3, 800, 1200, device=DEV)
+    idx = torch.tensor([0, 1, 2, 3], dtype=torch.int32, device=DEV)
+    gavg, _, _ = timeit(lambda: ops.texture_parts_gather(atlas, idx), n=50)
+    out.append({"config": "rank 2: gather 24 parts x 4 refs from the 800x1200 atlas", "ms_avg": round(gavg, 4),
+                "GBps": round(2 * 4 * 3 * 800 * 1200 * 4 / gavg / 1e6, 1)})
+    iuv = torch.randint(0, 25, (240, 256, 256, 3), device=DEV, dtype=torch.uint8)
+    texu = torch.randint(0, 256, (800, 1200, 3), device=DEV, dtype=torch.uint8)
+    imu = torch.randint(0, 256, (240, 256, 256, 3), device=DEV, dtype=torch.uint8)
+    tavg2, _, _ = timeit(lambda: ops.transfer_texture(texu, iuv, imu), n=30)
+    savg2, _, _ = timeit(lambda: ops.iuv_part_stats(iuv), n=30)
+    out.append({"config": "rank 4: TransferTexture, 240 frames @256^2", "ms_avg": round(tavg2, 4), "frames_per_s": round(240 / tavg2 * 1e3, 1)})
+    out.append({"config": "rank 4: compute_angle statistics, 240 frames @256^2", "ms_avg": round(savg2, 4), "frames_per_s": round(240 / savg2 * 1e3, 1)})
+    tex24 = torch.randn(24, 3, 200, 200, device=DEV)
+    xavg, _, _ = timeit(lambda: ops.texture_warp(tex24, iuv), n=30)
+    out.append({"config": "rank 1: texture_warp (IUV lookup), 240 frames @256^2", "ms_avg": round(xavg, 4), "frames_per_s": round(240 / xavg * 1e3, 1)})
     for o in out:
         print(json.dumps(o))
 
