@@ -99,7 +99,9 @@ extern "C" int jaf_warp_fuse_host(const JafWarpFuseParams* hp, int frames_per_ch
                            (hp->ref_index ? 0 : (want_rgb ? rgb_set : 0) + (want_feat ? feat_set : 0));
   int n = frames_per_chunk;
   if (n <= 0) {
-    const size_t fit = ((size_t)256 << 20) / (per_frame > 0 ? per_frame : 1);  // ~256 MB per slot
+    // ~96 MB per slot: the transfer of a chunk (~2 ms over PCIe 5) dwarfs launch overheads, and a short first chunk
+    // keeps the pipeline prologue (nothing overlaps the first upload) small
+    const size_t fit = ((size_t)96 << 20) / (per_frame > 0 ? per_frame : 1);
     n = fit < 1 ? 1 : (fit > 64 ? 64 : (int)fit);
   }
   if (n > B) n = B;
