@@ -627,6 +627,18 @@ def test_convlstm_grouped_module_matches_per_part_lstms():
         o_ref, last = lstms[g](x[g])
         assert float((out[g] - o_ref).abs().max()) <= 1e-4
         assert float((h[g] - last[0][0]).abs().max()) <= 1e-4 and float((c[g] - last[0][1]).abs().max()) <= 1e-4
+    # the single cell's opt-in tensor-core path (G = 1) gives the grouped result bit for bit; weights are re-packed
+    # when they change
+    cell = lstms[1].cell_list[0]
+    cell.tensor_cores = True
+    o_tc, _ = lstms[1](x[1])
+    assert torch.equal(o_tc, out[1])
+    with torch.no_grad():
+        cell.conv.weight.mul_(0.5)
+    o_half, _ = lstms[1](x[1])
+    cell.tensor_cores = False
+    o_half_exact, _ = lstms[1](x[1])
+    assert float((o_half - o_half_exact).abs().max()) <= 1e-4 and not torch.equal(o_half, o_tc)
 
 
 # ------------------------------------------------------------------ row F: per-reference visibility (get_vis_f2pts rule)
