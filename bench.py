@@ -210,7 +210,7 @@ def run_reference(args):
             "cpu_baseline": dict(best, value=round(mean, 2)),
             "e2e": {"value": round(mean, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -389,7 +389,27 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_leg(wl)
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_json_out = None
+
+
+def reserve_stdout():
+    """stdout carries exactly one JSON line.  Native libraries also write there (NCCL prints its version banner with
+    printf), so file descriptor 1 is pointed at stderr for the rest of the process and the JSON line goes out through
+    a private duplicate of the original stdout."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _json_out if _json_out is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -405,6 +425,7 @@ def main():
     ap.add_argument("--videos-per-gpu", type=int, default=0, help="override the workload's videos per GPU (profiling)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    reserve_stdout()
     if args.videos_per_gpu > 0:
         w = WORKLOADS[args.workload]
         WORKLOADS[args.workload] = (args.videos_per_gpu,) + tuple(w[1:])

@@ -22,6 +22,9 @@ def init(backend: str | None = None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend == "nccl":
+            # NCCL writes its banner ("NCCL version ...") and debug lines to stdout by default; rank 0's stdout is
+            # reserved for the one JSON line of bench.py
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             torch.cuda.set_device(local)
             dist.init_process_group(backend, device_id=torch.device("cuda", local))
         else:
