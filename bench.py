@@ -219,6 +219,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    full_affinity = os.sched_getaffinity(0)
+    numa_bound = jd.bind_to_gpu_cpus(local)  # pinned e2e buffers land on the GPU's NUMA node
     wl = args.workload
     V, Fv, S, K, C = WORKLOADS[wl]
     inp = make_inputs(wl, rank, dev, args.flow)
@@ -381,13 +383,14 @@ def run_ours(args):
                 "per_frame_refs": {"value": round(e2e_frame_refs, 1), "h2d_bytes_per_step": int(h2d_b),
                                    "note": "every frame carries its own K references (the device benchmark's layout)"},
                 "api": "jafpro_b200.fusion.warp_fuse_host -> jaf_warp_fuse_host (pinned host buffers)",
-                "matches_device_path": e2e_ok},
+                "matches_device_path": e2e_ok, "cpu_affinity_bound_to_gpu": bool(numa_bound)},
         "from_poses": from_poses,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "checksums": [float(g.item()) for g in gathered],
     }
     if world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, full_affinity)  # the CPU leg uses every host core
         line["cpu_baseline"] = cpu_leg(wl)
     emit(line)
 

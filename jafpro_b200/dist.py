@@ -32,6 +32,25 @@ def init(backend: str | None = None):
     return rank, world, local
 
 
+def bind_to_gpu_cpus(local: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `local` (same NUMA node / PCIe root), so that
+    pinned host buffers allocated afterwards are first-touched on that node.  Matters for the host-buffer path when
+    several ranks share a two-socket host; harmless otherwise.  Returns False when NVML is not usable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            props = torch.cuda.get_device_properties(local)
+            bus_id = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode() if hasattr(bus_id, "encode") else bus_id)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:
+        return False
+
+
 def shard_videos(n_videos: int, rank: int, world: int):
     """Rank r takes videos r, r+G, r+2G, ... (keeps a video's K references and 30 frames on one GPU)."""
     return list(range(rank, n_videos, world))
