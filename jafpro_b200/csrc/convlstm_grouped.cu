@@ -49,6 +49,7 @@ struct GArgs {
   int Wp, HpWp;      // padded row pitch, padded image size
   long Q;            // B * HpWp flattened padded positions per group
   int Ct, Ctp, N, nsplit, Nsub;
+  int CS, Chs, Ns;   // hidden-channel slices per cell, channels per slice, gate rows per slice (= 4 * Chs)
   int MT, R;         // accumulator tiles per CTA, staged rows
   int S, KS, nstages;
   int tiles_per_group;
@@ -153,7 +154,9 @@ k_convlstm_grouped(const GArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRing + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x / a.tiles_per_group, t = blockIdx.x % a.tiles_per_group;
+  const int t = blockIdx.x % a.tiles_per_group;
+  const int gs = blockIdx.x / a.tiles_per_group;
+  const int g = gs / a.CS, sl = gs % a.CS;  // cell, hidden-channel slice
   const long p_end = a.Q - a.Wp - 1;                          // one past the last output position
   const long p0 = (long)a.Wp + 1 + (long)t * a.MT * 128;      // first output position of this CTA
   const int mt_here = (int)min((long)a.MT, (p_end - p0 + 127) / 128);
@@ -186,14 +189,28 @@ k_convlstm_grouped(const GArgs a) {
       const uint8_t* wg = a.wpack + (size_t)g * a.S * 64 * a.N;
       const uint32_t stage_bytes = a.stage_bytes;
       const int nstages = a.nstages, KS = a.KS;
+      // one stage = KS k-steps of this slice's rows.  A k-step of the pack is [hi | lo][2 chunks][N rows][16 B]; a slice
+      // is a contiguous run of Ns rows in each of the four blocks (one copy when the cell is not sliced)
+      auto load_stage = [&](int st, int slot) {
+        uint8_t* dst = sB + (size_t)slot * stage_bytes;
+        mbar_expect_tx(&full_bar[slot], stage_bytes);
+        if (a.CS == 1) {
+          bulk_g2s(dst, wg + (size_t)st * stage_bytes, stage_bytes, &full_bar[slot]);
+        } else {
+          const uint32_t run = (uint32_t)a.Ns * 16u;
+          for (int j = 0; j < KS; ++j) {
+            const uint8_t* src = wg + (size_t)(st * KS + j) * 64 * a.N + (size_t)sl * run;
+#pragma unroll
+            for (int blk = 0; blk < 4; ++blk)
+              bulk_g2s(dst + (size_t)(j * 4 + blk) * run, src + (size_t)blk * 16 * a.N, run, &full_bar[slot]);
+          }
+        }
+      };
       const int pre = min(kRing, nstages);
       if (leader) {
-        for (int st = 0; st < pre; ++st) {
-          mbar_expect_tx(&full_bar[st], stage_bytes);
-          bulk_g2s(sB + (size_t)st * stage_bytes, wg + (size_t)st * stage_bytes, stage_bytes, &full_bar[st]);
-        }
+        for (int st = 0; st < pre; ++st) load_stage(st, st);
       }
-      const uint32_t N = (uint32_t)a.N, Nsub = (uint32_t)a.Nsub, R = (uint32_t)a.R, Wp = (uint32_t)a.Wp;
+      const uint32_t N = (uint32_t)a.Ns, Nsub = (uint32_t)a.Nsub, R = (uint32_t)a.R, Wp = (uint32_t)a.Wp;  // N: rows of this slice
       const uint32_t idesc = a.idesc;
       const int nsplit = a.nsplit, spt = a.Ctp / 16;
       const uint64_t ad0 = desc_noswz(smem_u32(sA), R * 16u), bd0 = desc_noswz(smem_u32(sB), N * 16u);
@@ -233,11 +250,7 @@ k_convlstm_grouped(const GArgs a) {
         if (st >= 1 && st - 1 + kRing < nstages) {
           const int ps = (st - 1) % kRing;
           mbar_wait(&empty_bar[ps], (uint32_t)((st - 1) / kRing) & 1u);
-          if (leader) {
-            mbar_expect_tx(&full_bar[ps], stage_bytes);
-            bulk_g2s(sB + (size_t)ps * stage_bytes, wg + (size_t)(st - 1 + kRing) * stage_bytes, stage_bytes,
-                     &full_bar[ps]);
-          }
+          if (leader) load_stage(st - 1 + kRing, ps);
         }
       }
       if (leader) umma_commit(tfull_bar);
@@ -301,26 +314,27 @@ k_convlstm_grouped(const GArgs a) {
     const int nsets = ((int)(blockDim.x >> 5) - 1) >> 2;  // epilogue warps per TMEM lane quarter (7 or 3)
     if (warp <= 4 * nsets) {
       const int qd = warp & 3, set = (warp - 1) >> 2;  // lane quarter this warp may read; which share of the items
-      const int nblk = a.Ch / 4;
+      const int nblk = a.Chs / 4;
       const int nitems = mt_here * nblk;  // (accumulator tile, block of 4 hidden channels)
       const float* bp = a.bias ? a.bias + (size_t)g * a.N : nullptr;
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
       for (int it0 = set; it0 < nitems; it0 += 2 * nsets) {
-        // two items per pass so that two sets of TMEM / global loads overlap
-        float gi[2][4], gf[2][4], go[2][4], gg[2][4], cv[2][4];
+        // two items per pass so that two sets of TMEM / global loads overlap.  The packed row order puts the four
+        // gates of a block of four channels in 16 consecutive accumulator columns: one tcgen05.ld per item.
+        float acc[2][16], cv[2][4];
         size_t base[2];
         bool valid[2];
-        int j0[2];
+        int c0[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int it = it0 + nsets * u;
           valid[u] = false;
           base[u] = 0;
-          j0[u] = 0;
+          c0[u] = 0;
           if (it < nitems) {  // warp-uniform
-            const int m = it / nblk;
-            j0[u] = (it - m * nblk) * 4;
+            const int m = it / nblk, jb = it - m * nblk;
+            c0[u] = sl * a.Chs + jb * 4;
             const long p = p0 + (long)m * 128 + qd * 32 + lane;
             bool ok = p < p_end;
             if (ok) {
@@ -331,13 +345,9 @@ k_convlstm_grouped(const GArgs a) {
               base[u] = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)(xp - 1);
             }
             valid[u] = ok;
-            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(m * a.N + j0[u]);
-            tmem_ld4(taddr, gi[u]);
-            tmem_ld4(taddr + a.Ch, gf[u]);
-            tmem_ld4(taddr + 2 * a.Ch, go[u]);
-            tmem_ld4(taddr + 3 * a.Ch, gg[u]);
+            tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(m * a.Ns + jb * 16), acc[u]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) cv[u][e] = ok ? __ldg(a.c + base[u] + (size_t)(j0[u] + e) * HW) : 0.f;
+            for (int e = 0; e < 4; ++e) cv[u][e] = ok ? __ldg(a.c + base[u] + (size_t)(c0[u] + e) * HW) : 0.f;
           }
         }
         tmem_ld_wait();
@@ -346,7 +356,7 @@ k_convlstm_grouped(const GArgs a) {
           if (!valid[u]) continue;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int ch = j0[u] + e;
+            const int ch = c0[u] + e;
             float bi = 0.f, bf = 0.f, bo = 0.f, bg = 0.f;
             if (bp) {
               bi = __ldg(bp + ch);
@@ -354,8 +364,8 @@ k_convlstm_grouped(const GArgs a) {
               bo = __ldg(bp + 2 * a.Ch + ch);
               bg = __ldg(bp + 3 * a.Ch + ch);
             }
-            const float ig = sigmoid_f(gi[u][e] + bi), fg = sigmoid_f(gf[u][e] + bf), og = sigmoid_f(go[u][e] + bo);
-            const float g_ = tanh_f(gg[u][e] + bg);
+            const float ig = sigmoid_f(acc[u][e] + bi), fg = sigmoid_f(acc[u][4 + e] + bf);
+            const float og = sigmoid_f(acc[u][8 + e] + bo), g_ = tanh_f(acc[u][12 + e] + bg);
             const float cn = fg * cv[u][e] + ig * g_;  // src/convLSTM.py:53
             const float hn = og * tanh_f(cn);          // :54
             a.c_out[base[u] + (size_t)ch * HW] = cn;
@@ -397,7 +407,11 @@ k_gpack_weight(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, int
   const int g = (int)(r / S);
   const int tap = step / spt, kc = step % spt;
   const int ch = kc * 16 + cc * 8 + e;
-  const float v = ch < Ct ? w[(((size_t)g * N + n) * Ct + ch) * 9 + tap] : 0.f;
+  // packed row n = (hidden channel / 4) * 16 + gate * 4 + hidden channel % 4: any run of 4k channels is a contiguous
+  // run of rows (so a cell can be sliced over CTAs) and the four gates of a channel block sit in 16 adjacent columns
+  const int Chh = N / 4;
+  const int orow = ((n % 16) / 4) * Chh + (n / 16) * 4 + n % 4;  // reference row: gate * Ch + channel (:46)
+  const float v = ch < Ct ? w[(((size_t)g * N + orow) * Ct + ch) * 9 + tap] : 0.f;
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
   uint8_t* stepb = wp + ((size_t)g * S + step) * 64 * N;
@@ -451,53 +465,68 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
   a.Ct = Cin + Ch;
   a.Ctp = (a.Ct + 15) / 16 * 16;
   a.N = 4 * Ch;
-  a.nsplit = a.N > 256 ? 2 : 1;
-  a.Nsub = a.N / a.nsplit;
   a.S = 9 * (a.Ctp / 16);
+  const long out_rows = a.Q - 2L * a.Wp - 2;
+  const int tiles_total = jaf::ceil_div(out_rows, 128);
+  static const int forced_mode = [] {
+    const char* e = getenv("JAF_CG_MODE");
+    return e ? atoi(e) : 0;
+  }();
+  static const int forced_cs = [] {
+    const char* e = getenv("JAF_CG_SLICES");
+    return e ? atoi(e) : 0;
+  }();
+  // Hidden-channel slices: a small map with wide cells (the 96-channel 13x13 level) has too few pixel tiles to fill
+  // the GPU; its cell is then split over CS CTAs, each with Ch/CS hidden channels (4*Ch/CS gate rows, all inputs).
+  int CS = 1;
+  if ((long)G * tiles_total * 2 <= sm_count) {
+    for (int cs = 2; cs <= 8; ++cs)
+      if (Ch % cs == 0 && (Ch / cs) % 4 == 0 && (long)G * tiles_total * cs <= sm_count + sm_count / 4) CS = cs;
+  }
+  if (forced_cs >= 1 && Ch % forced_cs == 0 && (Ch / forced_cs) % 4 == 0) CS = forced_cs;
+  a.CS = CS;
+  a.Chs = Ch / CS;
+  a.Ns = 4 * a.Chs;
+  a.nsplit = a.Ns > 256 ? 2 : 1;
+  a.Nsub = a.Ns / a.nsplit;
   // Two launch shapes.  "Half": 512 threads, <= 112 KB and <= 256 TMEM columns per CTA, so two CTAs share an SM and
   // one stages / runs its epilogue while the other's MMAs execute.  "Full": 1024 threads, the whole SM, the largest
   // MT (smallest halo overhead).  Half is used when it fits and the grid is more than one wave of it.
-  const long out_rows = a.Q - 2L * a.Wp - 2;
-  const int tiles_total = jaf::ceil_div(out_rows, 128);
   auto plan = [&](long smem_cap, int col_cap, long stage_cap, int& KS, int& MT) {
     KS = 1;
     for (int ks = 1; ks <= a.S; ++ks)
-      if (a.S % ks == 0 && (long)ks * 64 * a.N <= stage_cap) KS = ks;
+      if (a.S % ks == 0 && (long)ks * 64 * a.Ns <= stage_cap) KS = ks;
     MT = 0;
     for (int m = 1; m <= 8; ++m) {
       const long R = (long)m * 128 + 2L * a.Wp + 2;
-      const long smem = 4L * a.Ctp * R + (long)kRing * KS * 64 * a.N + 256 + 128;
-      if ((long)m * a.N <= col_cap && smem <= smem_cap && m <= tiles_total) MT = m;
+      const long smem = 4L * a.Ctp * R + (long)kRing * KS * 64 * a.Ns + 256 + 128;
+      if ((long)m * a.Ns <= col_cap && smem <= smem_cap && m <= tiles_total) MT = m;
     }
   };
   int ks_full, mt_full, ks_half, mt_half;
   plan(kMaxSmem, 512, 28 * 1024, ks_full, mt_full);
   plan(kHalfSmem, 256, 10 * 1024, ks_half, mt_half);
   JAF_REQUIRE(mt_full >= 1, "cell does not fit shared memory (W or channel count too large)");
-  static const int forced_mode = [] {
-    const char* e = getenv("JAF_CG_MODE");
-    return e ? atoi(e) : 0;
-  }();
-  bool half = mt_half >= 1 && (long)G * jaf::ceil_div(tiles_total, mt_half) > sm_count;
+  bool half = mt_half >= 1 && (long)G * CS * jaf::ceil_div(tiles_total, mt_half) > sm_count;
   if (forced_mode == 1) half = false;
   if (forced_mode == 2 && mt_half >= 1) half = true;
   int MT = half ? mt_half : mt_full;
   a.KS = half ? ks_half : ks_full;
   a.nstages = a.S / a.KS;
-  a.stage_bytes = (uint32_t)a.KS * 64u * (uint32_t)a.N;
+  a.stage_bytes = (uint32_t)a.KS * 64u * (uint32_t)a.Ns;
   // keep at least one CTA per SM
-  while (!half && MT > 1 && (long)G * jaf::ceil_div(tiles_total, MT) < sm_count) --MT;
+  while (!half && MT > 1 && (long)G * CS * jaf::ceil_div(tiles_total, MT) < sm_count) --MT;
   a.MT = MT;
   a.R = MT * 128 + 2 * a.Wp + 2;
   a.a_half = (uint32_t)(a.Ctp / 8) * (uint32_t)a.R * 16u;
   JAF_REQUIRE((uint32_t)a.R * 16u < (1u << 18), "row window too large for the descriptor");
   a.tiles_per_group = jaf::ceil_div(tiles_total, MT);
   uint32_t cols = 32;
-  while (cols < (uint32_t)(MT * a.N)) cols <<= 1;
+  while (cols < (uint32_t)(MT * a.Ns)) cols <<= 1;
   a.tmem_cols = cols;
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Nsub >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const size_t smem = 2 * (size_t)a.a_half + (size_t)kRing * a.stage_bytes + 256 + 128;
-  const long grid = (long)G * a.tiles_per_group;
+  const long grid = (long)G * CS * a.tiles_per_group;
   JAF_REQUIRE(grid < (1L << 31), "too many tiles");
   k_convlstm_grouped<<<(unsigned)grid, half ? kThreadsHalf : kThreads, smem, jaf::as_stream(stream)>>>(a);
   return jaf::finish_launch("k_convlstm_grouped");
