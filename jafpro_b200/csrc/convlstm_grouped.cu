@@ -12,7 +12,9 @@
 //   buffer with a different start address.  That needs rows at a uniform 16-byte pitch, i.e. the
 //   no-swizzle K-major canonical layout [channel chunk of 8][row][16 B] with SBO = 128 B and
 //   LBO = rows * 16 B.  Outputs computed for the two padding columns of each row are discarded.
-//   The batch is flattened into the same index (padded images stacked), so tiles may straddle images.
+//   The batch is flattened into the same index (padded images stacked), so tiles may straddle images.  Wide maps are
+//   cut into vertical bands of ~25 columns, each flattened on its own with its neighbours' columns as halo: the row
+//   window of a tile is then 128*MT + 2*(band width + 3) rows instead of 128*MT + 2*(W + 3).
 // * The fp32 NCHW activations (x for channels < Cin, h above: the cat of :43 never exists) are read
 //   coalesced along x, split to hi/lo bf16 in registers and stored with conflict-free 16-byte stores.
 // * Weights are repacked once per model (jaf_convlstm_gpack_weight) into the exact shared-memory image of
@@ -46,8 +48,9 @@ struct GArgs {
   float* h_out;
   float* c_out;
   int G, B, Cin, Ch, H, W;
-  int Wp, HpWp;      // padded row pitch, padded image size
-  long Q;            // B * HpWp flattened padded positions per group
+  int nb, Wb;        // vertical bands per image and their width: each band is flattened on its own (short halo)
+  int Wp, HpWp;      // padded row pitch of a band (Wb + 2), padded band size (H + 2) * Wp
+  long Q;            // B * nb * HpWp flattened padded positions per group
   int Ct, Ctp, N, nsplit, Nsub;
   int CS, Chs, Ns;   // hidden-channel slices per cell, channels per slice, gate rows per slice (= 4 * Chs)
   int MT, R;         // accumulator tiles per CTA, staged rows
@@ -279,11 +282,13 @@ k_convlstm_grouped(const GArgs a) {
         size_t pix = 0;
         int b = 0;
         if (inside) {
-          b = (int)(q / a.HpWp);
-          const int rem = (int)(q - (long)b * a.HpWp);
+          const int u = (int)(q / a.HpWp);  // (image, band)
+          const int rem = (int)(q - (long)u * a.HpWp);
           const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
-          inside = xp >= 1 && xp <= a.W && yp >= 1 && yp <= a.H;
-          pix = (size_t)(yp - 1) * a.W + (size_t)(xp - 1);
+          b = u / a.nb;
+          const int x = (u - b * a.nb) * a.Wb + xp - 1;  // a band's halo columns are its neighbours' pixels
+          inside = x >= 0 && x < a.W && yp >= 1 && yp <= a.H;
+          pix = (size_t)(yp - 1) * a.W + (size_t)x;
         }
         const float* xb = a.x + ((size_t)g * a.B + b) * a.Cin * HW + pix;
         const float* hb = a.h + ((size_t)g * a.B + b) * a.Ch * HW + pix;
@@ -338,11 +343,13 @@ k_convlstm_grouped(const GArgs a) {
             const long p = p0 + (long)m * 128 + qd * 32 + lane;
             bool ok = p < p_end;
             if (ok) {
-              const int b = (int)(p / a.HpWp);
-              const int rem = (int)(p - (long)b * a.HpWp);
+              const int un = (int)(p / a.HpWp);
+              const int rem = (int)(p - (long)un * a.HpWp);
               const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
-              ok = xp >= 1 && xp <= a.W && yp >= 1 && yp <= a.H;
-              base[u] = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)(xp - 1);
+              const int b = un / a.nb;
+              const int x = (un - b * a.nb) * a.Wb + xp - 1;
+              ok = xp >= 1 && xp <= a.Wb && x < a.W && yp >= 1 && yp <= a.H;
+              base[u] = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)x;
             }
             valid[u] = ok;
             tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(m * a.Ns + jb * 16), acc[u]);
@@ -459,9 +466,19 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
   a.x = x; a.h = h; a.c = c; a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
   a.h_out = h_out; a.c_out = c_out;
   a.G = G; a.B = B; a.Cin = Cin; a.Ch = Ch; a.H = H; a.W = W;
-  a.Wp = W + 2;
-  a.HpWp = (H + 2) * (W + 2);
-  a.Q = (long)B * a.HpWp;
+  // vertical bands of ~25 columns: the halo of a flattened tile is two padded rows, so narrow bands keep it short
+  // (W = 200: 2 x 28 rows instead of 2 x 203) at the price of two extra columns per band row
+  static const int band_target = [] {
+    const char* e = getenv("JAF_CG_BAND");
+    const int v = e ? atoi(e) : 25;  // measured best of 16 / 25 / 34 / 50 / 67 / 100 on the reference pyramid
+    return v >= 8 ? v : 25;
+  }();
+  a.nb = (W + band_target / 2) / band_target;
+  if (a.nb < 1) a.nb = 1;
+  a.Wb = (W + a.nb - 1) / a.nb;
+  a.Wp = a.Wb + 2;
+  a.HpWp = (H + 2) * a.Wp;
+  a.Q = (long)B * a.nb * a.HpWp;
   a.Ct = Cin + Ch;
   a.Ctp = (a.Ct + 15) / 16 * 16;
   a.N = 4 * Ch;
