@@ -444,9 +444,14 @@ def test_convlstm_cell_matches_reference_fixture(golden_dir):
     lstm = ConvLSTM((H, W), Cin, Ch, (3, 3), 1, batch_first=True, bias=True).to(DEV)
     lstm.load_state_dict({"cell_list.0.conv.weight": torch.from_numpy(d["seq_weight"]),
                           "cell_list.0.conv.bias": torch.from_numpy(d["seq_bias"])})
+    lstm.cell_list[0].tensor_cores = False   # exact fp32 kernel
     out, last = lstm(_cu(d["seq_x"]))  # default zero state on the module's device
     assert float(np.abs(_np(out) - d["seq_out"]).max()) <= 2e-5
     assert float(np.abs(_np(last[0][1]) - d["seq_c"]).max()) <= 2e-5
+    lstm.cell_list[0].tensor_cores = True    # the default: split-bf16 on tensor cores, inside the 1e-4 fp32 bound
+    out, last = lstm(_cu(d["seq_x"]))
+    assert float(np.abs(_np(out) - d["seq_out"]).max()) <= 1e-4
+    assert float(np.abs(_np(last[0][1]) - d["seq_c"]).max()) <= 1e-4
 
 
 @pytest.mark.parametrize("Cin,Ch,H,W,k", [(12, 12, 50, 50, 3), (24, 48, 25, 25, 3), (7, 5, 13, 13, 5), (3, 2, 9, 20, 7)])
@@ -630,7 +635,7 @@ def test_convlstm_grouped_module_matches_per_part_lstms():
     # the single cell's opt-in tensor-core path (G = 1) gives the grouped result bit for bit; weights are re-packed
     # when they change
     cell = lstms[1].cell_list[0]
-    cell.tensor_cores = True
+    assert cell.tensor_cores
     o_tc, _ = lstms[1](x[1])
     assert torch.equal(o_tc, out[1])
     with torch.no_grad():
