@@ -373,7 +373,8 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (every frame owns its K references: %.1f GB read per step)" % (alg_bytes / 1e9),
                    "layout": "refs RGB planar f32 + features channels-last bf16"},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                     "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_avg": round(avg_launch_ms, 4),
                      "launch_ms_median": round(per_launch_ms[len(per_launch_ms) // 2], 4),
                      "kernel": "k_warp_fuse_nhwc<LPP=C/8,K>"},
