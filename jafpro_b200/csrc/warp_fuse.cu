@@ -122,6 +122,15 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
                                           const float* __restrict__ b_mask, const float* __restrict__ b_fake,
                                           const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
                                           unsigned HW, unsigned HWs, unsigned Ws) {
+  // every load that does not depend on another one is issued first: sample positions, logits, target mask
+  float2 gxy0[KT];
+  if constexpr (!SKIP && KT <= 4) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) gxy0[k] = __ldg(b_grid + ((unsigned)k * HW + pix));
+  }
+  constexpr bool kEarly = !SKIP && KT <= 4;
+  float tm = 1.f;
+  if (kEarly && b_mask) tm = __ldg(b_mask + pix);
   // softmax in the reference order: max, exp, running sum; one correctly-rounded reciprocal replaces the
   // K divisions (identical for K = 1, within 1 ulp otherwise)
   float aw[KT];
@@ -146,6 +155,53 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
   const bool ac = a.align_corners != 0;
   const char* __restrict__ rgb_bytes = reinterpret_cast<const char*>(rgb_base);
   float acc[3] = {0.f, 0.f, 0.f};
+  if constexpr (!SKIP && KT <= 4) {  // beyond 4 references the taps no longer fit the register budget
+    // No visibility input: nothing is skipped, so the whole pixel is software-pipelined by hand — all K sample
+    // positions are loaded up front, all K taps are built, and the 12 gathers of reference k+1 are in flight while
+    // reference k is reduced.  (Left to itself the compiler serialises load -> taps -> gathers -> FMAs per reference:
+    // 2K exposed memory latencies per pixel, measured as 20 stall cycles per issued instruction.)
+    const float2* gxy = gxy0;
+    unsigned ok[KT];
+    float tw[KT][4], wk[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      wk[k] = (KT == 1) ? aw[k] : (aw[k] * inv);
+      float ix = ac ? __fmul_rn(__fmul_rn(__fadd_rn(gxy[k].x, 1.f), 0.5f), wm1) : __fmul_rn(__fmaf_rn(__fadd_rn(gxy[k].x, 1.f), wsf, -1.f), 0.5f);
+      float iy = ac ? __fmul_rn(__fmul_rn(__fadd_rn(gxy[k].y, 1.f), 0.5f), hm1) : __fmul_rn(__fmaf_rn(__fadd_rn(gxy[k].y, 1.f), hsf, -1.f), 0.5f);
+      ix = fminf(wm1, fmaxf(ix, 0.f));
+      iy = fminf(hm1, fmaxf(iy, 0.f));
+      const float fx = fminf(floorf(ix), wm2), fy = fminf(floorf(iy), hm2);
+      const float ax = __fsub_rn(fx + 1.f, ix), bx = __fsub_rn(ix, fx), ay = __fsub_rn(fy + 1.f, iy), by = __fsub_rn(iy, fy);
+      tw[k][0] = __fmul_rn(ax, ay); tw[k][1] = __fmul_rn(bx, ay); tw[k][2] = __fmul_rn(ax, by); tw[k][3] = __fmul_rn(bx, by);
+      ok[k] = (unsigned)(k * 3) * HWs + (unsigned)((int)fy * (int)Ws + (int)fx);
+    }
+    float vbuf[2][12];
+    auto gather = [&](int k, float* v) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* p0 = reinterpret_cast<const float*>(rgb_bytes + (size_t)(ok[k] + (unsigned)c * HWs) * 4u);
+        const float* p1 = reinterpret_cast<const float*>(rgb_bytes + (size_t)(ok[k] + (unsigned)c * HWs + Ws) * 4u);
+        v[4 * c + 0] = __ldg(p0);
+        v[4 * c + 1] = __ldg(p0 + 1);
+        v[4 * c + 2] = __ldg(p1);
+        v[4 * c + 3] = __ldg(p1 + 1);
+      }
+    };
+    gather(0, vbuf[0]);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      if (k + 1 < KT) gather(k + 1, vbuf[(k + 1) & 1]);
+      const float* v = vbuf[k & 1];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sacc = fmaf(v[4 * c + 0], tw[k][0], 0.f);
+        sacc = fmaf(v[4 * c + 1], tw[k][1], sacc);
+        sacc = fmaf(v[4 * c + 2], tw[k][2], sacc);
+        sacc = fmaf(v[4 * c + 3], tw[k][3], sacc);
+        acc[c] = fmaf(wk[k], sacc, acc[c]);
+      }
+    }
+  } else {
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
     const float v = b_vis ? __ldg(b_vis + ((unsigned)k * HW + pix)) : vf;
@@ -173,7 +229,8 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
       }
     }
   }
-  const float tm = b_mask ? __ldg(b_mask + pix) : 1.f;
+  }
+  if (!kEarly && b_mask) tm = __ldg(b_mask + pix);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float ov = acc[c];
@@ -196,6 +253,14 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
                                           const float* __restrict__ b_mask, const float* __restrict__ b_fake,
                                           const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
                                           unsigned HW, unsigned HWs, unsigned Ws) {
+  float2 gxy0[KT];
+  if constexpr (!SKIP && KT <= 4) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) gxy0[k] = __ldg(b_grid + ((unsigned)k * HW + pix));
+  }
+  constexpr bool kEarly = !SKIP && KT <= 4;
+  float tm = 1.f;
+  if (kEarly && b_mask) tm = __ldg(b_mask + pix);
   // softmax in the reference order: max, exp, running sum, divide
   float aw[KT];
   float m = -CUDART_INF_F;
@@ -212,6 +277,43 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
   }
   const float vf = b_fim ? ((__ldg(b_fim + pix) != -1) ? 1.f : 0.f) : 1.f;
   float acc[3] = {0.f, 0.f, 0.f};
+  if constexpr (!SKIP && KT <= 4) {  // beyond 4 references the taps no longer fit the register budget
+    // hand-pipelined like rgb_pixel_lean: all K sample positions first, then the gathers of reference k+1 in flight
+    // while reference k is reduced (same operations in the same order: bit-identical to the generic kernel)
+    const float2* gxy = gxy0;
+    HotTap tp[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      tp[k] = make_hot_tap(gxy[k].x, gxy[k].y, (int)Ws, a.Hs, a.align_corners);
+      tp[k].off += k * 3 * (int)HWs;
+    }
+    float vbuf[2][12];
+    auto gather = [&](int k, float* v) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* p0 = rgb_base + ((unsigned)tp[k].off + (unsigned)c * HWs);
+        v[4 * c + 0] = __ldg(p0);
+        v[4 * c + 1] = __ldg(p0 + 1);
+        v[4 * c + 2] = __ldg(p0 + Ws);
+        v[4 * c + 3] = __ldg(p0 + Ws + 1);
+      }
+    };
+    gather(0, vbuf[0]);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      if (k + 1 < KT) gather(k + 1, vbuf[(k + 1) & 1]);
+      const float* v = vbuf[k & 1];
+      const float w = (aw[k] / ssum) * vf;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sacc = fmaf(v[4 * c + 0], tp[k].nw, 0.f);
+        sacc = fmaf(v[4 * c + 1], tp[k].ne, sacc);
+        sacc = fmaf(v[4 * c + 2], tp[k].sw, sacc);
+        sacc = fmaf(v[4 * c + 3], tp[k].se, sacc);
+        acc[c] = fmaf(w, sacc, acc[c]);
+      }
+    }
+  } else {
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
     const float v = b_vis ? __ldg(b_vis + ((unsigned)k * HW + pix)) : vf;
@@ -232,7 +334,8 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
       }
     }
   }
-  const float tm = b_mask ? __ldg(b_mask + pix) : 1.f;
+  }
+  if (!kEarly && b_mask) tm = __ldg(b_mask + pix);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float ov = acc[c];
@@ -413,10 +516,13 @@ __global__ void __launch_bounds__(256)
 k_warp_fuse_rgb(const WFArgs a) {
   const unsigned W = (unsigned)a.W, Ws = (unsigned)a.Ws;
   const unsigned HW = (unsigned)a.H * W, HWs = (unsigned)a.Hs * Ws;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)a.B * HW) return;
-  const int b = (int)(i / HW);
-  const unsigned pix = (unsigned)(i % HW);
+  // a CTA is a 32 x 8 pixel tile: the lower tap row of one pixel row is the upper tap row of the next (L1 hits)
+  const int tile = blockIdx.x % (a.tiles_x * a.tiles_y);
+  const int b = blockIdx.x / (a.tiles_x * a.tiles_y);
+  const unsigned x = (unsigned)(tile % a.tiles_x) * 32u + (threadIdx.x & 31u);
+  const unsigned y = (unsigned)(tile / a.tiles_x) * 8u + (threadIdx.x >> 5);
+  if (x >= W || y >= (unsigned)a.H) return;
+  const unsigned pix = y * W + x;
   const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
   const size_t bK = (size_t)b * KT * HW;
   rgb_pixel_lean<KT, SKIP>(a, a.rgb + r * KT * 3 * (size_t)HWs, reinterpret_cast<const float2*>(a.grid) + bK,
@@ -429,7 +535,10 @@ k_warp_fuse_rgb(const WFArgs a) {
 }
 
 template <int KT>
-void launch_rgb_k(const WFArgs& a, int grid, cudaStream_t st) {
+void launch_rgb_k(WFArgs a, int, cudaStream_t st) {
+  a.tiles_x = (a.W + 31) / 32;
+  a.tiles_y = (a.H + 7) / 8;
+  const int grid = a.tiles_x * a.tiles_y * a.B;
   if (a.vis != nullptr || a.fim != nullptr) k_warp_fuse_rgb<KT, true><<<grid, 256, 0, st>>>(a);
   else k_warp_fuse_rgb<KT, false><<<grid, 256, 0, st>>>(a);
 }
@@ -638,13 +747,20 @@ int wf_env(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-// resident CTAs per SM the kernel is compiled for (register cap = 65536 / (256 * MINB)); tunable
-int wf_minb() {
-  static int mb = [] {
-    const int v = wf_env("JAF_WF_MINB", 5);
+// Resident CTAs per SM the headline kernel is compiled for (register cap = 65536 / (256 * MINB)) and rows per CTA
+// tile; measured on the 240-frame workload.  Without a visibility input the hand-pipelined RGB phase wants 64 registers
+// (4 CTAs/SM, 32-row tiles: 87.8 k f/s vs 78.6 k at 5); with one, the skipping variant is best at 5 CTAs/SM and 16 rows
+// (216 k f/s on SMPL flows vs 189 k).
+int wf_minb(bool skip) {
+  static const int mb_dense = [] {
+    const int v = wf_env("JAF_WF_MINB", 4);
+    return (v >= 4 && v <= 6) ? v : 4;
+  }();
+  static const int mb_skip = [] {
+    const int v = wf_env("JAF_WF_MINB_SKIP", 5);
     return (v >= 4 && v <= 6) ? v : 5;
   }();
-  return mb;
+  return skip ? mb_skip : mb_dense;
 }
 
 template <int LPP, int KV>
@@ -652,7 +768,7 @@ bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
   if constexpr (KV <= LPP) {
     const bool skip = a.vis != nullptr || a.fim != nullptr;
     if constexpr (LPP == 8 && KV == 4) {  // the headline shape carries the occupancy variants
-      const int mb = wf_minb();
+      const int mb = wf_minb(skip);
       static const int rows = wf_env("JAF_WF_ROWS", 2);
 #define JAF_V(MB, R) if (mb == MB && rows == R) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true, R><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, R><<<grid, 256, 0, st>>>(a); return true; }
       JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1) JAF_V(4, 2) JAF_V(5, 2) JAF_V(6, 2)
@@ -701,8 +817,10 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
   const int ppw = 32 / lpp;
   const int tw = 8 * ppw;
   a.tiles_x = (a.W + tw - 1) / tw;
-  static const int rows_env = wf_env("JAF_WF_ROWS_PER_CTA", 16);
-  a.rows_per_cta = a.H < rows_env ? a.H : rows_env;
+  static const int rows_env = wf_env("JAF_WF_ROWS_PER_CTA", 0);
+  const bool tuned_dense = lpp == 8 && a.K == 4 && a.vis == nullptr && a.fim == nullptr;
+  const int rows_dflt = rows_env > 0 ? rows_env : (tuned_dense ? 32 : 16);
+  a.rows_per_cta = a.H < rows_dflt ? a.H : rows_dflt;
   a.tiles_y = (a.H + a.rows_per_cta - 1) / a.rows_per_cta;
   const long grid = (long)a.tiles_x * a.tiles_y * a.B;
   if (grid > 0x7fffffffL) return false;
