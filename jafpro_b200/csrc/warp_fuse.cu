@@ -754,7 +754,7 @@ int wf_env(const char* name, int dflt) {
 int wf_minb(bool skip) {
   static const int mb_dense = [] {
     const int v = wf_env("JAF_WF_MINB", 4);
-    return (v >= 4 && v <= 6) ? v : 4;
+    return (v >= 3 && v <= 6) ? v : 4;
   }();
   static const int mb_skip = [] {
     const int v = wf_env("JAF_WF_MINB_SKIP", 5);
@@ -771,7 +771,7 @@ bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
       const int mb = wf_minb(skip);
       static const int rows = wf_env("JAF_WF_ROWS", 2);
 #define JAF_V(MB, R) if (mb == MB && rows == R) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true, R><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, R><<<grid, 256, 0, st>>>(a); return true; }
-      JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1) JAF_V(4, 2) JAF_V(5, 2) JAF_V(6, 2)
+      JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1) JAF_V(3, 2) JAF_V(4, 2) JAF_V(5, 2) JAF_V(6, 2)
 #undef JAF_V
     }
     if (skip) k_warp_fuse_nhwc<LPP, KV, 6, true><<<grid, 256, 0, st>>>(a);
