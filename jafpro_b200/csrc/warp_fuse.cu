@@ -245,7 +245,8 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
 }
 
 // One output pixel of the RGB planes (planar fp32, the reference layout): softmax in the reference's
-// sequential order, ATen's tap order, acc += w_k * warped_k — bit-identical to k_warp_fuse_generic.
+// sequential order, ATen's tap order, acc += w_k * warped_k (the visibility-skipping flavour is bit-identical to
+// k_warp_fuse_generic; the pipelined one replaces the K softmax divisions by one reciprocal, <= 1 ulp).
 template <int KT, bool SKIP>
 __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restrict__ rgb_base,
                                           const float2* __restrict__ b_grid, const float* __restrict__ b_logit,
@@ -281,35 +282,41 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
     // hand-pipelined like rgb_pixel_lean: all K sample positions first, then the gathers of reference k+1 in flight
     // while reference k is reduced (same operations in the same order: bit-identical to the generic kernel)
     const float2* gxy = gxy0;
-    HotTap tp[KT];
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      tp[k] = make_hot_tap(gxy[k].x, gxy[k].y, (int)Ws, a.Hs, a.align_corners);
-      tp[k].off += k * 3 * (int)HWs;
-    }
+    // taps are built one reference ahead of their use (two live sets instead of K: no register spills at 64)
     float vbuf[2][12];
-    auto gather = [&](int k, float* v) {
+    auto tap_of = [&](int k) {
+      HotTap t = make_hot_tap(gxy[k].x, gxy[k].y, (int)Ws, a.Hs, a.align_corners);
+      t.off += k * 3 * (int)HWs;
+      return t;
+    };
+    auto gather = [&](const HotTap& t, float* v) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float* p0 = rgb_base + ((unsigned)tp[k].off + (unsigned)c * HWs);
+        const float* p0 = rgb_base + ((unsigned)t.off + (unsigned)c * HWs);
         v[4 * c + 0] = __ldg(p0);
         v[4 * c + 1] = __ldg(p0 + 1);
         v[4 * c + 2] = __ldg(p0 + Ws);
         v[4 * c + 3] = __ldg(p0 + Ws + 1);
       }
     };
-    gather(0, vbuf[0]);
+    const float inv = (KT == 1) ? 1.0f : __frcp_rn(ssum);  // one correctly-rounded reciprocal instead of K divisions
+    HotTap tn = tap_of(0);
+    gather(tn, vbuf[0]);
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
-      if (k + 1 < KT) gather(k + 1, vbuf[(k + 1) & 1]);
+      const HotTap tc = tn;
+      if (k + 1 < KT) {
+        tn = tap_of(k + 1);
+        gather(tn, vbuf[(k + 1) & 1]);
+      }
       const float* v = vbuf[k & 1];
-      const float w = (aw[k] / ssum) * vf;
+      const float w = (KT == 1) ? aw[k] : (aw[k] * inv);  // vf == 1 here (no visibility input)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float sacc = fmaf(v[4 * c + 0], tp[k].nw, 0.f);
-        sacc = fmaf(v[4 * c + 1], tp[k].ne, sacc);
-        sacc = fmaf(v[4 * c + 2], tp[k].sw, sacc);
-        sacc = fmaf(v[4 * c + 3], tp[k].se, sacc);
+        float sacc = fmaf(v[4 * c + 0], tc.nw, 0.f);
+        sacc = fmaf(v[4 * c + 1], tc.ne, sacc);
+        sacc = fmaf(v[4 * c + 2], tc.sw, sacc);
+        sacc = fmaf(v[4 * c + 3], tc.se, sacc);
         acc[c] = fmaf(w, sacc, acc[c]);
       }
     }
