@@ -247,7 +247,7 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
 // One output pixel of the RGB planes (planar fp32, the reference layout): softmax in the reference's
 // sequential order, ATen's tap order, acc += w_k * warped_k (the visibility-skipping flavour is bit-identical to
 // k_warp_fuse_generic; the pipelined one replaces the K softmax divisions by one reciprocal, <= 1 ulp).
-template <int KT, bool SKIP>
+template <int KT, bool SKIP, bool PIPE = (KT <= 4)>  // PIPE: hand-pipelined flavour (needs ~2*KT + 45 registers)
 __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restrict__ rgb_base,
                                           const float2* __restrict__ b_grid, const float* __restrict__ b_logit,
                                           const float* __restrict__ b_vis, const int* __restrict__ b_fim,
@@ -255,11 +255,11 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
                                           const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
                                           unsigned HW, unsigned HWs, unsigned Ws) {
   float2 gxy0[KT];
-  if constexpr (!SKIP && KT <= 4) {
+  if constexpr (!SKIP && PIPE) {
 #pragma unroll
     for (int k = 0; k < KT; ++k) gxy0[k] = __ldg(b_grid + ((unsigned)k * HW + pix));
   }
-  constexpr bool kEarly = !SKIP && KT <= 4;
+  constexpr bool kEarly = !SKIP && PIPE;
   float tm = 1.f;
   if (kEarly && b_mask) tm = __ldg(b_mask + pix);
   // softmax in the reference order: max, exp, running sum, divide
@@ -278,7 +278,7 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
   }
   const float vf = b_fim ? ((__ldg(b_fim + pix) != -1) ? 1.f : 0.f) : 1.f;
   float acc[3] = {0.f, 0.f, 0.f};
-  if constexpr (!SKIP && KT <= 4) {  // beyond 4 references the taps no longer fit the register budget
+  if constexpr (!SKIP && PIPE) {  // beyond 4 references the taps no longer fit the register budget
     // hand-pipelined like rgb_pixel_lean: all K sample positions first, then the gathers of reference k+1 in flight
     // while reference k is reduced (same operations in the same order: bit-identical to the generic kernel)
     const float2* gxy = gxy0;
@@ -669,6 +669,175 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
   }
 }
 
+// The same kernel for 5..8 references: every lane of the 4-lane group prepares two references (k = j and j + 4).
+// (Kept apart from the K <= 4 kernel: folding both into one template costs the headline shape 3.5 %, measured.)
+template <int KT, int MINB, bool SKIP>
+__global__ void __launch_bounds__(256, MINB)
+k_warp_fuse_nhwc_wide2(const WFArgs a) {
+  static_assert(KT <= 8, "each lane of the 4-lane pixel group prepares at most two references");
+  constexpr int LPP = 4, PPW = 8, TW = 64;
+  constexpr int NP = (KT + LPP - 1) / LPP;  // references prepared per lane: lane j takes k = j, j + 4
+  constexpr int KL = KT < LPP ? KT : LPP;   // lanes of a group that prepare slot 0
+  constexpr bool KPOW2 = (KL & (KL - 1)) == 0 && KT % KL == 0;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned PIXB = 128;  // bytes of one channels-last pixel (64 bf16)
+  int bid = blockIdx.x;
+  const int tx = bid % a.tiles_x;
+  bid /= a.tiles_x;
+  const int ty = bid % a.tiles_y;
+  const int b = bid / a.tiles_y;
+  const int y_begin = ty * a.rows_per_cta;
+  const int y_end = min(a.H, y_begin + a.rows_per_cta);
+  const unsigned W = (unsigned)a.W, Ws = (unsigned)a.Ws;
+  const unsigned HW = (unsigned)a.H * W, HWs = (unsigned)a.Hs * Ws;
+  const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
+  const size_t bK = (size_t)b * KT * HW;
+  const float* __restrict__ b_logit = a.logits ? a.logits + bK : nullptr;
+  const float* __restrict__ b_vis = a.vis ? a.vis + bK : nullptr;
+  const int* __restrict__ b_fim = (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr;
+  const float2* __restrict__ b_grid = reinterpret_cast<const float2*>(a.grid) + bK;
+  const float* __restrict__ b_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
+
+  // =========================== phase A: features ===========================
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPP, j = lane % LPP, gl = g * LPP;
+    const int x = tx * TW + warp * PPW + g;
+    const bool xin = x < (int)W;
+    const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + j * 32;
+    char* __restrict__ o_lane = reinterpret_cast<char*>(a.out_feat) + (size_t)b * HW * PIXB + j * 32;
+    const uint64_t keep = l2_policy_evict_last();
+    unsigned pix = (unsigned)y_begin * W + (unsigned)x;
+#pragma unroll 1
+    for (int y = y_begin; y < y_end; ++y, pix += W) {
+      // ---- prepare: slot n of lane j is reference kk = j % KL + n * LPP (surplus lanes / slots replicate or idle)
+      float lg[NP], vv[NP];
+      float2 gxy[NP];
+      bool act[NP];
+      float vm = 1.f;
+      if (xin) {
+        if (b_fim) vm = (ld_stream_s32(b_fim + pix) != -1) ? 1.f : 0.f;
+        if (b_mask) vm *= ld_stream_f32(b_mask + pix);  // fused*mask == sum_k (alpha_k vis_k mask) warped_k
+      }
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const int kk = j % KL + n * LPP;
+        act[n] = xin && kk < KT;
+        lg[n] = 0.f;
+        vv[n] = vm;
+        gxy[n] = make_float2(0.f, 0.f);
+        if (act[n]) {
+          const unsigned li = (unsigned)kk * HW + pix;
+          gxy[n] = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + li), keep);
+          if (b_logit) lg[n] = ld_stream_keep_f32(b_logit + li, keep);
+          if (b_vis) vv[n] = ld_stream_f32(b_vis + li) * (b_mask ? vm : 1.f);
+        }
+      }
+      // softmax over the K references: own slots first, then the KL preparing lanes of the group
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int n = 0; n < NP; ++n)
+        if (j % KL + n * LPP < KT) m = fmaxf(m, lg[n]);
+      if constexpr (KPOW2) {
+#pragma unroll
+        for (int s = KL / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
+      } else {
+        float mm = m;
+#pragma unroll
+        for (int k = 0; k < KL; ++k) mm = fmaxf(mm, __shfl_sync(FULL, m, gl + k));
+        m = mm;
+      }
+      float e[NP], esum = 0.f;
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        e[n] = expf(lg[n] - m);
+        if (j % KL + n * LPP < KT) esum += e[n];
+      }
+      float ssum;
+      if constexpr (KPOW2) {
+        ssum = esum;
+#pragma unroll
+        for (int s = 1; s < KL; s <<= 1) ssum += __shfl_xor_sync(FULL, ssum, s);
+      } else {
+        ssum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KL; ++k) ssum += __shfl_sync(FULL, esum, gl + k);
+      }
+      HotTap t[NP];
+      unsigned off[NP];
+      bool vis_any = false;
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const float aw = act[n] ? __fdividef(e[n], ssum) * vv[n] : 0.f;  // alpha_k * vis_k * mask
+        t[n] = make_hot_tap(gxy[n].x, gxy[n].y, (int)Ws, a.Hs, a.align_corners);
+        t[n].nw *= aw;
+        t[n].ne *= aw;
+        t[n].sw *= aw;
+        t[n].se *= aw;
+        off[n] = (aw != 0.f) ? (unsigned)t[n].off : 0u;
+        vis_any = vis_any || aw != 0.f;
+      }
+      const bool any = SKIP ? (__ballot_sync(FULL, vis_any) != 0u) : true;
+
+      float2 acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
+      if (any) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          const int src = gl + k % LPP, n = k / LPP;
+          const unsigned o0 = __shfl_sync(FULL, off[n], src) + (unsigned)k * HWs;
+          const char* p0 = f_lane + (size_t)o0 * PIXB;
+          const char* p1 = f_lane + (size_t)(o0 + Ws) * PIXB;
+          U256 q[4];
+          q[0] = ld_gather_u256(p0);
+          q[1] = ld_gather_u256(p0 + PIXB);
+          q[2] = ld_gather_u256(p1);
+          q[3] = ld_gather_u256(p1 + PIXB);
+          float wt[4];
+          wt[0] = __shfl_sync(FULL, t[n].nw, src);
+          wt[1] = __shfl_sync(FULL, t[n].ne, src);
+          wt[2] = __shfl_sync(FULL, t[n].sw, src);
+          wt[3] = __shfl_sync(FULL, t[n].se, src);
+#pragma unroll
+          for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+            const float2 w2 = make_float2(wt[tp], wt[tp]);
+            const uint32_t wd[8] = {q[tp].lo.x, q[tp].lo.y, q[tp].lo.z, q[tp].lo.w,
+                                    q[tp].hi.x, q[tp].hi.y, q[tp].hi.z, q[tp].hi.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
+          }
+        }
+      }
+      if (xin) {
+        uint4 o0v, o1v;
+        o0v.x = pack_bf16x2(acc[0].x, acc[0].y); o0v.y = pack_bf16x2(acc[1].x, acc[1].y);
+        o0v.z = pack_bf16x2(acc[2].x, acc[2].y); o0v.w = pack_bf16x2(acc[3].x, acc[3].y);
+        o1v.x = pack_bf16x2(acc[4].x, acc[4].y); o1v.y = pack_bf16x2(acc[5].x, acc[5].y);
+        o1v.z = pack_bf16x2(acc[6].x, acc[6].y); o1v.w = pack_bf16x2(acc[7].x, acc[7].y);
+        uint4* op = reinterpret_cast<uint4*>(o_lane + (size_t)pix * PIXB);
+        st_stream_u128(op, o0v);
+        st_stream_u128(op + 1, o1v);
+      }
+    }
+  }
+
+  // =========================== phase B: RGB ===========================
+  if (a.rgb != nullptr && a.out_rgb != nullptr) {
+    const float* __restrict__ rgb_base = a.rgb + r * KT * 3 * (size_t)HWs;
+    const float* __restrict__ b_fake = (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr;
+    const float* __restrict__ b_conf = (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr;
+    float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
+    const int npx = TW * (y_end - y_begin);
+    for (int p = threadIdx.x; p < npx; p += 256) {
+      const int x = tx * TW + p % TW, y = y_begin + p / TW;
+      if (x >= (int)W) continue;
+      rgb_pixel<KT, SKIP, true>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
+    }
+  }
+}
+
 // RGB-only calls (no feature tensor): one thread per pixel, the same per-pixel code as phase B
 template <int KT, bool SKIP>
 __global__ void __launch_bounds__(256)
@@ -980,7 +1149,7 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
   static const int wide_minb = wf_env("JAF_WF_WIDE_MINB", 4);
   static const int wide_rows = wf_env("JAF_WF_WIDE_ROWS_PER_CTA", 16);
   const bool wide_ok = wide_env == 2 || (wide_env == 1 && a.vis == nullptr && a.fim == nullptr);
-  if (wide_ok && a.C == 64 && a.K <= 4 && (reinterpret_cast<uintptr_t>(a.feat) & 31u) == 0 &&
+  if (wide_ok && a.C == 64 && a.K <= 8 && (reinterpret_cast<uintptr_t>(a.feat) & 31u) == 0 &&
       (reinterpret_cast<uintptr_t>(a.out_feat) & 31u) == 0) {
     a.tiles_x = (a.W + 63) / 64;
     a.rows_per_cta = a.H < wide_rows ? a.H : wide_rows;
@@ -990,6 +1159,13 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
       const bool skip = a.vis != nullptr || a.fim != nullptr;
 #define JAF_W(KV, MB) if (a.K == KV && wide_minb == MB) { if (skip) k_warp_fuse_nhwc_wide<KV, MB, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide<KV, MB, false><<<(unsigned)gridw, 256, 0, st>>>(a); return true; }
       JAF_W(4, 2) JAF_W(4, 3) JAF_W(4, 4) JAF_W(4, 5) JAF_W(4, 6) JAF_W(1, 4) JAF_W(2, 4) JAF_W(3, 4)
+      static const int wide_minb8 = wf_env("JAF_WF_WIDE_MINB8", 3);
+#define JAF_W8(KV) if (a.K == KV) { \
+        if (wide_minb8 == 4) { if (skip) k_warp_fuse_nhwc_wide2<KV, 4, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide2<KV, 4, false><<<(unsigned)gridw, 256, 0, st>>>(a); } \
+        else { if (skip) k_warp_fuse_nhwc_wide2<KV, 3, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide2<KV, 3, false><<<(unsigned)gridw, 256, 0, st>>>(a); } \
+        return true; }
+      JAF_W8(5) JAF_W8(6) JAF_W8(7) JAF_W8(8)
+#undef JAF_W8
 #undef JAF_W
     }
   }
