@@ -261,6 +261,32 @@ def test_warp_fuse_hot_kernel_matches_oracle(K, C):
     assert float((out_feat.float() - ref).abs().max()) <= 2e-2
 
 
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 8])
+def test_warp_fuse_wide_lane_kernel_matches_oracle(K):
+    """C = 64 without a visibility input takes the wide-lane kernel (4 lanes x 32 B per pixel, 256-bit gathers;
+    two references per lane beyond K = 4).  Ragged sizes: W is not a multiple of the 64-column tile, H is odd."""
+    B, H, W, C = 2, 37, 75, 64
+    c = _rand_case(B, K, C, H, W, seed=900 + K, Hs=29, Ws=58)
+    feat_bits = oracle.f32_to_bf16_bits(c["feat"].transpose(0, 1, 3, 4, 2))
+    o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=feat_bits, feat_layout="nhwc", feat_bf16=True,
+                         logits=c["logits"], tgt_mask=c["mask"])
+    feat = _cu(feat_bits.view(np.int16)).view(torch.bfloat16).permute(0, 1, 4, 2, 3)
+    n0 = _lib.launch_count()
+    out_rgb, out_feat = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, logits=_cu(c["logits"]),
+                                      tgt_mask=_cu(c["mask"]))
+    assert _lib.launch_count() == n0 + 1
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 2e-6
+    ok, frac = _bf16_close(_bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
+    assert ok and frac < 2e-3, frac
+    # the same call with an all-ones visibility map runs the 8-lane kernel: the two kernels agree
+    ones = torch.ones(B, K, H, W, device=DEV)
+    rgb2, feat2 = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, logits=_cu(c["logits"]), vis=ones,
+                                tgt_mask=_cu(c["mask"]))
+    assert float((rgb2 - out_rgb).abs().max()) <= 2e-6
+    ok2, frac2 = _bf16_close(_bf16_bits(feat2.permute(0, 2, 3, 1).contiguous()), _bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()))
+    assert ok2 and frac2 < 2e-3
+
+
 def test_warp_fuse_k1_is_exactly_warp_image_times_mask():
     c = _rand_case(2, 1, 64, 32, 32, seed=9)
     mask3 = np.repeat(c["mask"], 3, axis=1)
