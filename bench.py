@@ -326,7 +326,7 @@ def run_ours(args):
         sverts = torch.cat([v_[Fv:].unsqueeze(0).expand(Fv, -1, -1, -1) for v_ in verts]).contiguous()
 
         def pose_step():
-            T, fm, _ = ops.cal_flow_multi(scam, sverts, tcam, tverts, f_idx, S)
+            T, fm, _ = ops.cal_flow_multi(scam, sverts, tcam, tverts, f_idx, S, return_wim=False)
             return ops.warp_fuse(T, rgb=inp["rgb"], feat=feat, logits=inp["logits"], fim=fm, tgt_mask=inp["mask"])
 
         for _ in range(3):

@@ -299,9 +299,23 @@ k_raster_resolve(const unsigned long long* __restrict__ zbuf, const float* __res
   }
   if (fim) fim[o] = fn;
   if (wim) {
-    wim[o * 3 + 0] = w[0];
-    wim[o * 3 + 1] = w[1];
-    wim[o * 3 + 2] = w[2];
+    if ((is & 31) == 0) {
+      // a warp's 32 pixels are 96 consecutive floats of wim: hand the values round so that every store instruction
+      // writes 128 contiguous bytes (three strided 4-byte stores per lane would touch every sector three times)
+      const unsigned lane = threadIdx.x & 31u;
+      float* wbase = wim + (o - lane) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const unsigned e = lane + 32u * c, src = e / 3u, comp = e - 3u * src;
+        const float v0 = __shfl_sync(0xffffffffu, w[0], src), v1 = __shfl_sync(0xffffffffu, w[1], src);
+        const float v2 = __shfl_sync(0xffffffffu, w[2], src);
+        wbase[e] = comp == 0 ? v0 : (comp == 1 ? v1 : v2);
+      }
+    } else {
+      wim[o * 3 + 0] = w[0];
+      wim[o * 3 + 1] = w[1];
+      wim[o * 3 + 2] = w[2];
+    }
   }
   if (depth) depth[o] = zp;
   if (COMPOSE) {

@@ -43,7 +43,7 @@ def warp_fuse_from_poses(renderer, src_cams, src_vertices, tgt_cam, tgt_vertices
     Returns (out_rgb, out_feat, T, fim)."""
     T, fim, _ = ops.cal_flow_multi(src_cams.contiguous(), src_vertices.contiguous(), tgt_cam.contiguous(),
                                    tgt_vertices.contiguous(), renderer.faces, renderer.image_size,
-                                   eye_z=renderer._eye_z)
+                                   eye_z=renderer._eye_z, return_wim=False)
     vis = reference_visibility(renderer, src_cams, src_vertices, fim) if per_reference_visibility else None
     out_rgb, out_feat = ops.warp_fuse(T, rgb=rgb, feat=feat, logits=logits, vis=vis, fim=None if vis is not None else fim,
                                       tgt_mask=tgt_mask, ref_index=ref_index, align_corners=align_corners)

@@ -440,10 +440,11 @@ def texture_warp(tex_parts, iuv, align_corners: bool = False):
 
 # ----------------------------------------------------------------------------- a8 for K references
 def cal_flow_multi(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx, image_size: int, eye_z: float = EYE_Z,
-                   near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR, return_maps: bool = True):
+                   near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR, return_maps: bool = True,
+                   return_wim: bool = True):
     """Transfer flows from K source poses into one target pose per frame: the target is rasterised once,
     composed K times.  src_cam [B,K,3], src_vertices [B,K,V,3], tgt_cam [B,3], tgt_vertices [B,V,3]
-    -> T [B,K,S,S,2] (+ fim [B,S,S], wim [B,S,S,3])."""
+    -> T [B,K,S,S,2] (+ fim [B,S,S], wim [B,S,S,3]; wim is None with return_wim=False: it then never touches HBM)."""
     sc, sv = _check(src_cam, "src_cam", torch.float32), _check(src_vertices, "src_vertices", torch.float32)
     tc, tv = _check(tgt_cam, "tgt_cam", torch.float32), _check(tgt_vertices, "tgt_vertices", torch.float32)
     faces_idx = _check(faces_idx, "faces", torch.int32)
@@ -454,7 +455,7 @@ def cal_flow_multi(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx, imag
     dev = tv.device
     T = torch.empty((B, K, image_size, image_size, 2), dtype=torch.float32, device=dev)
     fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=dev) if return_maps else None
-    wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev) if return_maps else None
+    wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=dev) if (return_maps and return_wim) else None
     with _on(dev):
         ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, image_size))
         _lib.check(_lib.lib().jaf_cal_flow_multi(_ptr(sc), _ptr(sv), _ptr(tc), _ptr(tv), _ptr(faces_idx), B, K, V, F,
