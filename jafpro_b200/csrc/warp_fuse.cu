@@ -262,6 +262,24 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
   constexpr bool kEarly = !SKIP && PIPE;
   float tm = 1.f;
   if (kEarly && b_mask) tm = __ldg(b_mask + pix);
+  if constexpr (SKIP) {
+    // pixel-level visibility (fim): a background pixel contributes nothing whatever the logits are — write the empty
+    // result (or the blend with it) without touching logits, flows or references
+    if (b_fim != nullptr && b_vis == nullptr && __ldg(b_fim + pix) == -1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float ov = 0.f;
+        if (b_mask) ov *= (a.mask_c == 3) ? __ldg(b_mask + ((unsigned)c * HW + pix)) : __ldg(b_mask + pix);
+        if (b_fake) {
+          const float wc = __ldg(b_conf + pix);
+          const float fkv = __ldg(b_fake + ((unsigned)c * HW + pix));
+          ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+        }
+        st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
+      }
+      return;
+    }
+  }
   // softmax in the reference order: max, exp, running sum, divide
   float aw[KT];
   float m = -CUDART_INF_F;
@@ -418,11 +436,25 @@ k_warp_fuse_nhwc(const WFArgs a) {
       const bool pin = xin && (y + rr < y_end);
       float lg = 0.f, v = 1.f;
       float2 gxy = make_float2(0.f, 0.f);
+      if constexpr (SKIP) {
+        if (b_fim != nullptr) {  // uniform.  Pixel-level visibility: look at the face-index map first
+          if (pin) v = (ld_stream_s32(b_fim + (pix + (unsigned)rr * W)) != -1) ? 1.f : 0.f;
+          if (__ballot_sync(FULL, pin && v != 0.f) == 0u) {
+            // every pixel this warp owns in these rows is background: empty output, no flow / logit / reference read
+            if (xin) {
+#pragma unroll
+              for (int rs = 0; rs < ROWS; ++rs)
+                if (y + rs < y_end) st_stream_u128(o_lane + (size_t)(pix + (unsigned)rs * W) * LPP, make_uint4(0u, 0u, 0u, 0u));
+            }
+            continue;
+          }
+        }
+      }
       if (pin) {
         gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
         if (b_logit) lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
         if (b_vis) v = ld_stream_f32(b_vis + (lane_in + pix));
-        if (b_fim) v = (ld_stream_s32(b_fim + (pix + (unsigned)rr * W)) != -1) ? 1.f : 0.f;
+        if (!SKIP && b_fim) v = (ld_stream_s32(b_fim + (pix + (unsigned)rr * W)) != -1) ? 1.f : 0.f;
         if (b_mask) v *= ld_stream_f32(b_mask + (pix + (unsigned)rr * W));  // fused*mask == sum_k (alpha_k vis_k mask) warped_k
       }
       // softmax over the KT lanes of this row slot (they are an aligned block when KT is a power of two)
