@@ -804,3 +804,14 @@ def test_transfer_texture_and_compute_angle_match_the_reference_functions(golden
     angles = compute_angles(_cu(iuv))
     assert [float(a) for a in angles] == [float(a) for a in d["angles"]]   # bit-identical float64
     assert float(compute_angle(iuv[2])) == float(d["angles"][2])
+
+
+def test_example_video_pipeline_runs():
+    """examples/video_pipeline.py chains every drop-in on one synthetic video; it must keep running end to end."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "examples", "video_pipeline.py")], capture_output=True,
+                         text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip().endswith("ok")
