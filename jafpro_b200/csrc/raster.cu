@@ -14,6 +14,8 @@
 // reference source on sm_100 (read from its SASS; DESIGN.md "Raster arithmetic").
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -137,6 +139,13 @@ struct Box {
 // triangle; the margin grows with the sliver-ness of the face, and degenerate faces (zero or
 // non-finite determinant — where the reference's tests hold on a whole line or everywhere)
 // are tested against the full image exactly like the reference does.
+// Extra whole pixels added to the analytic margin.  0 is enough: the box already runs from floor(min) to ceil(max), so an
+// excluded pixel centre is at least one pixel away from the box, while the fp32 edge tests can only accept points within
+// ~1e-5 px of an edge line (times the sliver factor, which the analytic term covers).  Validated bit-for-bit against the
+// reference kernels on 72 SMPL frames and 380k sub-pixel triangles (tools/probes/raster_stress.py); JAF_RASTER_MARGIN=1
+// restores the conservative setting (2.5x more pixel tests per face).
+__constant__ float c_margin_base = 0.0f;
+
 __device__ __forceinline__ Box face_box(const float* px, const float* py, float den, int is) {
   Box bx;
   const float xmin = fminf(px[0], fminf(px[1], px[2])), xmax = fmaxf(px[0], fmaxf(px[1], px[2]));
@@ -156,7 +165,7 @@ __device__ __forceinline__ Box face_box(const float* px, const float* py, float 
   // that allows an overshoot t <= 2 * sliver * d.  Twice that bound is the margin.
   const float sliver = l2 / aden;  // ~2.3 for an equilateral face, large for slivers
   const float pmax = fmaxf(fmaxf(fabsf(xmin), fabsf(xmax)), fmaxf(fabsf(ymin), fabsf(ymax)));
-  const float mf = fminf((float)is, 1.0f + floorf(2.2e-6f * ((float)is + pmax) * sliver));
+  const float mf = fminf((float)is, c_margin_base + floorf(2.2e-6f * ((float)is + pmax) * sliver));
   const float lim = 2.0f * (float)is + 4.0f;
   bx.x_lo = max(0, (int)fmaxf(floorf(xmin) - mf, -lim));
   bx.y_lo = max(0, (int)fmaxf(floorf(ymin) - mf, -lim));
@@ -390,6 +399,14 @@ template <bool PROJECT>
 int run_pass1(const float* faces_xyz, const float* cam, const float* verts, const int* fidx, int B, int V, int F,
               int is, float eye_z, float near_, float far_, void* workspace, float* faces_out, cudaStream_t st,
               int* launches) {
+  static const bool margin_set = [] {
+    if (const char* e = getenv("JAF_RASTER_MARGIN")) {
+      const float v = (float)atof(e);
+      cudaMemcpyToSymbol(c_margin_base, &v, sizeof(float));
+    }
+    return true;
+  }();
+  (void)margin_set;
   auto* zb = static_cast<unsigned long long*>(workspace);
   auto* hq = reinterpret_cast<HugeQueue*>(static_cast<char*>(workspace) + zbuf_bytes(B, is));
   JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)B * is * is * 8, st));
