@@ -815,3 +815,29 @@ def test_example_video_pipeline_runs():
                          text=True, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip().endswith("ok")
+
+
+def test_raster_box_margin_stress_against_reference_kernels():
+    """The scatter pass tests only the pixels of [floor(min), ceil(max)] (+ the analytic sliver margin).  Guard that
+    choice where it could bite: many poses and soups of sub-pixel triangles at random sub-pixel positions, bit-exact
+    against the reference's own kernels (a slimmed tools/probes/raster_stress.py)."""
+    try:
+        ref = oracle.RefRaster()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libjaf_ref_raster.so not built (needs /root/reference at build time)")
+    rend = SMPLRenderer(image_size=256).to(DEV)
+    cam, verts = synth.smpl_poses(16, seed=404, device=DEV)
+    for i in range(0, 16, 8):
+        faces, fim, wim = rend.render_fim_wim(cam[i:i + 8].contiguous(), verts[i:i + 8].contiguous())
+        rfim, rwim, _ = ref(faces, 256)
+        assert torch.equal(fim, rfim) and np.array_equal(_bits(wim), _bits(rwim))
+    g = torch.Generator().manual_seed(9)
+    for size, nf, scale in ((128, 30000, 0.01), (64, 20000, 0.004), (200, 20000, 0.02)):
+        c = torch.rand((2, nf, 1, 3), generator=g) * 2.2 - 1.1
+        tri = c + (torch.rand((2, nf, 3, 3), generator=g) - 0.5) * 2 * scale
+        tri[..., 2] = torch.rand((2, nf, 3), generator=g) * 3 + 0.5
+        tri = tri.to(DEV).contiguous()
+        a = ops.raster_fim_wim(tri, size, return_depth=True)
+        b = ref(tri, size)
+        assert torch.equal(a[0], b[0]), size
+        assert np.array_equal(_bits(a[1]), _bits(b[1])) and np.array_equal(_bits(a[2]), _bits(b[2])), size
