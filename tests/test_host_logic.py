@@ -100,3 +100,12 @@ def test_compute_angle_host_formula_matches_reference_fixture(golden_dir):
         xs = np.broadcast_to(np.arange(part.shape[1])[None], part.shape)
         sumx = np.array([xs[part == p].sum() for p in range(32)])
         assert float(_angle_from_stats(counts, sumx)) == float(d["angles"][i])
+
+
+def test_bind_to_gpu_cpus_is_a_no_op_without_nvml():
+    """The per-rank CPU binding used by the host-buffer path must never raise: without a GPU (or NVML) it reports
+    False and leaves the affinity alone."""
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert jdist.bind_to_gpu_cpus(0) is False
+    assert os.sched_getaffinity(0) == before or torch.cuda.is_available()
