@@ -106,7 +106,8 @@ extern "C" int jaf_warp_fuse_host(const JafWarpFuseParams* hp, int frames_per_ch
   }
   if (n > B) n = B;
 
-  // resident reference sets (ref_index given): upload once
+  // resident reference sets (ref_index given): each is uploaded once
+  std::vector<char> ref_done;
   const float* d_ref_rgb = nullptr;
   const void* d_ref_feat = nullptr;
   if (hp->ref_index) {
@@ -115,15 +116,18 @@ extern "C" int jaf_warp_fuse_host(const JafWarpFuseParams* hp, int frames_per_ch
       JAF_REQUIRE(hp->ref_index[b] >= 0, "negative ref_index");
       if (hp->ref_index[b] + 1 > R) R = hp->ref_index[b] + 1;
     }
+    // reference sets go up lazily, right before the first chunk that uses them: the pipeline starts after ONE set has
+    // arrived instead of all R (for a 30-frame video per set that is most of the prologue)
     if (want_rgb) {
-      JAF_TRY(h2d(P.ref_rgb, hp->rgb, rgb_set * R, P.s_in));
+      JAF_TRY(P.ref_rgb.ensure(rgb_set * R));
       d_ref_rgb = static_cast<const float*>(P.ref_rgb.p);
     }
     if (want_feat) {
-      JAF_TRY(h2d(P.ref_feat, hp->feat, feat_set * R, P.s_in));
+      JAF_TRY(P.ref_feat.ensure(feat_set * R));
       d_ref_feat = P.ref_feat.p;
     }
     JAF_TRY(h2d(P.ref_index, hp->ref_index, sizeof(int32_t) * B, P.s_in));
+    ref_done.assign((size_t)R, 0);
   }
 
   const int nchunks = (B + n - 1) / n;
@@ -134,6 +138,20 @@ extern "C" int jaf_warp_fuse_host(const JafWarpFuseParams* hp, int frames_per_ch
     // the slot's previous result must have left before its inputs/outputs are overwritten
     if (ci >= 2) JAF_CUDA(cudaStreamWaitEvent(P.s_in, S.downloaded, 0));
     // ---- upload
+    if (hp->ref_index) {
+      for (int bb = b0; bb < b0 + nb; ++bb) {
+        const int rset = hp->ref_index[bb];
+        if (ref_done[rset]) continue;
+        ref_done[rset] = 1;
+        if (want_rgb)
+          JAF_CUDA(cudaMemcpyAsync(static_cast<char*>(P.ref_rgb.p) + rgb_set * rset, hp->rgb + (size_t)rset * K * 3 * HWs,
+                                   rgb_set, cudaMemcpyHostToDevice, P.s_in));
+        if (want_feat)
+          JAF_CUDA(cudaMemcpyAsync(static_cast<char*>(P.ref_feat.p) + feat_set * rset,
+                                   static_cast<const char*>(hp->feat) + feat_set * rset, feat_set,
+                                   cudaMemcpyHostToDevice, P.s_in));
+      }
+    }
     JAF_TRY(h2d(S.grid, hp->grid + (size_t)b0 * K * HW * 2, (size_t)nb * K * HW * 8, P.s_in));
     if (hp->logits) JAF_TRY(h2d(S.logits, hp->logits + (size_t)b0 * K * HW, (size_t)nb * K * HW * 4, P.s_in));
     if (hp->vis) JAF_TRY(h2d(S.vis, hp->vis + (size_t)b0 * K * HW, (size_t)nb * K * HW * 4, P.s_in));
