@@ -2,19 +2,24 @@
 """Benchmark of the appearance warp-and-fuse hot path (BASELINE.json metric: warped+fused frames/s
 at 256^2, K=4; HBM GB/s vs peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--flow KIND]
 
-A "step" is one pass of the fused warp+fuse kernel over one batch of synthetic DanceVideo-shaped
-input: BASELINE config 2 = 8 videos x 30 target frames per GPU (240 frames), 256x256, K=4 references
-per frame, RGB f32 + 64-channel bf16 features.  Work per GPU is fixed (weak scaling); videos are
-sharded by rank with NO collective on the hot path — the only collectives are the barrier around the
-timed region and the final reduction/gather of counters.
+Default workload (the headline): a "step" is one pass of the fused warp+fuse kernel over one batch of synthetic
+DanceVideo-shaped input: BASELINE config 2 = 8 videos x 30 target frames per GPU (240 frames), 256x256, K=4
+references per frame, RGB f32 + 64-channel bf16 features.  Work per GPU is fixed (weak scaling); videos are
+sharded by rank with NO collective on the hot path — the only collectives are the barrier around the timed
+region and the final reduction/gather of counters.
 
-Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM;
-`e2e` = the same metric through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed
-region); `roofline` = algorithmic bytes / CUDA-event time of the kernel vs the measured HBM copy peak;
-`cpu_baseline` = the same operation on the box's host cores (oracle port), bounded sample.
-`--impl reference` times that CPU path alone (rank 0 only).
+Prints ONE JSON line (rank 0).  `value` = whole-job throughput with inputs resident in HBM; `e2e` = the same
+metric through the host-buffer C-ABI call (H2D + kernels + D2H inside the timed region); `roofline` =
+algorithmic bytes (or flops) of the dominant kernel / its CUDA-event time vs the measured peak; `cpu_baseline` =
+the same operation on the box's host cores (oracle port), bounded sample.  `--impl reference` times that CPU
+path alone (rank 0 only) with the same `config`.
+
+Other workloads (BASELINE configs 1, 3, 4, 5 and diagnostics), each with roofline + cpu_baseline + clocks:
+    scaled_512_k8_c64   config 5 (512^2, K=8; 8 videos per GPU)          rgb_only_256_k4   RGB planes only
+    c1_latency          config 1 (1 reference, batch 1: latency)        c3_flow           config 3 (poses -> flow, 30 frames)
+    c4_convlstm         config 4 (fusion at 64^2 x 256 ch + K=4 tcgen05 ConvLSTM steps, B=16)
 """
 import argparse
 import json
@@ -33,7 +38,7 @@ import torch  # noqa: E402
 METRIC = "warped+fused frames/sec @256^2 K=4"
 UNIT = "frames/s"
 
-WORKLOADS = {
+WF_WORKLOADS = {
     # name: (videos per GPU, frames per video, H=W, K, C)
     "dancevideo_256_k4_c64": (8, 30, 256, 4, 64),      # BASELINE configs[1]  (the headline)
     "scaled_512_k8_c64": (8, 30, 512, 8, 64),          # BASELINE configs[4]: 64 videos over 8 GPUs
@@ -41,17 +46,21 @@ WORKLOADS = {
     "diag_240_k4_c64": (8, 30, 240, 4, 64),            # non-power-of-two strides (diagnostics)
     "diag_272_k4_c64": (8, 30, 272, 4, 64),
 }
+AUX_WORKLOADS = ("c1_latency", "c3_flow", "c4_convlstm")
+FLOWS = ("dense", "smpl", "hard", "perm")
 
 
-def load_peak():
+def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
             d = json.load(open(path))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
+            return {"hbm": float(d["hbm_gbs"]), "tf_burst": float(d["bf16_tflops"]),
+                    "tf_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    "source": "measured (MEASURED_PEAKS.json)"}
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)", {}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -104,18 +113,106 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def timed(fn, steps, warmup, dev=None, sampler=None, barrier=None):
+    """W warm-ups, then exactly `steps` calls bracketed by CUDA events on the current stream.
+    -> (total_ms, sorted per-call ms, result of the last call)."""
+    out = None
+    for _ in range(max(3, warmup)):
+        out = fn()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+        torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    global last_timed_launches
+    from jafpro_b200 import _lib
+    n0 = _lib.launch_count()
+    ev[0].record()
+    for s in range(steps):
+        out = fn()
+        ev[s + 1].record()
+    torch.cuda.synchronize()
+    last_timed_launches = _lib.launch_count() - n0
+    if barrier:
+        barrier()
+    total = ev[0].elapsed_time(ev[-1])
+    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    return total, per, out
+
+
+last_timed_launches = 0  # kernels of this library launched inside the most recent timed() region
+
+
+# ----------------------------------------------------------------------------------------------------------
+# configuration shared by both arms (the driver compares `config` of the two JSON lines)
+# ----------------------------------------------------------------------------------------------------------
+def config_for(args, world):
+    from jafpro_b200 import _lib
+    wl = args.workload
+    cfg = {"workload": wl}
+    if wl in WF_WORKLOADS:
+        V, Fv, S, K, C = WF_WORKLOADS[wl]
+        alg = wf_alg_bytes_dense(K, S, C) * V * Fv
+        cfg.update({"videos_per_gpu": V, "frames_per_video": Fv, "frames_per_step_per_gpu": V * Fv, "H": S, "W": S,
+                    "K": K, "C": C, "flow": args.flow,
+                    "parallelism": f"video-sharded x{world}, no hot-path collective",
+                    "l2": "inputs larger than L2 (every frame owns its K references: %.1f GB read per step)" % (alg / 1e9),
+                    "layout": "refs RGB planar f32 + features channels-last bf16"})
+    elif wl == "c1_latency":
+        cfg.update({"H": 256, "W": 256, "K": 1, "C": 0, "batch": 1, "parallelism": f"replicas x{world}",
+                    "l2": "latency workload: 2.4 MB per call, L2 flushed between timed calls"})
+    elif wl == "c3_flow":
+        cfg.update({"frames_per_step_per_gpu": 30, "H": 256, "W": 256, "vertices": 6890, "faces": 13776,
+                    "parallelism": f"frame-sharded x{world}, no collective",
+                    "l2": "L2 flushed between timed calls (working set 3 MB per frame)"})
+    elif wl == "c4_convlstm":
+        cfg.update({"B": 16, "H": 64, "W": 64, "Cin": 256, "Ch": 256, "K": 4, "parallelism": f"replicas x{world}",
+                    "l2": "activations + state 0.4 GB per step > L2"})
+    try:
+        cfg["knobs"] = _lib.tuning_info()
+    except Exception as e:  # library missing: the reference arm still runs
+        cfg["knobs"] = {"unavailable": str(e)[:80]}
+    return cfg
+
+
+def wf_alg_bytes_dense(K, S, C):
+    from jafpro_b200 import synth
+    return synth.warp_fuse_bytes(K, S, S, C)
+
+
+def wf_alg_bytes_visible(K, S, C, n_frames, n_visible):
+    """Real (SMPL) flows with pixel-level visibility: the face-index map is read for every pixel and the outputs are
+    written for every pixel; flows, logits, references and the target mask only matter where the pixel is visible."""
+    hw = S * S
+    return n_frames * hw * (4 + 12 + 2 * C) + n_visible * (K * (8 + 4 + 12 + 2 * C) + 4)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# warp+fuse workloads
+# ----------------------------------------------------------------------------------------------------------
 def make_inputs(wl, rank, device, flow="dense"):
     """Per-rank synthetic inputs, resident on `device`.  Every target frame has its own K reference
     images/feature maps, so each step reads ~11.8 GB of distinct data (>> the 126 MB L2): the HBM
     numbers are honest and no L2 flush is needed between timed iterations."""
     from jafpro_b200 import synth
-    V, Fv, S, K, C = WORKLOADS[wl]
+    V, Fv, S, K, C = WF_WORKLOADS[wl]
     B = V * Fv
     seed = 1000 + rank
     rgb, feat = synth.reference_sets(B, K, C, S, S, seed=seed, device=device, channels_last=True)
+    fim = None
     if flow == "dense":
         grid = synth.dense_flows(B, K, S, S, seed=seed, device=device)
-        fim = None
+    elif flow == "hard":
+        grid = torch.empty((B, K, S, S, 2), dtype=torch.float32, device=device)
+        for v in range(V):  # chunked: the generator's temporaries stay small
+            grid[v * Fv:(v + 1) * Fv] = synth.hard_flows(Fv, K, S, S, seed=seed * 100 + v, device=device,
+                                                         max_disp_px=64.0 * S / 256)
+    elif flow == "perm":
+        grid = torch.empty((B, K, S, S, 2), dtype=torch.float32, device=device)
+        for v in range(V):
+            grid[v * Fv:(v + 1) * Fv] = synth.perm_flows(Fv, K, S, S, seed=seed * 100 + v, device=device)
     else:  # transfer flows from random SMPL poses through the real raster+compose path (~12 % foreground)
         from jafpro_b200 import ops
         from jafpro_b200.nmr import load_smpl_template
@@ -137,83 +234,86 @@ def make_inputs(wl, rank, device, flow="dense"):
     return dict(B=B, K=K, C=C, S=S, rgb=rgb, feat=feat, grid=grid, logits=logits, mask=mask, fim=fim)
 
 
-def cpu_leg(wl, budget_s=12.0, seed=0):
+def cpu_frames_per_pass(S, K, C):
+    """Frames of one CPU pass: one 30-frame video when its fp32 working set stays under ~2.5 GB."""
+    per_frame = K * S * S * 4 * (3 + C + 3) + S * S * 4 * (3 + C)
+    return max(1, min(30, int(2.5e9 // max(1, per_frame))))
+
+
+class CpuWarpFuse:
     """The same operation on the host cores: the C oracle (OpenMP, channels-last fp32) and the torch-CPU
-    composition of the reference's primitives; reports the faster.  Bounded sample."""
-    import numpy as np
-    import oracle
-    from oracle.torch_ref import warp_fuse_torch
-    from jafpro_b200 import synth
-    V, Fv, S, K, C = WORKLOADS[wl]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    oracle.set_num_threads(cores)
-    n = 2
-    rgb, feat = synth.reference_sets(n, K, C, S, S, seed=seed, channels_last=False)
-    grid = synth.dense_flows(n, K, S, S, seed=seed)
-    logits = torch.randn(n, K, S, S)
-    mask = torch.ones(n, 1, S, S)
-    featf = feat.float() if feat is not None else None
-    res = {}
-    # torch CPU (the reference's primitives)
-    warp_fuse_torch(grid, rgb, featf, logits, None, mask)
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
-        warp_fuse_torch(grid, rgb, featf, logits, None, mask)
-        reps += 1
-        if time.perf_counter() - t0 > budget_s / 2 or reps >= 20:
-            break
-    res["torch_cpu"] = n * reps / (time.perf_counter() - t0)
-    # C oracle
-    g, r, l, m = grid.numpy(), rgb.numpy(), logits.numpy(), mask.numpy()
-    fn = np.ascontiguousarray(featf.numpy().transpose(0, 1, 3, 4, 2)) if featf is not None else None
-    kw = dict(rgb=r, logits=l, tgt_mask=m)
-    if fn is not None:
-        kw.update(feat=fn, feat_layout="nhwc")
-    oracle.warp_fuse(g, **kw)
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
-        oracle.warp_fuse(g, **kw)
-        reps += 1
-        if time.perf_counter() - t0 > budget_s / 2 or reps >= 20:
-            break
-    res["c_oracle_openmp"] = n * reps / (time.perf_counter() - t0)
-    best = max(res, key=res.get)
-    return {"value": round(res[best], 2), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} frames of {wl} per pass, fp32, repeated for ~{budget_s / 2:.0f}s per variant; "
+    composition of the reference's primitives (oracle/torch_ref.py).  One pass = `n` frames."""
+
+    def __init__(self, wl, flow="dense", seed=0):
+        import numpy as np
+        import oracle
+        from jafpro_b200 import synth
+        V, Fv, S, K, C = WF_WORKLOADS[wl]
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        oracle.set_num_threads(self.cores)
+        self.n = n = cpu_frames_per_pass(S, K, C)
+        rgb, feat = synth.reference_sets(n, K, C, S, S, seed=seed, channels_last=False)
+        gen = {"hard": synth.hard_flows, "perm": synth.perm_flows}.get(flow, synth.dense_flows)
+        self.grid = gen(n, K, S, S, seed=seed)  # (smpl flows need the GPU rasteriser: the CPU arm times the dense ones)
+        self.logits = torch.randn(n, K, S, S)
+        self.mask = torch.ones(n, 1, S, S)
+        self.rgb = rgb
+        self.featf = feat.float() if feat is not None else None
+        self.kw = dict(rgb=rgb.numpy(), logits=self.logits.numpy(), tgt_mask=self.mask.numpy())
+        if self.featf is not None:
+            self.kw.update(feat=np.ascontiguousarray(self.featf.numpy().transpose(0, 1, 3, 4, 2)), feat_layout="nhwc")
+        self.g_np = self.grid.numpy()
+        self.wl = wl
+
+    def run_torch(self):
+        from oracle.torch_ref import warp_fuse_torch
+        warp_fuse_torch(self.grid, self.rgb, self.featf, self.logits, None, self.mask)
+
+    def run_c(self):
+        import oracle
+        oracle.warp_fuse(self.g_np, **self.kw)
+
+    def rate(self, fn, budget_s, max_reps=20):
+        fn()
+        t0 = time.perf_counter()
+        reps = 0
+        while True:
+            fn()
+            reps += 1
+            if time.perf_counter() - t0 > budget_s or reps >= max_reps:
+                break
+        return self.n * reps / (time.perf_counter() - t0)
+
+    def best(self, budget_s=12.0):
+        res = {"torch_cpu": self.rate(self.run_torch, budget_s / 2), "c_oracle_openmp": self.rate(self.run_c, budget_s / 2)}
+        name = max(res, key=res.get)
+        return name, res
+
+
+def cpu_baseline_wf(wl, flow, budget_s=12.0):
+    leg = CpuWarpFuse(wl, flow)
+    name, res = leg.best(budget_s)
+    return {"value": round(res[name], 2), "unit": UNIT, "cores": leg.cores, "kind": "port",
+            "sample": f"{leg.n} frames of {wl} per pass (one video), fp32, repeated for ~{budget_s / 2:.0f}s per variant; "
                       f"best of {{torch CPU grid_sample composition: {res['torch_cpu']:.2f}, "
-                      f"C oracle OpenMP channels-last: {res['c_oracle_openmp']:.2f}}} = {best}"}
+                      f"C oracle OpenMP channels-last: {res['c_oracle_openmp']:.2f}}} = {name}"}
 
 
-def run_reference(args):
-    """--impl reference: the CPU implementation of the path on the host cores, rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    wl = args.workload
-    V, Fv, S, K, C = WORKLOADS[wl]
-    t0 = time.perf_counter()
-    vals = []
-    for _ in range(max(1, args.warmup // 3)):
-        cpu_leg(wl, budget_s=2.0)
-    for s in range(args.steps):
-        vals.append(cpu_leg(wl, budget_s=max(2.0, 60.0 / args.steps), seed=s))
-    best = max(vals, key=lambda d: d["value"])
-    mean = sum(d["value"] for d in vals) / len(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": round(mean, 2), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * (time.perf_counter() - t0) / max(1, args.steps), 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl, "frames_per_step": 2, "K": K, "C": C, "H": S, "W": S,
-                       "note": "reference torch/CPU path of the same fused op on the host cores; bounded sample per step"},
-            "cpu_baseline": dict(best, value=round(mean, 2)),
-            "e2e": {"value": round(mean, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    emit(line)
+def load_traffic(wl, flow, kernel):
+    """DRAM bytes of one launch from an `ncu --set full` capture of THIS kernel variant (tools/ncu_traffic.py writes
+    profiles/r02_traffic.json); None when no capture of the kernel that ran exists."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        rec = json.load(open(path)).get(f"{wl}|{flow}")
+    except Exception:
+        return None, None
+    if not rec or rec.get("kernel") != kernel:
+        return None, None
+    return rec.get("dram_bytes"), rec.get("source")
 
 
-def run_ours(args):
+def run_wf(args):
     from jafpro_b200 import _lib, dist as jd, ops, synth
     rank, world, local = jd.init()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -222,7 +322,7 @@ def run_ours(args):
     full_affinity = os.sched_getaffinity(0)
     numa_bound = jd.bind_to_gpu_cpus(local)  # pinned e2e buffers land on the GPU's NUMA node
     wl = args.workload
-    V, Fv, S, K, C = WORKLOADS[wl]
+    V, Fv, S, K, C = WF_WORKLOADS[wl]
     inp = make_inputs(wl, rank, dev, args.flow)
     B = inp["B"]
     feat = inp["feat"]
@@ -231,26 +331,12 @@ def run_ours(args):
         return ops.warp_fuse(inp["grid"], rgb=inp["rgb"], feat=feat, logits=inp["logits"], fim=inp["fim"],
                              tgt_mask=inp["mask"])
 
-    for _ in range(max(3, args.warmup)):
-        out = step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    jd.barrier()
-    torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    n0 = _lib.launch_count()
-    ev[0].record()
-    for s in range(args.steps):
-        out = step()
-        ev[s + 1].record()
-    torch.cuda.synchronize()
-    launches = _lib.launch_count() - n0
-    jd.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    step()
+    kernel = _lib.last_kernel()
+    total_ms, per_launch_ms, out = timed(step, args.steps, args.warmup, sampler=sampler, barrier=jd.barrier)
+    launches = last_timed_launches
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
     max_ms, total_frames = jd.reduce_max_sum(total_ms, float(B * args.steps), device=dev)
     value = total_frames / (max_ms / 1000.0)
 
@@ -308,44 +394,13 @@ def run_ours(args):
     h2d = nbytes(common + [hv_rgb, hv_feat, ref_index])
     h2d_b = nbytes(common + [hf_rgb, hf_feat])
     d2h = nbytes([o_rgb, o_feat])
+    del hf_rgb, hf_feat
 
     # ---- the whole §8 path from poses (rows a1-a12): per step, the transfer flows of the K reference poses into every
     # target pose (one raster per target, K composes) followed by the fused warp + fusion with fim visibility
     from_poses = None
-    if feat is not None:
-        from jafpro_b200.nmr import load_smpl_template
-        f_idx = torch.from_numpy(load_smpl_template()[1]).to(dev)
-        cams, verts = [], []
-        for v in range(V):
-            c_, v_ = synth.smpl_poses(Fv + K, seed=(1000 + rank) * 100 + v, device=dev)
-            cams.append(c_)
-            verts.append(v_)
-        tcam = torch.cat([c_[:Fv] for c_ in cams]).contiguous()
-        tverts = torch.cat([v_[:Fv] for v_ in verts]).contiguous()
-        scam = torch.cat([c_[Fv:].unsqueeze(0).expand(Fv, -1, -1) for c_ in cams]).contiguous()
-        sverts = torch.cat([v_[Fv:].unsqueeze(0).expand(Fv, -1, -1, -1) for v_ in verts]).contiguous()
-
-        def pose_step():
-            T, fm, _ = ops.cal_flow_multi(scam, sverts, tcam, tverts, f_idx, S, return_wim=False)
-            return ops.warp_fuse(T, rgb=inp["rgb"], feat=feat, logits=inp["logits"], fim=fm, tgt_mask=inp["mask"])
-
-        for _ in range(3):
-            pose_step()
-        n = max(3, min(args.steps, 20))
-        jd.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n1 = _lib.launch_count()
-        e0.record()
-        for _ in range(n):
-            pose_step()
-        e1.record()
-        torch.cuda.synchronize()
-        pl = (_lib.launch_count() - n1) // n
-        mx, fr = jd.reduce_max_sum(e0.elapsed_time(e1), float(B * n), device=dev)
-        from_poses = {"value": round(fr / (mx / 1000.0), 1), "unit": UNIT, "launches_per_step": int(pl),
-                      "note": "poses -> jaf_cal_flow_multi (one raster per target frame, K composes) -> jaf_warp_fuse with "
-                              "fim visibility; SMPL flows are ~88 % background, which the kernel skips"}
+    if feat is not None and S == 256:
+        from_poses = run_from_poses(args, inp, rank, dev, jd)
 
     # final result gather over NCCL (the only data collective of the job): a per-rank checksum
     chk = out[0].double().sum().reshape(1)
@@ -353,31 +408,31 @@ def run_ours(args):
 
     if rank != 0:
         return
-    peak, peak_src, _ = load_peak()
-    alg_bytes = synth.warp_fuse_bytes(K, S, S, C) * B
+    peaks = load_peaks()
+    if inp["fim"] is not None:
+        n_vis = int((inp["fim"] != -1).sum().item())
+        alg_bytes = wf_alg_bytes_visible(K, S, C, B, n_vis)
+        alg_note = (f"visible-pixel bytes: fim + outputs for every pixel, flows/logits/references/mask for the "
+                    f"{n_vis / (B * S * S):.3f} visible fraction only")
+    else:
+        alg_bytes = wf_alg_bytes_dense(K, S, C) * B
+        alg_note = "SURVEY §8d formula: every input read once, outputs written once"
     avg_launch_ms = total_ms / args.steps
     achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "warp_fuse_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(wl)
-        except Exception:
-            traffic = None
+    traffic, traffic_src = load_traffic(wl, args.flow, kernel)
     line = {
-        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if (S, K) == (256, 4) else f"warped+fused frames/sec @{S}^2 K={K}",
+        "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(max_ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 arithmetic; bf16 feature storage", "data": "synthetic",
-        "config": {"workload": wl, "videos_per_gpu": V, "frames_per_video": Fv, "frames_per_step_per_gpu": B,
-                   "H": S, "W": S, "K": K, "C": C, "flow": args.flow, "parallelism": f"video-sharded x{world}, no hot-path collective",
-                   "l2": "inputs larger than L2 (every frame owns its K references: %.1f GB read per step)" % (alg_bytes / 1e9),
-                   "layout": "refs RGB planar f32 + features channels-last bf16"},
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
-                     "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_avg": round(avg_launch_ms, 4),
+        "config": config_for(args, world),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": round(achieved / peaks["hbm"], 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"] + " hbm_gbs (burst copy)",
+                     "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_rule": alg_note,
+                     "launch_ms_avg": round(avg_launch_ms, 4),
                      "launch_ms_median": round(per_launch_ms[len(per_launch_ms) // 2], 4),
-                     "kernel": "k_warp_fuse_nhwc<LPP=C/8,K>"},
+                     "kernel": kernel},
         "e2e": {"value": round(e2e_video_refs, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "frames_per_step": Be,
                 "refs": "K references per video, uploaded every step, frames index them via ref_index",
@@ -392,7 +447,402 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, full_affinity)  # the CPU leg uses every host core
-        line["cpu_baseline"] = cpu_leg(wl)
+        del inp, feat
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_baseline_wf(wl, args.flow)
+    emit(line)
+
+
+def run_from_poses(args, inp, rank, dev, jd):
+    from jafpro_b200 import _lib, ops, synth
+    from jafpro_b200.nmr import load_smpl_template
+    V, Fv, S, K, C = WF_WORKLOADS[args.workload]
+    B = V * Fv
+    f_idx = torch.from_numpy(load_smpl_template()[1]).to(dev)
+    cams, verts = [], []
+    for v in range(V):
+        c_, v_ = synth.smpl_poses(Fv + K, seed=(1000 + rank) * 100 + v, device=dev)
+        cams.append(c_)
+        verts.append(v_)
+    tcam = torch.cat([c_[:Fv] for c_ in cams]).contiguous()
+    tverts = torch.cat([v_[:Fv] for v_ in verts]).contiguous()
+    scam = torch.cat([c_[Fv:].unsqueeze(0).expand(Fv, -1, -1) for c_ in cams]).contiguous()
+    sverts = torch.cat([v_[Fv:].unsqueeze(0).expand(Fv, -1, -1, -1) for v_ in verts]).contiguous()
+
+    fused = hasattr(ops, "warp_fuse_from_poses")
+
+    def pose_step():
+        if fused:
+            return ops.warp_fuse_from_poses(scam, sverts, tcam, tverts, f_idx, S, rgb=inp["rgb"], feat=inp["feat"],
+                                            logits=inp["logits"], tgt_mask=inp["mask"])
+        T, fm, _ = ops.cal_flow_multi(scam, sverts, tcam, tverts, f_idx, S, return_wim=False)
+        return ops.warp_fuse(T, rgb=inp["rgb"], feat=inp["feat"], logits=inp["logits"], fim=fm, tgt_mask=inp["mask"])
+
+    n = max(3, min(args.steps, 20))
+    total, _, _ = timed(pose_step, n, 3, barrier=jd.barrier)
+    pl = last_timed_launches // n
+    mx, fr = jd.reduce_max_sum(total, float(B * n), device=dev)
+    return {"value": round(fr / (mx / 1000.0), 1), "unit": UNIT, "launches_per_step": int(pl), "kernel": _lib.last_kernel(),
+            "note": "poses -> target raster (one per frame) -> fused warp + fusion with fim visibility; the transfer flows "
+                    "of the K reference poses are composed inside the warp kernel (no [B,K,S,S,2] flow tensor in HBM); "
+                    "SMPL flows are ~88 % background, which the kernel skips"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# BASELINE configs 1, 3, 4
+# ----------------------------------------------------------------------------------------------------------
+class L2Flusher:
+    """Writes a buffer larger than L2 between timed calls of the small workloads."""
+
+    def __init__(self, dev):
+        self.buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def __call__(self):
+        self.buf.add_(1.0)
+
+
+def timed_flushed(fn, steps, warmup, flush):
+    """Per-call CUDA-event times with an L2 flush before every timed call (the flush is outside the events)."""
+    for _ in range(max(3, warmup)):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return ts
+
+
+def run_aux(args):
+    from jafpro_b200 import _lib, dist as jd, ops, synth
+    from jafpro_b200.nmr import load_smpl_template
+    import torch.nn.functional as F
+    rank, world, local = jd.init()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    wl = args.workload
+    steps = max(args.steps, 5)
+    sampler = ClockSampler(local) if rank == 0 else None
+    flush = L2Flusher(dev)
+    line = {"n_gpus": world, "steps": steps, "warmup": max(3, args.warmup), "scaling": "weak", "vs_baseline": None,
+            "data": "synthetic", "config": config_for(args, world)}
+
+    if wl == "c1_latency":
+        # BASELINE config 1: bilinear warp + fusion of 1 reference 256x256 RGB frame, batch 1 (the reference's
+        # per-frame call, test/conv_pro_test.py:255-278): warp_image x visibility mask, confidence blend.
+        rgb, _ = synth.reference_sets(1, 1, 0, 256, 256, seed=1, device=dev)
+        grid = synth.dense_flows(1, 1, 256, 256, seed=1, device=dev)
+        mask = torch.ones(1, 1, 256, 256, device=dev)
+        fake = torch.randn(1, 3, 256, 256, device=dev)
+        conf = torch.rand(1, 1, 256, 256, device=dev)
+        out_buf = torch.empty(1, 3, 256, 256, device=dev)
+        fn = lambda: ops.warp_fuse(grid, rgb=rgb, tgt_mask=mask, fake=fake, conf=conf, out_rgb=out_buf)
+        n0 = _lib.launch_count()
+        fn()
+        launches_per_call = _lib.launch_count() - n0
+        kernel = _lib.last_kernel()
+        if sampler:
+            sampler.start()
+        cold = sorted(timed_flushed(fn, steps * 10, args.warmup, flush))
+        total, per, _ = timed(fn, steps * 10, args.warmup)       # back to back, L2-warm
+        # the same per-frame step captured once in a CUDA graph and replayed (launch-overhead-free submission)
+        seq = ops.FrameGraph(fn)
+        tg, perg, _ = timed(seq.replay, steps * 10, args.warmup)
+        src_img, g1 = rgb[:, 0].contiguous(), grid[:, 0].contiguous()
+
+        def torch_ref():
+            t = F.grid_sample(src_img, g1, padding_mode="border", align_corners=False) * mask
+            return fake * conf + t * (1 - conf)
+        tt, pert, _ = timed(torch_ref, steps * 10, args.warmup)
+        clocks = sampler.stop() if sampler else None
+        alg = 2359296 + 786432 + 262144   # SURVEY §8d C1 + the blend's fake and conf
+        us = per[len(per) // 2] * 1e3
+        line.update({"metric": "warp+mask+blend latency, 1 reference 256^2, batch 1", "unit": "us", "higher_is_better": False,
+                     "value": round(us, 2), "ms_per_step": round(total / (steps * 10), 5), "dtype": "f32",
+                     "roofline": {"bound": "hbm", "achieved": round(alg / (us * 1e-6) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                  "frac": round(alg / (us * 1e-6) / 1e9 / peaks["hbm"], 4), "traffic": None, "kernel": kernel,
+                                  "algorithmic_bytes_per_launch": alg,
+                                  "note": "launch-latency bound by construction: 0.5 us of HBM time at peak"},
+                     "latency_us": {"median_back_to_back": round(us, 2), "median_l2_flushed": round(cold[len(cold) // 2] * 1e3, 2),
+                                    "median_cuda_graph_replay": round(perg[len(perg) // 2] * 1e3, 2),
+                                    "torch_cuda_op_sequence_median": round(pert[len(pert) // 2] * 1e3, 2),
+                                    "torch_cuda_launches": 5, "our_launches": int(launches_per_call)},
+                     "gpu_launches": int(launches_per_call * steps * 10), "clocks": clocks})
+        line["e2e"] = e2e_c1(ops, rgb, grid, mask, fake, conf, steps)
+        if world == 1 and not args.no_cpu and rank == 0:
+            line["cpu_baseline"] = cpu_c1()
+
+    elif wl == "c3_flow":
+        # BASELINE config 3: SMPL transfer-flow construction, 30 frames (project + raster + compose)
+        _, fidx = load_smpl_template()
+        f_idx = torch.from_numpy(fidx).to(dev)
+        cam, verts = synth.smpl_poses(60, seed=3 + rank, device=dev)
+        sc, sv, tc, tv = cam[:30].contiguous(), verts[:30].contiguous(), cam[30:].contiguous(), verts[30:].contiguous()
+        fn = lambda: ops.cal_flow(sc, sv, tc, tv, f_idx, 256)
+        n0 = _lib.launch_count()
+        fn()
+        lpc = _lib.launch_count() - n0
+        if sampler:
+            sampler.start()
+        cold = sorted(timed_flushed(fn, steps * 3, args.warmup, flush))
+        total, per, _ = timed(fn, steps * 3, args.warmup, barrier=jd.barrier)
+        # the reference's own CUDA rasteriser (oracle/_ref, compiled unmodified) on the same target faces, timed beside
+        # ours: kernel_1 + kernel_2 only (the fills / clone / flips of NR/rasterize.py around it are not timed)
+        ref_cuda = None
+        try:
+            import oracle
+            rr = oracle.RefRaster()
+            faces = ops.project_gather(tc, tv, f_idx)
+            ref_cuda = rr.time_kernels(faces, 256, reps=3)
+            ours = sorted(timed_flushed(lambda: ops.render_fim_wim(tc, tv, f_idx, 256, return_faces=False), 10, 3, flush))
+            ref_cuda = {"reference_cuda_raster_ms": round(ref_cuda, 3), "ours_render_fim_wim_ms": round(ours[len(ours) // 2], 4),
+                        "speedup": round(ref_cuda / ours[len(ours) // 2], 1),
+                        "note": "30 frames 256^2, 13776 faces; reference = forward_face_index_map kernels 1+2 of "
+                                "rasterize_cuda_kernel.cu compiled unmodified for sm_100a"}
+        except Exception as e:  # oracle/_ref not built on this box
+            ref_cuda = {"unavailable": str(e)[:120]}
+        clocks = sampler.stop() if sampler else None
+        ms = cold[len(cold) // 2]
+        alg = 30 * (1131268 + 1903488)
+        mx, fr = jd.reduce_max_sum(total, float(30 * steps * 3), device=dev)
+        line.update({"metric": "SMPL transfer-flow frames/sec @256^2 (project + raster + compose)", "unit": UNIT,
+                     "higher_is_better": True, "value": round(fr / (mx / 1e3), 1), "ms_per_step": round(mx / (steps * 3), 4),
+                     "dtype": "f32 + int32 (bit-exact)",
+                     "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                  "frac": round(alg / (ms * 1e-3) / 1e9 / peaks["hbm"], 4), "traffic": None,
+                                  "kernel": "k_raster_scatter + k_raster_huge + k_raster_resolve(compose)",
+                                  "algorithmic_bytes_per_launch": alg, "launch_ms_median_l2_flushed": round(ms, 4),
+                                  "note": "atomic / latency bound by design (face-parallel z-buffer); bytes = SURVEY §8d raster "
+                                          "1,131,268 + compose 1,903,488 per frame",
+                                  "brute_force_equiv_tests_per_s": round(30 * 902823936 / (ms * 1e-3), 0)},
+                     "reference_cuda": ref_cuda, "gpu_launches": int(lpc * steps * 3), "clocks": clocks})
+        line["e2e"] = e2e_c3(ops, sc, sv, tc, tv, f_idx, steps)
+        if world == 1 and not args.no_cpu and rank == 0:
+            line["cpu_baseline"] = cpu_c3(fidx)
+
+    elif wl == "c4_convlstm":
+        # BASELINE config 4: appearance fusion + ConvLSTM step at 64x64x256 features, K=4 refs, batch 16
+        B, Cin, Ch, H, W, K = 16, 256, 256, 64, 64, 4
+        torch.manual_seed(rank)
+        wgt = torch.randn(4 * Ch, Cin + Ch, 3, 3, device=dev) * 0.01
+        bias = torch.zeros(4 * Ch, device=dev)
+        wpack = ops.convlstm_pack_weight(wgt, Cin, Ch)
+        rgb, feat = synth.reference_sets(B, K, Ch, H, W, seed=5 + rank, device=dev)
+        grid = synth.dense_flows(B, K, H, W, seed=5 + rank, device=dev)
+        logits = torch.randn(B, K, H, W, device=dev)
+        h0 = torch.zeros(B, H, W, Ch, device=dev, dtype=torch.bfloat16)
+        c0 = torch.zeros(B, H, W, Ch, device=dev)
+        # K warped references feed K sequential recurrent steps (src/convLSTM.py:131-134); the fused frame is the blend
+        warped = [feat[:, k].permute(0, 2, 3, 1).contiguous() for k in range(K)]  # [B,H,W,C] bf16 each
+        flop = 2 * (B * H * W) * (4 * Ch) * (9 * (Cin + Ch))
+
+        def fusion():
+            return ops.warp_fuse(grid, rgb=rgb, feat=feat, logits=logits)
+
+        def lstm():
+            hh, cc = h0, c0
+            for t in range(K):
+                hh, cc = ops.convlstm_step_tc(warped[t], hh, cc, wpack, bias, Cin, Ch)
+            return hh
+
+        def both():
+            fusion()
+            return lstm()
+
+        one = lambda: ops.convlstm_step_tc(warped[0], h0, c0, wpack, bias, Cin, Ch)
+        n0 = _lib.launch_count()
+        both()
+        lpc = _lib.launch_count() - n0
+        if sampler:
+            sampler.start()
+        t1, p1, _ = timed(one, steps * 2, args.warmup)
+        tf, pf, _ = timed(fusion, steps * 2, args.warmup)
+        kernel_f = _lib.last_kernel()
+        tb, pb, _ = timed(both, steps, args.warmup, barrier=jd.barrier)
+        clocks = sampler.stop() if sampler else None
+        ms1 = t1 / (steps * 2)
+        msf = pf[len(pf) // 2]
+        mx, fr = jd.reduce_max_sum(tb, float(B * steps), device=dev)
+        fus_bytes = synth.warp_fuse_bytes(K, H, W, Ch) * B
+        line.update({"metric": "fused frames/sec @64^2 x256ch K=4 (warp+fuse + 4 ConvLSTM steps, B=16)", "unit": UNIT,
+                     "higher_is_better": True, "value": round(fr / (mx / 1e3), 1), "ms_per_step": round(mx / steps, 4),
+                     "dtype": "bf16 operands, fp32 accumulate / state / gates",
+                     "roofline": {"bound": "tensor", "achieved": round(flop / (ms1 * 1e-3) / 1e12, 1), "peak": peaks["tf_sustained"],
+                                  "unit": "TFLOP/s", "frac": round(flop / (ms1 * 1e-3) / 1e12 / peaks["tf_sustained"], 4),
+                                  "frac_of_burst": round(flop / (p1[0] * 1e-3) / 1e12 / peaks["tf_burst"], 4),
+                                  "traffic": None, "kernel": "k_convlstm_tc", "flop_per_launch": flop,
+                                  "launch_ms_avg": round(ms1, 4), "launch_ms_best": round(p1[0], 4),
+                                  "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"},
+                     "fusion_half": {"kernel": kernel_f, "ms_median": round(msf, 4), "algorithmic_bytes": fus_bytes,
+                                     "GBps": round(fus_bytes / (msf * 1e-3) / 1e9, 1),
+                                     "frac_of_hbm": round(fus_bytes / (msf * 1e-3) / 1e9 / peaks["hbm"], 4),
+                                     "note": "16 frames x 64^2: 74 MB per call, L2-resident and launch-size bound"},
+                     "gpu_launches": int(lpc * steps), "clocks": clocks})
+        line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "note": "recurrent state lives on the device between steps; no host entry point for this workload"}
+        if world == 1 and not args.no_cpu and rank == 0:
+            line["cpu_baseline"] = cpu_c4(Cin, Ch, H, W)
+    if rank == 0:
+        emit(line)
+
+
+def e2e_c1(ops, rgb, grid, mask, fake, conf, steps):
+    """Config 1 through the host entry point: one frame up, one frame down per call."""
+    pin = lambda t: t.cpu().contiguous().pin_memory()
+    hg, hr, hm, hf, hc = pin(grid), pin(rgb), pin(mask), pin(fake), pin(conf)
+    o = torch.empty((1, 3, 256, 256)).pin_memory()
+    fn = lambda: ops.warp_fuse_host(hg, rgb=hr, tgt_mask=hm, fake=hf, conf=hc, out_rgb=o)
+    for _ in range(5):
+        fn()
+    n = steps * 10
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    us = (time.perf_counter() - t0) / n * 1e6
+    nb = lambda ts: sum(t.numel() * t.element_size() for t in ts)
+    return {"value": round(us, 2), "unit": "us", "h2d_bytes_per_step": nb([hg, hr, hm, hf, hc]), "d2h_bytes_per_step": nb([o]),
+            "api": "jafpro_b200.fusion.warp_fuse_host (pinned host buffers, blocking)"}
+
+
+def e2e_c3(ops, sc, sv, tc, tv, f_idx, steps):
+    """Config 3 end to end: poses from pinned host memory, flows back to pinned host memory."""
+    pin = lambda t: t.cpu().contiguous().pin_memory()
+    hsc, hsv, htc, htv = pin(sc), pin(sv), pin(tc), pin(tv)
+    dev = sc.device
+    o = torch.empty((30, 256, 256, 2)).pin_memory()
+
+    def fn():
+        T = ops.cal_flow(hsc.to(dev, non_blocking=True), hsv.to(dev, non_blocking=True), htc.to(dev, non_blocking=True),
+                         htv.to(dev, non_blocking=True), f_idx, 256)
+        o.copy_(T, non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(3):
+        fn()
+    n = steps * 3
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    dt = (time.perf_counter() - t0) / n
+    nb = lambda ts: sum(t.numel() * t.element_size() for t in ts)
+    return {"value": round(30 / dt, 1), "unit": UNIT, "h2d_bytes_per_step": nb([hsc, hsv, htc, htv]), "d2h_bytes_per_step": nb([o]),
+            "api": "jafpro_b200.cal_flow (poses uploaded from pinned memory, flows downloaded)"}
+
+
+def cpu_c1():
+    import torch.nn.functional as F
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    src, grid = torch.randn(1, 3, 256, 256), torch.rand(1, 256, 256, 2) * 2 - 1
+    mask, fake, conf = torch.ones(1, 1, 256, 256), torch.randn(1, 3, 256, 256), torch.rand(1, 1, 256, 256)
+
+    def fn():
+        t = F.grid_sample(src, grid, padding_mode="border", align_corners=False) * mask   # src/cal_flow.py:37-39, flow_net.py:91
+        return fake * conf + t * (1 - conf)                                                # flow_net.py:98
+    for _ in range(20):
+        fn()
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < 5.0:
+        fn()
+        n += 1
+    return {"value": round((time.perf_counter() - t0) / n * 1e6, 2), "unit": "us", "cores": cores, "kind": "port",
+            "sample": f"{n} calls of the reference's torch CPU op sequence (grid_sample border, mask, blend), 5 s"}
+
+
+def cpu_c3(fidx):
+    import oracle
+    from jafpro_b200 import synth
+    cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
+    cam, verts = synth.smpl_poses(4, seed=3)
+    a = [t.numpy() for t in (cam[:2], verts[:2], cam[2:], verts[2:])]
+    oracle.cal_flow(*a, fidx, 256)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < 12.0:
+        oracle.cal_flow(*a, fidx, 256)
+        n += 2
+    return {"value": round(n / (time.perf_counter() - t0), 2), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} frames (2 per call) through the C restatement of rasterize_cuda_kernel.cu + cal_bc_transform, "
+                      "OpenMP over pixels, ~12 s (the reference has no CPU rasteriser)"}
+
+
+def cpu_c4(Cin, Ch, H, W):
+    import torch.nn.functional as F
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, h, c = torch.randn(1, Cin, H, W), torch.randn(1, Ch, H, W), torch.randn(1, Ch, H, W)
+    w, b = torch.randn(4 * Ch, Cin + Ch, 3, 3) * 0.01, torch.zeros(4 * Ch)
+
+    def cell():  # src/convLSTM.py:41-56
+        cc = F.conv2d(torch.cat([x, h], 1), w, b, padding=1)
+        i, f, o, g = torch.split(cc, Ch, dim=1)
+        cn = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        return torch.sigmoid(o) * torch.tanh(cn), cn
+    cell()
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < 10.0:
+        cell()
+        n += 1
+    per_step = (time.perf_counter() - t0) / n     # one frame, one recurrent step
+    return {"value": round(1.0 / (4 * per_step), 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} ConvLSTMCell.forward calls at B=1 (fp32 torch CPU, the reference's cell); frames/s = 1 / (K=4 steps); "
+                      "the warp+fuse half is not included (it is <2 % of the CPU time)"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores, rank 0 only.  Same `config`, metric and
+    unit as our arm; every step is one pass over a bounded sample (one 30-frame video for the headline)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    t_all = time.perf_counter()
+    if wl in WF_WORKLOADS:
+        V, Fv, S, K, C = WF_WORKLOADS[wl]
+        leg = CpuWarpFuse(wl, args.flow)
+        name, res = leg.best(budget_s=max(2.0, 0.5 * args.warmup))   # warm-up doubles as the variant pick
+        fn = leg.run_torch if name == "torch_cpu" else leg.run_c
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        dt = time.perf_counter() - t0
+        value = leg.n * args.steps / dt
+        metric = METRIC if (S, K) == (256, 4) else f"warped+fused frames/sec @{S}^2 K={K}"
+        base = {"value": round(value, 2), "unit": UNIT, "cores": leg.cores, "kind": "port",
+                "sample": f"each step = one pass over {leg.n} frames of {wl} (fp32) through {name} "
+                          f"(picked in warm-up: {', '.join(f'{k} {v:.1f} f/s' for k, v in res.items())})"}
+        unit, hib, ms = UNIT, True, 1000.0 * dt / args.steps
+    else:
+        fidx = None
+        if wl == "c3_flow":
+            from jafpro_b200.nmr import load_smpl_template
+            fidx = load_smpl_template()[1]
+        base = {"c1_latency": cpu_c1, "c3_flow": lambda: cpu_c3(fidx), "c4_convlstm": lambda: cpu_c4(256, 256, 64, 64)}[wl]()
+        value, unit = base["value"], base["unit"]
+        hib = unit != "us"
+        metric = {"c1_latency": "warp+mask+blend latency, 1 reference 256^2, batch 1",
+                  "c3_flow": "SMPL transfer-flow frames/sec @256^2 (project + raster + compose)",
+                  "c4_convlstm": "fused frames/sec @64^2 x256ch K=4 (warp+fuse + 4 ConvLSTM steps, B=16)"}[wl]
+        ms = 1000.0 * (time.perf_counter() - t_all) / max(1, args.steps)
+    line = {"impl": "reference", "metric": metric, "value": value if not isinstance(value, float) else round(value, 2),
+            "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 1),
+            "higher_is_better": hib, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_for(args, world), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
     emit(line)
 
 
@@ -422,21 +872,24 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dancevideo_256_k4_c64", choices=sorted(WORKLOADS))
-    ap.add_argument("--flow", default="dense", choices=["dense", "smpl"],
-                    help="dense: every pixel visible (worst case, headline); smpl: real transfer flows, ~12%% foreground")
+    ap.add_argument("--workload", default="dancevideo_256_k4_c64", choices=sorted(WF_WORKLOADS) + list(AUX_WORKLOADS))
+    ap.add_argument("--flow", default="dense", choices=FLOWS,
+                    help="dense: every pixel visible, smooth <= 8 px displacement (headline); smpl: real transfer flows, ~12%% "
+                         "foreground; hard: full coverage, piecewise-affine with rotation / scale / +-64 px; perm: random permutation")
     ap.add_argument("--e2e-frames", type=int, default=60)
     ap.add_argument("--videos-per-gpu", type=int, default=0, help="override the workload's videos per GPU (profiling)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     reserve_stdout()
-    if args.videos_per_gpu > 0:
-        w = WORKLOADS[args.workload]
-        WORKLOADS[args.workload] = (args.videos_per_gpu,) + tuple(w[1:])
+    if args.videos_per_gpu > 0 and args.workload in WF_WORKLOADS:
+        w = WF_WORKLOADS[args.workload]
+        WF_WORKLOADS[args.workload] = (args.videos_per_gpu,) + tuple(w[1:])
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in WF_WORKLOADS:
+        run_wf(args)
     else:
-        run_ours(args)
+        run_aux(args)
     if torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
 

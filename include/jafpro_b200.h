@@ -42,6 +42,12 @@ int jaf_version(void);
 const char* jaf_last_error(void);
 /* Number of kernels this library has launched in the calling process (monotonic). */
 uint64_t jaf_launch_count(void);
+/* Measurement aids (no reference counterpart): the kernel variant the calling thread launched last through
+ * jaf_warp_fuse / jaf_warp_fuse_from_maps, e.g. "k_warp_fuse_nhwc_wide<K=4,MINB=4,SKIP=0,RGBM=1>", and the effective
+ * values of the JAF_* tuning knobs (environment, read once per process) as "NAME=value ..." written into buf
+ * (returns the length needed). */
+const char* jaf_last_kernel(void);
+int jaf_tuning_info(char* buf, int n);
 
 /* ---------------------------------------------------------------------------------
  * a1-a3  projection + y flip + look_at + face gather

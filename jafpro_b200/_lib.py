@@ -34,6 +34,8 @@ SIGNATURES = {
     "jaf_version": (_i, []),
     "jaf_last_error": (C.c_char_p, []),
     "jaf_launch_count": (_u64, []),
+    "jaf_last_kernel": (C.c_char_p, []),
+    "jaf_tuning_info": (_i, [C.c_char_p, _i]),
     "jaf_project_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "jaf_raster_workspace_bytes": (_sz, [_i, _i]),
     "jaf_raster_fim_wim": (_i, [_vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -106,3 +108,19 @@ def check(status: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib().jaf_launch_count())
+
+
+def last_kernel() -> str:
+    """Kernel variant the calling thread launched last through jaf_warp_fuse (measurement aid)."""
+    return lib().jaf_last_kernel().decode("utf-8", "replace")
+
+
+def tuning_info() -> dict:
+    """Effective JAF_* tuning knobs of the loaded library (environment, read once per process)."""
+    buf = C.create_string_buffer(1024)
+    lib().jaf_tuning_info(buf, len(buf))
+    out = {}
+    for tok in buf.value.decode().split():
+        k, _, v = tok.partition("=")
+        out[k] = int(v) if v.lstrip("-").isdigit() else v
+    return out

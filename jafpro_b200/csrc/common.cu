@@ -7,6 +7,7 @@
 
 namespace {
 thread_local char g_err[512] = "";
+thread_local char g_kernel[160] = "";
 std::atomic<uint64_t> g_launches{0};
 }  // namespace
 
@@ -16,6 +17,13 @@ void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void note_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_kernel, sizeof(g_kernel), fmt, ap);
   va_end(ap);
 }
 
@@ -36,6 +44,7 @@ extern "C" {
 
 int jaf_version(void) { return 100; }
 const char* jaf_last_error(void) { return g_err; }
+const char* jaf_last_kernel(void) { return g_kernel; }
 uint64_t jaf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

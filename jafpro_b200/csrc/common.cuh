@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...);
 int finish_launch(const char* what, int launches = 1);
 int cuda_status(cudaError_t e, const char* what);
 
+// Name of the kernel variant the calling thread launched last (behind jaf_last_kernel()): measurement tools
+// report the kernel that actually ran instead of guessing from the shapes.
+void note_kernel(const char* fmt, ...);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 

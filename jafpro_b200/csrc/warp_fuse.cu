@@ -21,6 +21,7 @@
 // (ATen/native/cuda/GridSampler.cuh:14-45 and the kernel body in GridSampler.cu).
 #include <math_constants.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -567,7 +568,16 @@ __device__ __forceinline__ U256 ld_gather_u256(const void* p) {
   return v;
 }
 
-template <int KT, int MINB, bool SKIP>
+// RGBM ("RGB merged"): the RGB planes are produced inside the feature row loop instead of a second pass over the
+// tile.  In the reduction over the references every lane of the pixel group already receives reference k's corner
+// offset and its four bilinear weights (pre-multiplied by softmax * visibility * mask) by shuffle; lane c < 3 of the
+// group uses them once more for plane c of the planar fp32 RGB reference: 4 scalar taps per reference, issued with the
+// same batch of loads as the feature taps, one running FMA chain in ATen's tap order, one plane store per row.
+// Nothing is re-read (the two-pass flavour reads flows, logits and masks twice and rebuilds softmax and taps per
+// pixel), no CTA barrier, one extra accumulator register.  The weights carry the approximate softmax division and
+// the mask before the sum instead of after it: <= 1e-5 of the generic kernel instead of bit-identical (the north
+// star's fp32 tolerance is 1e-4).  Per-channel target masks (mask_c == 3) keep the two-pass flavour.
+template <int KT, int MINB, bool SKIP, bool RGBM>
 __global__ void __launch_bounds__(256, MINB)
 k_warp_fuse_nhwc_wide(const WFArgs a) {
   static_assert(KT <= 4, "one lane of the 4-lane pixel group per reference");
@@ -604,6 +614,9 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
     const unsigned lane_in = (unsigned)kk * HW;
     const uint64_t keep = l2_policy_evict_last();
     unsigned pix = (unsigned)y_begin * W + (unsigned)x;
+    // merged RGB: CTA-uniform 64-bit base + 32-bit per-lane offsets (lane 3 shadows plane 0 and stores nothing)
+    const float* __restrict__ rgb_cta = RGBM ? a.rgb + r * KT * 3 * (size_t)HWs : nullptr;
+    const unsigned rgb_c = (j < 3 ? (unsigned)j : 0u) * HWs;
 #pragma unroll 1
     for (int y = y_begin; y < y_end; ++y, pix += W) {
       float lg = 0.f, v = 1.f;
@@ -643,13 +656,15 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
       const bool any = SKIP ? (__ballot_sync(FULL, aw != 0.f) != 0u) : true;
 
       float2 acc[8];
+      float racc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
       if (any) {
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
           const int src = gl + k;
-          const unsigned o0 = __shfl_sync(FULL, off, src) + (unsigned)k * HWs;
+          const unsigned osh = __shfl_sync(FULL, off, src);
+          const unsigned o0 = osh + (unsigned)k * HWs;
           const char* p0 = f_lane + (size_t)o0 * PIXB;
           const char* p1 = f_lane + (size_t)(o0 + Ws) * PIXB;
           U256 q[4];
@@ -657,11 +672,23 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
           q[1] = ld_gather_u256(p0 + PIXB);
           q[2] = ld_gather_u256(p1);
           q[3] = ld_gather_u256(p1 + PIXB);
+          float rv[4];
+          if constexpr (RGBM) {
+            const float* r0 = rgb_cta + (osh + (unsigned)(3 * k) * HWs + rgb_c);
+            rv[0] = __ldg(r0);
+            rv[1] = __ldg(r0 + 1);
+            rv[2] = __ldg(r0 + Ws);
+            rv[3] = __ldg(r0 + Ws + 1);
+          }
           float wt[4];
           wt[0] = __shfl_sync(FULL, t.nw, src);
           wt[1] = __shfl_sync(FULL, t.ne, src);
           wt[2] = __shfl_sync(FULL, t.sw, src);
           wt[3] = __shfl_sync(FULL, t.se, src);
+          if constexpr (RGBM) {
+#pragma unroll
+            for (int tp = 0; tp < 4; ++tp) racc = fmaf(rv[tp], wt[tp], racc);
+          }
 #pragma unroll
           for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
             const float2 w2 = make_float2(wt[tp], wt[tp]);
@@ -683,11 +710,23 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
         st_stream_u128(op, o0v);
         st_stream_u128(op + 1, o1v);
       }
+      if constexpr (RGBM) {
+        if (xin && j < 3) {
+          const unsigned po = (unsigned)j * HW + pix;
+          float ov = racc;
+          if (a.fake != nullptr && a.conf != nullptr) {  // uniform
+            const float wc = __ldg(a.conf + ((size_t)b * HW + pix));
+            const float fkv = __ldg(a.fake + ((size_t)b * 3 * HW + po));
+            ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+          }
+          st_stream_f32(a.out_rgb + ((size_t)b * 3 * HW + po), ov);
+        }
+      }
     }
   }
 
-  // =========================== phase B: RGB ===========================
-  if (a.rgb != nullptr && a.out_rgb != nullptr) {
+  // =========================== phase B: RGB (two-pass flavour) ===========================
+  if (!RGBM && a.rgb != nullptr && a.out_rgb != nullptr) {
     const float* __restrict__ rgb_base = a.rgb + r * KT * 3 * (size_t)HWs;
     const float* __restrict__ b_fake = (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr;
     const float* __restrict__ b_conf = (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr;
@@ -1107,21 +1146,40 @@ int wf_env(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-// Resident CTAs per SM the headline kernel is compiled for (register cap = 65536 / (256 * MINB)) and rows per CTA
-// tile; measured on the 240-frame workload.  Without a visibility input the hand-pipelined RGB phase wants 64 registers
-// (4 CTAs/SM, 32-row tiles: 87.8 k f/s vs 78.6 k at 5); with one, the skipping variant is best at 5 CTAs/SM and 16 rows
-// (216 k f/s on SMPL flows vs 189 k).
-int wf_minb(bool skip) {
-  static const int mb_dense = [] {
-    const int v = wf_env("JAF_WF_MINB", 4);
-    return (v >= 3 && v <= 6) ? v : 4;
+// Tuning knobs (environment, read once per process; jaf_tuning_info() reports the effective values).  The defaults are
+// the measured best on B200 for the 240-frame 256^2 K=4 C=64 workload.
+struct WFTune {
+  int minb_dense;   // JAF_WF_MINB: CTAs/SM of the 8-lane kernel, C=64 K=4, dense (register cap = 65536 / (256 * MINB))
+  int minb_skip;    // JAF_WF_MINB_SKIP: the same for the visibility-skipping variant
+  int rows;         // JAF_WF_ROWS: rows per iteration of the 8-lane kernel
+  int rows_per_cta; // JAF_WF_ROWS_PER_CTA: rows of an 8-lane tile (0 = 32 dense / 16)
+  int wide;         // JAF_WF_WIDE: 1 wide-lane kernel for C=64 without a visibility input, 2 also with one, 0 never
+  int wide_minb;    // JAF_WF_WIDE_MINB: CTAs/SM of the wide kernel, K <= 4
+  int wide_minb8;   // JAF_WF_WIDE_MINB8: the same for K = 5..8
+  int wide_rows;    // JAF_WF_WIDE_ROWS_PER_CTA: rows of a wide tile (64 columns)
+  int rgb_merge;    // JAF_WF_RGB_MERGE: RGB planes inside the feature row loop (1) or as a second pass (0)
+};
+const WFTune& wf_tune() {
+  static const WFTune t = [] {
+    WFTune v;
+    v.minb_dense = wf_env("JAF_WF_MINB", 4);
+    if (v.minb_dense < 3 || v.minb_dense > 6) v.minb_dense = 4;
+    v.minb_skip = wf_env("JAF_WF_MINB_SKIP", 5);
+    if (v.minb_skip < 4 || v.minb_skip > 6) v.minb_skip = 5;
+    v.rows = wf_env("JAF_WF_ROWS", 2);
+    v.rows_per_cta = wf_env("JAF_WF_ROWS_PER_CTA", 0);
+    v.wide = wf_env("JAF_WF_WIDE", 1);
+    v.wide_minb = wf_env("JAF_WF_WIDE_MINB", 4);
+    if (v.wide_minb < 3 || v.wide_minb > 5) v.wide_minb = 4;
+    v.wide_minb8 = wf_env("JAF_WF_WIDE_MINB8", 3) == 4 ? 4 : 3;
+    v.wide_rows = wf_env("JAF_WF_WIDE_ROWS_PER_CTA", 16);
+    if (v.wide_rows < 1) v.wide_rows = 16;
+    v.rgb_merge = wf_env("JAF_WF_RGB_MERGE", 1);
+    return v;
   }();
-  static const int mb_skip = [] {
-    const int v = wf_env("JAF_WF_MINB_SKIP", 5);
-    return (v >= 4 && v <= 6) ? v : 5;
-  }();
-  return skip ? mb_skip : mb_dense;
+  return t;
 }
+int wf_minb(bool skip) { return skip ? wf_tune().minb_skip : wf_tune().minb_dense; }
 
 template <int LPP, int KV>
 bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
@@ -1129,11 +1187,14 @@ bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
     const bool skip = a.vis != nullptr || a.fim != nullptr;
     if constexpr (LPP == 8 && KV == 4) {  // the headline shape carries the occupancy variants
       const int mb = wf_minb(skip);
-      static const int rows = wf_env("JAF_WF_ROWS", 2);
-#define JAF_V(MB, R) if (mb == MB && rows == R) { if (skip) k_warp_fuse_nhwc<8, 4, MB, true, R><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, R><<<grid, 256, 0, st>>>(a); return true; }
+      const int rows = wf_tune().rows;
+#define JAF_V(MB, R) if (mb == MB && rows == R) { \
+        jaf::note_kernel("k_warp_fuse_nhwc<LPP=8,K=4,MINB=%d,SKIP=%d,ROWS=%d>", MB, (int)skip, R); \
+        if (skip) k_warp_fuse_nhwc<8, 4, MB, true, R><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, R><<<grid, 256, 0, st>>>(a); return true; }
       JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1) JAF_V(3, 2) JAF_V(4, 2) JAF_V(5, 2) JAF_V(6, 2)
 #undef JAF_V
     }
+    jaf::note_kernel("k_warp_fuse_nhwc<LPP=%d,K=%d,MINB=6,SKIP=%d,ROWS=1>", LPP, KV, (int)skip);
     if (skip) k_warp_fuse_nhwc<LPP, KV, 6, true><<<grid, 256, 0, st>>>(a);
     else k_warp_fuse_nhwc<LPP, KV, 6, false><<<grid, 256, 0, st>>>(a);
     return true;
@@ -1177,22 +1238,30 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
   // C = 64 without a visibility input goes to the wide-lane kernel (256-bit gathers): 94.3 k frames/s against 90.9 k
   // for k_warp_fuse_nhwc<8,4> on the headline workload (4 CTAs/SM, 64 registers, 64 x 16 pixel tiles; 5 or 6 CTAs/SM
   // spill).  With visibility the narrow skipping variant stays ahead (216 k vs 199 k frames/s on SMPL flows).
-  static const int wide_env = wf_env("JAF_WF_WIDE", 1);
-  static const int wide_minb = wf_env("JAF_WF_WIDE_MINB", 4);
-  static const int wide_rows = wf_env("JAF_WF_WIDE_ROWS_PER_CTA", 16);
-  const bool wide_ok = wide_env == 2 || (wide_env == 1 && a.vis == nullptr && a.fim == nullptr);
+  const WFTune& tn = wf_tune();
+  const int wide_minb = tn.wide_minb, wide_minb8 = tn.wide_minb8;
+  const bool wide_ok = tn.wide == 2 || (tn.wide == 1 && a.vis == nullptr && a.fim == nullptr);
   if (wide_ok && a.C == 64 && a.K <= 8 && (reinterpret_cast<uintptr_t>(a.feat) & 31u) == 0 &&
       (reinterpret_cast<uintptr_t>(a.out_feat) & 31u) == 0) {
     a.tiles_x = (a.W + 63) / 64;
-    a.rows_per_cta = a.H < wide_rows ? a.H : wide_rows;
+    a.rows_per_cta = a.H < tn.wide_rows ? a.H : tn.wide_rows;
     a.tiles_y = (a.H + a.rows_per_cta - 1) / a.rows_per_cta;
     const long gridw = (long)a.tiles_x * a.tiles_y * a.B;
     if (gridw <= 0x7fffffffL) {
       const bool skip = a.vis != nullptr || a.fim != nullptr;
-#define JAF_W(KV, MB) if (a.K == KV && wide_minb == MB) { if (skip) k_warp_fuse_nhwc_wide<KV, MB, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide<KV, MB, false><<<(unsigned)gridw, 256, 0, st>>>(a); return true; }
-      JAF_W(4, 2) JAF_W(4, 3) JAF_W(4, 4) JAF_W(4, 5) JAF_W(4, 6) JAF_W(1, 4) JAF_W(2, 4) JAF_W(3, 4)
-      static const int wide_minb8 = wf_env("JAF_WF_WIDE_MINB8", 3);
+      const bool rgbm = tn.rgb_merge != 0 && a.rgb != nullptr && a.out_rgb != nullptr && a.mask_c == 1;
+#define JAF_W(KV, MB) if (a.K == KV && wide_minb == MB) { \
+        jaf::note_kernel("k_warp_fuse_nhwc_wide<K=%d,MINB=%d,SKIP=%d,RGBM=%d>", KV, MB, (int)skip, (int)rgbm); \
+        if (skip) { if (rgbm) k_warp_fuse_nhwc_wide<KV, MB, true, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide<KV, MB, true, false><<<(unsigned)gridw, 256, 0, st>>>(a); } \
+        else { if (rgbm) k_warp_fuse_nhwc_wide<KV, MB, false, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide<KV, MB, false, false><<<(unsigned)gridw, 256, 0, st>>>(a); } \
+        return true; }
+      JAF_W(4, 3) JAF_W(4, 4) JAF_W(4, 5)
+      if (a.K <= 3) {
+        const int wide_minb = 4;  // K < 4 carries one occupancy variant
+        JAF_W(1, 4) JAF_W(2, 4) JAF_W(3, 4)
+      }
 #define JAF_W8(KV) if (a.K == KV) { \
+        jaf::note_kernel("k_warp_fuse_nhwc_wide2<K=%d,MINB=%d,SKIP=%d>", KV, wide_minb8, (int)skip); \
         if (wide_minb8 == 4) { if (skip) k_warp_fuse_nhwc_wide2<KV, 4, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide2<KV, 4, false><<<(unsigned)gridw, 256, 0, st>>>(a); } \
         else { if (skip) k_warp_fuse_nhwc_wide2<KV, 3, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide2<KV, 3, false><<<(unsigned)gridw, 256, 0, st>>>(a); } \
         return true; }
@@ -1204,7 +1273,7 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
   const int ppw = 32 / lpp;
   const int tw = 8 * ppw;
   a.tiles_x = (a.W + tw - 1) / tw;
-  static const int rows_env = wf_env("JAF_WF_ROWS_PER_CTA", 0);
+  const int rows_env = tn.rows_per_cta;
   const bool tuned_dense = lpp == 8 && a.K == 4 && a.vis == nullptr && a.fim == nullptr;
   const int rows_dflt = rows_env > 0 ? rows_env : (tuned_dense ? 32 : 16);
   a.rows_per_cta = a.H < rows_dflt ? a.H : rows_dflt;
@@ -1268,7 +1337,12 @@ extern "C" int jaf_warp_fuse(const JafWarpFuseParams* p) {
   const int grid = jaf::ceil_div(npix, 256);
   if (!rgb_done || !feat_done) JAF_REQUIRE(p->K <= kMaxKGeneric, "K > 16 is not supported by the generic kernel");
   if (!rgb_done) {
-    if (!launch_rgb(a, st)) launch_generic<float, false, true>(a, grid, 1, st);
+    if (launch_rgb(a, st)) {
+      if (feat_done) jaf::note_kernel("k_warp_fuse_rgb<K=%d,SKIP=%d>", a.K, (int)(a.vis != nullptr || a.fim != nullptr));
+    } else {
+      launch_generic<float, false, true>(a, grid, 1, st);
+      if (feat_done) jaf::note_kernel("k_warp_fuse_generic<f32,planar,rgb,K=%d>", a.K);
+    }
     ++launches;
   }
   if (!feat_done) {
@@ -1289,9 +1363,23 @@ extern "C" int jaf_warp_fuse(const JafWarpFuseParams* p) {
       if (nhwc) launch_generic<__nv_bfloat16, true, false>(f, grid, ny, st);
       else      launch_generic<__nv_bfloat16, false, false>(f, grid, ny, st);
     }
+    jaf::note_kernel("k_warp_fuse_generic<%s,%s,K=%d>", p->feat_dtype == JAF_DTYPE_F32 ? "f32" : "bf16",
+                     nhwc ? "nhwc" : "planar", a.K);
     ++launches;
   }
   return jaf::finish_launch("jaf_warp_fuse", launches);
+}
+
+extern "C" int jaf_tuning_info(char* buf, int n) {
+  const WFTune& t = wf_tune();
+  char tmp[512];
+  const int len = snprintf(tmp, sizeof(tmp),
+                           "JAF_WF_WIDE=%d JAF_WF_WIDE_MINB=%d JAF_WF_WIDE_MINB8=%d JAF_WF_WIDE_ROWS_PER_CTA=%d "
+                           "JAF_WF_RGB_MERGE=%d JAF_WF_MINB=%d JAF_WF_MINB_SKIP=%d JAF_WF_ROWS=%d JAF_WF_ROWS_PER_CTA=%d",
+                           t.wide, t.wide_minb, t.wide_minb8, t.wide_rows, t.rgb_merge, t.minb_dense, t.minb_skip, t.rows,
+                           t.rows_per_cta);
+  if (buf != nullptr && n > 0) snprintf(buf, (size_t)n, "%s", tmp);
+  return len + 1;
 }
 
 extern "C" int jaf_warp_image(const float* src, const float* grid, int N, int C, int Hs, int Ws, int H, int W,

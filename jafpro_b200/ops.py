@@ -189,7 +189,7 @@ def _feat_layout(feat):
 
 
 def warp_fuse(grid, rgb=None, feat=None, *, logits=None, vis=None, fim=None, tgt_mask=None, fake=None, conf=None,
-              ref_index=None, align_corners: bool = False, return_warped: bool = False):
+              ref_index=None, align_corners: bool = False, return_warped: bool = False, out_rgb=None, out_feat=None):
     """Fused K-reference warp + fusion (include/jafpro_b200.h).
 
     grid [B,K,H,W,2] f32; rgb [R,K,3,Hs,Ws] f32; feat [R,K,C,Hs,Ws] f32/bf16 (contiguous, or with
@@ -205,14 +205,17 @@ def warp_fuse(grid, rgb=None, feat=None, *, logits=None, vis=None, fim=None, tgt
     q.B, q.K, q.H, q.W = B, K, H, W
     q.align_corners = int(bool(align_corners))
     q.grid = grid.data_ptr()
-    out_rgb = out_feat = warped = None
+    warped = None
     Hs = Ws = None
     if rgb is not None:
         rgb = _check(rgb, "rgb", torch.float32)
         if rgb.dim() != 5 or rgb.shape[1] != K or rgb.shape[2] != 3:
             raise RuntimeError("rgb must be [R, K, 3, Hs, Ws]")
         Hs, Ws = rgb.shape[-2:]
-        out_rgb = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        if out_rgb is None:
+            out_rgb = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        elif tuple(_check(out_rgb, "out_rgb", torch.float32).shape) != (B, 3, H, W):
+            raise RuntimeError("out_rgb must be [B, 3, H, W]")
         q.rgb, q.out_rgb = rgb.data_ptr(), out_rgb.data_ptr()
         if return_warped:
             warped = torch.empty((B, K, 3, H, W), dtype=torch.float32, device=dev)
@@ -224,7 +227,11 @@ def warp_fuse(grid, rgb=None, feat=None, *, logits=None, vis=None, fim=None, tgt
         if Hs is not None and (fh, fw) != (Hs, Ws):
             raise RuntimeError("rgb and feat must share the reference size")
         Hs, Ws = fh, fw
-        if layout == 1:
+        if out_feat is not None:  # caller-allocated (the reference extension's convention): same layout as feat
+            if out_feat.dtype != feat.dtype or tuple(out_feat.shape) != (B, Cc, H, W) or not out_feat.is_cuda or \
+                    not (out_feat.permute(0, 2, 3, 1) if layout == 1 else out_feat).is_contiguous():
+                raise RuntimeError("out_feat must be [B, C, H, W] with feat's dtype and memory format")
+        elif layout == 1:
             out_feat = torch.empty((B, H, W, Cc), dtype=feat.dtype, device=dev).permute(0, 3, 1, 2)
         else:
             out_feat = torch.empty((B, Cc, H, W), dtype=feat.dtype, device=dev)
@@ -262,6 +269,33 @@ def warp_fuse(grid, rgb=None, feat=None, *, logits=None, vis=None, fim=None, tgt
     if return_warped:
         return out_rgb, out_feat, warped
     return out_rgb, out_feat
+
+
+class FrameGraph:
+    """Capture a fixed call sequence of this module once into a CUDA graph and replay it with one launch.
+
+    The reference's inference loop runs the path per frame at batch 1 (test/conv_pro_test.py:255-278: cal_flow ->
+    warp_image -> mask / blend), where Python + launch overhead dominates the few microseconds of GPU work
+    (SURVEY §7 hard part 4).  `fn` is any closure over ops of this module with fixed tensors (write new inputs
+    into those tensors with copy_ before `replay`); every kernel behind the C ABI is capture-safe (no allocation,
+    synchronisation or host round trip inside a call)."""
+
+    def __init__(self, fn, warmup: int = 3):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up off the capture: one-time initialisation (workspaces, attributes)
+            for _ in range(warmup):
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
 
 
 def warp_fuse_host(grid, rgb=None, feat=None, *, feat_channels_last: bool = False, logits=None, vis=None, fim=None,

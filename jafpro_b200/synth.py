@@ -52,6 +52,53 @@ def dense_flows(B: int, K: int, H: int, W: int, seed: int = 0, device="cpu", max
     return (identity_grid(H, W, device)[None, None] + disp * scale).contiguous()
 
 
+def hard_flows(B: int, K: int, H: int, W: int, seed: int = 0, device="cpu", block: int = 32,
+               max_disp_px: float = 64.0, max_rot: float = 0.6, scale_range=(0.7, 1.4)):
+    """[B,K,H,W,2] full-frame coverage, piecewise-affine like real SMPL transfer flows (one affine map per body
+    part / triangle, src/nmr.py:617-659) but without the background: the frame is cut into `block`-pixel cells and
+    every (frame, reference, cell) gets its own rotation (|theta| <= max_rot rad), isotropic scale and translation
+    (up to +-max_disp_px pixels).  Gather locality is what real flows have INSIDE a part and is broken at every
+    cell boundary; samples that leave the reference are clamped by the border rule like real ones."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    by, bx = (H + block - 1) // block, (W + block - 1) // block
+    n = B * K
+    th = (torch.rand((n, by, bx), generator=g, device=device) * 2 - 1) * max_rot
+    sc = scale_range[0] + (scale_range[1] - scale_range[0]) * torch.rand((n, by, bx), generator=g, device=device)
+    tx = (torch.rand((n, by, bx), generator=g, device=device) * 2 - 1) * max_disp_px
+    ty = (torch.rand((n, by, bx), generator=g, device=device) * 2 - 1) * max_disp_px
+    ys = torch.arange(H, device=device, dtype=torch.float32)
+    xs = torch.arange(W, device=device, dtype=torch.float32)
+    cy = (torch.div(ys, block, rounding_mode="floor") + 0.5) * block  # cell centres
+    cx = (torch.div(xs, block, rounding_mode="floor") + 0.5) * block
+    iy = torch.div(ys, block, rounding_mode="floor").long()
+    ix = torch.div(xs, block, rounding_mode="floor").long()
+    up = lambda t: t[:, iy][:, :, ix]                                  # [n,H,W]
+    dx = (xs - cx)[None, None, :].expand(n, H, W)
+    dy = (ys - cy)[None, :, None].expand(n, H, W)
+    c, s_ = torch.cos(up(th)) * up(sc), torch.sin(up(th)) * up(sc)
+    m = 0.75 * block                                                   # keep the source cell (mostly) inside the frame
+    scx = (cx[None, None, :] + up(tx)).clamp(m, W - m)
+    scy = (cy[None, :, None] + up(ty)).clamp(m, H - m)
+    sx = scx + c * dx - s_ * dy                                        # source position in pixels
+    sy = scy + s_ * dx + c * dy
+    gx = (2 * sx + 1 - W) / W                                          # pixel-centre NDC (align_corners=False)
+    gy = (2 * sy + 1 - H) / H
+    return torch.stack([gx, gy], -1).reshape(B, K, H, W, 2).contiguous()
+
+
+def perm_flows(B: int, K: int, H: int, W: int, seed: int = 0, device="cpu"):
+    """[B,K,H,W,2] worst case for any gather: every target pixel samples the centre of an independently drawn random
+    source pixel (no two neighbouring pixels share a cache line of the reference)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    flat = torch.empty((B * K, H * W), dtype=torch.int64, device=device)
+    for i in range(B * K):
+        flat[i] = torch.randperm(H * W, generator=g, device=device)
+    sy, sx = torch.div(flat, W, rounding_mode="floor").float(), (flat % W).float()
+    gx = (2 * sx + 1 - W) / W
+    gy = (2 * sy + 1 - H) / H
+    return torch.stack([gx, gy], -1).reshape(B, K, H, W, 2).contiguous()
+
+
 def reference_sets(R: int, K: int, C: int, H: int, W: int, seed: int = 0, device="cpu", channels_last: bool = True):
     """-> rgb [R,K,3,H,W] f32 in [-1,1] (data range of src/data.py:591), feat [R,K,C,H,W] bf16 ~ N(0,1)
     (channels-last strides when asked)."""

@@ -302,6 +302,37 @@ class RefRaster:
         return fim, wim, depth
 
 
+    def time_kernels(self, faces_xyz, image_size: int, near: float = 0.1, far: float = 100.0, reps: int = 3):
+        """Median milliseconds of the reference's forward_face_index_map kernels (1 + 2) on `faces_xyz`, CUDA events
+        on the legacy default stream the reference launches on; the fills / clone / flips around them are outside."""
+        import torch
+        faces = faces_xyz.contiguous().clone()
+        B, F = faces.shape[:2]
+        dev = faces.device
+        fim = torch.full((B, image_size, image_size), -1, dtype=torch.int32, device=dev)
+        wim = torch.zeros((B, image_size, image_size, 3), dtype=torch.float32, device=dev)
+        depth = torch.full((B, image_size, image_size), float(far), dtype=torch.float32, device=dev)
+        finv_map = torch.zeros(1, dtype=torch.float32, device=dev)
+        faces_inv = torch.zeros_like(faces)
+        ts = []
+        legacy = torch.cuda.ExternalStream(0)
+        for _ in range(reps + 1):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(legacy)
+            rc = self._lib.jaf_ref_forward_face_index_map(
+                C.c_void_p(faces.data_ptr()), C.c_void_p(faces_inv.data_ptr()), C.c_void_p(fim.data_ptr()),
+                C.c_void_p(wim.data_ptr()), C.c_void_p(depth.data_ptr()), C.c_void_p(finv_map.data_ptr()),
+                B, F, image_size, C.c_float(near), C.c_float(far), 0)
+            e1.record(legacy)
+            e1.synchronize()
+            if rc != 0:
+                raise RuntimeError(f"reference rasteriser failed: cuda error {-rc}")
+            ts.append(e0.elapsed_time(e1))
+        ts = sorted(ts[1:])
+        return ts[len(ts) // 2]
+
+
 # --------------------------------------------------------------------------- §8f rank 1
 def texture_warp(tex_parts, iuv, align_corners: bool = False):
     """test/conv_pro_test.py:41-74 (texture_warp_pytorch).  tex_parts [P,3,Ht,Wt] f32, iuv [B,H,W,3] or

@@ -275,14 +275,16 @@ def test_warp_fuse_wide_lane_kernel_matches_oracle(K):
     out_rgb, out_feat = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, logits=_cu(c["logits"]),
                                       tgt_mask=_cu(c["mask"]))
     assert _lib.launch_count() == n0 + 1
-    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 2e-6
+    # the RGB planes are produced inside the feature row loop from the feature weights (softmax * mask folded into
+    # the taps, approximate softmax division): <= 1e-5 of the oracle, north-star tolerance 1e-4
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 1e-5
     ok, frac = _bf16_close(_bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
     assert ok and frac < 2e-3, frac
     # the same call with an all-ones visibility map runs the 8-lane kernel: the two kernels agree
     ones = torch.ones(B, K, H, W, device=DEV)
     rgb2, feat2 = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, logits=_cu(c["logits"]), vis=ones,
                                 tgt_mask=_cu(c["mask"]))
-    assert float((rgb2 - out_rgb).abs().max()) <= 2e-6
+    assert float((rgb2 - out_rgb).abs().max()) <= 1e-5
     ok2, frac2 = _bf16_close(_bf16_bits(feat2.permute(0, 2, 3, 1).contiguous()), _bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()))
     assert ok2 and frac2 < 2e-3
 
@@ -401,7 +403,7 @@ def test_full_size_properties_256_k4_c64():
     assert float((gotf.float() - (wf * a[:, :, None]).sum(1)).abs().max()) <= 2e-2
     # (5) a sub-batch of the oracle at full size (seconds on CPU)
     o = oracle.warp_fuse(_np(grid[:1]), rgb=_np(rgb[:1]), logits=_np(logits[:1]))
-    assert float(np.abs(_np(got[:1]) - o["out_rgb"]).max()) <= 2e-6
+    assert float(np.abs(_np(got[:1]) - o["out_rgb"]).max()) <= 1e-5
 
 
 def test_warp_fuse_host_pipeline_matches_device_path():
