@@ -397,10 +397,45 @@ def run_wf(args):
     del hf_rgb, hf_feat
 
     # ---- the whole §8 path from poses (rows a1-a12): per step, the transfer flows of the K reference poses into every
-    # target pose (one raster per target, K composes) followed by the fused warp + fusion with fim visibility
-    from_poses = None
-    if feat is not None and S == 256:
-        from_poses = run_from_poses(args, inp, rank, dev, jd)
+    # target pose (one raster per target) composed inside the fused warp + fusion kernel, pixel-level visibility
+    from_poses = app = None
+    if feat is not None and C == 64:
+        poses = pose_inputs(args, rank, dev)
+        from_poses = run_from_poses(args, inp, poses, dev, jd)
+        # the application-shaped end-to-end number: per frame a pose + logits + mask go up and the fused RGB frame comes
+        # down; K references + reference poses per video go up once per step; fused features stay on the device
+        hp = dict(tcam=pin(poses["tcam"][:Be]), tverts=pin(poses["tverts"][:Be]),
+                  scam=pin(poses["scam"][vid_first]), sverts=pin(poses["sverts"][vid_first]), f_idx=poses["f_idx"].cpu())
+        d_feat = torch.empty((Be, S, S, C), dtype=torch.bfloat16, device=dev)
+
+        def app_step():
+            ops.warp_fuse_from_poses_host(hp["scam"], hp["sverts"], hp["tcam"], hp["tverts"], hp["f_idx"], S, rgb=hv_rgb,
+                                          feat=hv_feat, logits=h["logits"], tgt_mask=h["mask"], ref_index=ref_index,
+                                          out_rgb=o_rgb, out_feat_device=d_feat)
+        for _ in range(3):
+            app_step()
+        n = max(3, min(args.steps, 10))
+        jd.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            app_step()
+        torch.cuda.synchronize()
+        mx, fr = jd.reduce_max_sum((time.perf_counter() - t0) * 1000.0, float(Be * n), device=dev)
+        chk2, chkf = ops.warp_fuse_from_poses(poses["scam"][vid_first].contiguous(), poses["sverts"][vid_first].contiguous(),
+                                              poses["tcam"][:Be].contiguous(), poses["tverts"][:Be].contiguous(), poses["f_idx"], S,
+                                              rgb=inp["rgb"][vid_first].contiguous(), feat=feat[vid_first],
+                                              logits=inp["logits"][:Be].contiguous(), tgt_mask=inp["mask"][:Be].contiguous(),
+                                              ref_index=ref_index.to(dev))
+        app = {"value": round(fr / (mx / 1000.0), 1), "unit": UNIT, "frames_per_step": Be,
+               "h2d_bytes_per_step": int(nbytes([hp["tcam"], hp["tverts"], hp["scam"], hp["sverts"], hp["f_idx"], hv_rgb, hv_feat,
+                                                 h["logits"], h["mask"], ref_index])),
+               "d2h_bytes_per_step": int(nbytes([o_rgb])),
+               "matches_device_path": bool(torch.equal(chk2.cpu(), o_rgb)) and bool(torch.equal(chkf.permute(0, 2, 3, 1), d_feat)),
+               "api": "jafpro_b200.fusion.warp_fuse_from_poses_host -> jaf_warp_fuse_from_poses_host",
+               "note": "poses (not flows) uploaded, references + reference poses once per video, fused RGB downloaded, fused "
+                       "features device-resident (they feed the next device stage)"}
+    pcie = pcie_probe(dev, jd)
 
     # final result gather over NCCL (the only data collective of the job): a per-rank checksum
     chk = out[0].double().sum().reshape(1)
@@ -439,7 +474,8 @@ def run_wf(args):
                 "per_frame_refs": {"value": round(e2e_frame_refs, 1), "h2d_bytes_per_step": int(h2d_b),
                                    "note": "every frame carries its own K references (the device benchmark's layout)"},
                 "api": "jafpro_b200.fusion.warp_fuse_host -> jaf_warp_fuse_host (pinned host buffers)",
-                "matches_device_path": e2e_ok, "cpu_affinity_bound_to_gpu": bool(numa_bound)},
+                "matches_device_path": e2e_ok, "cpu_affinity_bound_to_gpu": bool(numa_bound),
+                "application": app, "pinned_memcpy_probe": pcie},
         "from_poses": from_poses,
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -453,30 +489,62 @@ def run_wf(args):
     emit(line)
 
 
-def run_from_poses(args, inp, rank, dev, jd):
-    from jafpro_b200 import _lib, ops, synth
+def pose_inputs(args, rank, dev):
+    """Random SMPL poses of the workload: per video Fv target poses + K reference poses (expanded per frame, like the
+    references of the device benchmark)."""
+    from jafpro_b200 import synth
     from jafpro_b200.nmr import load_smpl_template
     V, Fv, S, K, C = WF_WORKLOADS[args.workload]
-    B = V * Fv
     f_idx = torch.from_numpy(load_smpl_template()[1]).to(dev)
     cams, verts = [], []
     for v in range(V):
         c_, v_ = synth.smpl_poses(Fv + K, seed=(1000 + rank) * 100 + v, device=dev)
         cams.append(c_)
         verts.append(v_)
-    tcam = torch.cat([c_[:Fv] for c_ in cams]).contiguous()
-    tverts = torch.cat([v_[:Fv] for v_ in verts]).contiguous()
-    scam = torch.cat([c_[Fv:].unsqueeze(0).expand(Fv, -1, -1) for c_ in cams]).contiguous()
-    sverts = torch.cat([v_[Fv:].unsqueeze(0).expand(Fv, -1, -1, -1) for v_ in verts]).contiguous()
+    return dict(f_idx=f_idx,
+                tcam=torch.cat([c_[:Fv] for c_ in cams]).contiguous(),
+                tverts=torch.cat([v_[:Fv] for v_ in verts]).contiguous(),
+                scam=torch.cat([c_[Fv:].unsqueeze(0).expand(Fv, -1, -1) for c_ in cams]).contiguous(),
+                sverts=torch.cat([v_[Fv:].unsqueeze(0).expand(Fv, -1, -1, -1) for v_ in verts]).contiguous())
 
-    fused = hasattr(ops, "warp_fuse_from_poses")
+
+def pcie_probe(dev, jd, mb=256, reps=4):
+    """Pinned-memory copy bandwidth of THIS run's ranks, all ranks copying at the same time (H2D and D2H together, like
+    the e2e pipeline): the host-side ceiling of any host-buffer number.  -> GB/s summed over the ranks."""
+    n = mb * 1024 * 1024
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    res = {}
+    for mode in ("h2d", "d2h", "both"):
+        jd.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if mode in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if mode in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1000.0
+        nb = n * reps * (2 if mode == "both" else 1)
+        mx, tot = jd.reduce_max_sum(ms, float(nb), device=dev)
+        res[mode + "_GBps_all_ranks"] = round(tot / (mx * 1e-3) / 1e9, 1)
+    res["note"] = f"{mb} MiB pinned buffers x {reps}, every rank at once; 'both' = H2D and D2H concurrently on two streams"
+    return res
+
+
+def run_from_poses(args, inp, poses, dev, jd):
+    from jafpro_b200 import _lib, ops
+    V, Fv, S, K, C = WF_WORKLOADS[args.workload]
+    B = V * Fv
+    scam, sverts, tcam, tverts, f_idx = (poses[k] for k in ("scam", "sverts", "tcam", "tverts", "f_idx"))
 
     def pose_step():
-        if fused:
-            return ops.warp_fuse_from_poses(scam, sverts, tcam, tverts, f_idx, S, rgb=inp["rgb"], feat=inp["feat"],
-                                            logits=inp["logits"], tgt_mask=inp["mask"])
-        T, fm, _ = ops.cal_flow_multi(scam, sverts, tcam, tverts, f_idx, S, return_wim=False)
-        return ops.warp_fuse(T, rgb=inp["rgb"], feat=inp["feat"], logits=inp["logits"], fim=fm, tgt_mask=inp["mask"])
+        return ops.warp_fuse_from_poses(scam, sverts, tcam, tverts, f_idx, S, rgb=inp["rgb"], feat=inp["feat"],
+                                        logits=inp["logits"], tgt_mask=inp["mask"])
 
     n = max(3, min(args.steps, 20))
     total, _, _ = timed(pose_step, n, 3, barrier=jd.barrier)
@@ -555,6 +623,24 @@ def run_aux(args):
         # the same per-frame step captured once in a CUDA graph and replayed (launch-overhead-free submission)
         seq = ops.FrameGraph(fn)
         tg, perg, _ = timed(seq.replay, steps * 10, args.warmup)
+        # a 30-frame batch-1 sequence from poses (cal_flow -> warp -> mask / blend per frame, conv_pro_test.py:255-278),
+        # eager and as ONE graph launch
+        _, fidx = load_smpl_template()
+        f_idx = torch.from_numpy(fidx).to(dev)
+        cam, verts = synth.smpl_poses(31, seed=3 + rank, device=dev)
+        outs = [torch.empty(1, 3, 256, 256, device=dev) for _ in range(30)]
+
+        def sequence():
+            for t in range(30):
+                flow, fim, _ = ops.cal_flow(cam[30:], verts[30:], cam[t:t + 1], verts[t:t + 1], f_idx, 256, return_maps=True)
+                ops.warp_fuse(flow[:, None], rgb=rgb, fim=fim, fake=fake, conf=conf, out_rgb=outs[t])
+            return outs
+        eager_out = [o.clone() for o in sequence()]
+        ts_e, pe, _ = timed(sequence, steps, 3)
+        seq_launches = last_timed_launches // steps
+        gseq = ops.FrameGraph(sequence)
+        ts_g, pg, _ = timed(gseq.replay, steps * 3, 3)
+        seq_ok = all(torch.equal(a, b) for a, b in zip(eager_out, outs))
         src_img, g1 = rgb[:, 0].contiguous(), grid[:, 0].contiguous()
 
         def torch_ref():
@@ -573,7 +659,13 @@ def run_aux(args):
                      "latency_us": {"median_back_to_back": round(us, 2), "median_l2_flushed": round(cold[len(cold) // 2] * 1e3, 2),
                                     "median_cuda_graph_replay": round(perg[len(perg) // 2] * 1e3, 2),
                                     "torch_cuda_op_sequence_median": round(pert[len(pert) // 2] * 1e3, 2),
-                                    "torch_cuda_launches": 5, "our_launches": int(launches_per_call)},
+                                    "torch_cuda_launches": 5, "our_launches": int(launches_per_call),
+                                    "sequence_30_frames_from_poses": {
+                                        "us_per_frame_eager": round(pe[len(pe) // 2] * 1e3 / 30, 2),
+                                        "us_per_frame_cuda_graph": round(pg[len(pg) // 2] * 1e3 / 30, 2),
+                                        "kernels_per_frame": seq_launches // 30, "graph_matches_eager_bits": bool(seq_ok),
+                                        "note": "per frame: jaf_cal_flow (memset + scatter + huge + resolve/compose) + jaf_warp_fuse "
+                                                "(warp x visibility, confidence blend), batch 1, 256^2"}},
                      "gpu_launches": int(launches_per_call * steps * 10), "clocks": clocks})
         line["e2e"] = e2e_c1(ops, rgb, grid, mask, fake, conf, steps)
         if world == 1 and not args.no_cpu and rank == 0:

@@ -79,6 +79,21 @@ int jaf_raster_fim_wim(const float* faces_xyz, int B, int F, int image_size, flo
                        void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * a4-a6 with the extension's OWN contract: rasterize_cuda.forward_face_index_map(faces, face_index_map, weight_map,
+ * depth_map, face_inv_map, faces_inv, image_size, near, far, return_rgb, return_alpha, return_depth)
+ * (NR/cuda/rasterize_cuda.cpp:70-95,194-200 -> rasterize_cuda_kernel.cu:24-169,596-651).
+ * Outputs are PRE-FILLED by the caller (fim -1, wim 0, depth far, faces_inv 0: NR/rasterize.py:50-52,164) and filled
+ * in place: only pixels covered by a face are written (rasterize_cuda_kernel.cu:156-168), rows are NOT flipped (the
+ * flip is Python's, NR/rasterize.py:334-338), faces_inv [B,F,3,3] (nullable) receives kernel_1's per-face inverse
+ * matrices for front faces, face_inv_map [B,S,S,3,3] is written only when return_depth != 0 (else it may be the
+ * reference's 1-element dummy or NULL).  return_rgb / return_alpha do not reach the kernels (:105-169) and are
+ * not parameters here.  Every written value is bit-identical to the reference kernels'.
+ * --------------------------------------------------------------------------------- */
+int jaf_forward_face_index_map(const float* faces, int32_t* face_index_map, float* weight_map, float* depth_map,
+                               float* face_inv_map, float* faces_inv, int B, int F, int image_size, float near_,
+                               float far_, int return_depth, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * a7  SMPLRenderer.render_fim_wim (src/nmr.py:263-278) in one call: a1-a3 + a4-a6.
  * faces_xyz out [B,F,3,3] may be NULL when the caller does not need `faces`
  * (then the [B,13776,3,3] tensor never touches HBM).
@@ -165,11 +180,49 @@ typedef struct JafWarpFuseParams {
 
 int jaf_warp_fuse(const JafWarpFuseParams* p);
 
+/* ---------------------------------------------------------------------------------
+ * rows a7-a12 in ONE pass from the poses: the transfer flows of the K reference poses into every
+ * target pose are composed inside the warp kernel, per tile, in shared memory — the flow tensor never round-trips HBM.
+ * replaces, per target frame: K x float_estimate.cal_flow (src/cal_flow.py:28-35: render_fim_wim of the target,
+ * src/nmr.py:263-278, + cal_bc_transform, :617-659) followed by the row-F operation above with the default visibility
+ * "the target pixel is on the body" (fim != -1, the -2 sentinel of src/nmr.py:627).
+ * `p` as for jaf_warp_fuse except: grid, vis and fim are ignored (they are what this call computes), H == W = the raster
+ * size, feat/out_feat are required.  Source poses are indexed like the reference sets (r = ref_index[b] | b).
+ * T / fim (optional outputs) are bit-identical to jaf_cal_flow_multi's; out_rgb / out_feat are bit-identical to
+ * jaf_cal_flow_multi + jaf_warp_fuse(fim).  Served shapes: jaf_warp_fuse_from_poses_supported() (C = 64 channels-last
+ * bf16, K <= 8); others return JAF_ERR_UNSUPPORTED and take the two-call path.
+ * --------------------------------------------------------------------------------- */
+typedef struct JafPoseFlowParams {
+  const float* tgt_cam;      /* [B,3] (s,tx,ty)                                      */
+  const float* tgt_verts;    /* [B,V,3]                                              */
+  const float* src_cam;      /* [R,K,3]                                              */
+  const float* src_verts;    /* [R,K,V,3]                                            */
+  const int32_t* faces_idx;  /* [F,3]                                                */
+  int32_t V, F;
+  float eye_z, near_, far_;  /* as jaf_render_fim_wim                                */
+  int32_t reserved;
+  float* T;                  /* [B,K,S,S,2] out, or NULL (then it never exists)      */
+  int32_t* fim;              /* [B,S,S] out, or NULL                                 */
+  void* workspace;           /* jaf_raster_workspace_bytes(B, S)                     */
+} JafPoseFlowParams;
+
+int jaf_warp_fuse_from_poses_supported(int C, int K, int feat_layout, int feat_dtype);
+int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPoseFlowParams* q);
+
 /* Same operation with every pointer in `p` a HOST pointer (pinned or pageable): the
  * library stages frames through device buffers it owns, overlapping H2D copies, the
  * kernel and D2H copies on its own streams, `frames_per_chunk` target frames at a time
  * (0 = pick).  Reference sets are uploaded once per distinct ref_index run.  Blocking. */
 int jaf_warp_fuse_host(const JafWarpFuseParams* p, int frames_per_chunk);
+
+/* The pose-driven operation (jaf_warp_fuse_from_poses) with HOST buffers: what the application really moves per target
+ * frame is a pose (82 KB), its logits and mask up, and the fused RGB frame down; the K references and reference poses
+ * of a video go up once (ref_index).  Every pointer of `p` and `q` is a HOST pointer (q->workspace, q->T, q->fim are
+ * ignored / must be NULL).  out_feat_device (DEVICE pointer [B,H,W,C], or NULL): when given, the fused features are
+ * written there and never cross PCIe (they feed the next device stage — ConvLSTM / generators); p->out_feat (host)
+ * is then ignored.  One pipeline per device; blocking. */
+int jaf_warp_fuse_from_poses_host(const JafWarpFuseParams* p, const JafPoseFlowParams* q, int frames_per_chunk,
+                                  void* out_feat_device);
 
 /* ---------------------------------------------------------------------------------
  * a10  float_estimate.warp_image (src/cal_flow.py:37-39): jaf_warp_fuse with K = 1.
@@ -247,6 +300,10 @@ int jaf_convlstm_step_tc(const void* x, const void* h, const float* c, const voi
  * (Ch % 8 == 0 above 64), Ch <= 128.
  * --------------------------------------------------------------------------------- */
 size_t jaf_convlstm_gpack_bytes(int G, int Cin, int Ch);
+/* 1 when jaf_convlstm_step_grouped can run this cell on the current device (channel counts supported AND the row
+ * window + weight ring fit the SM's shared memory), else 0: callers fall back to jaf_convlstm_step_f32, which takes
+ * every cell the reference constructor accepts. */
+int jaf_convlstm_grouped_supported(int G, int B, int Cin, int Ch, int H, int W);
 int jaf_convlstm_gpack_weight(const float* weight, int G, int Cin, int Ch, void* wpack,
                               void* stream);
 int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, const void* wpack,

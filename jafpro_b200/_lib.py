@@ -29,6 +29,15 @@ class WarpFuseParams(C.Structure):
     ]
 
 
+class PoseFlowParams(C.Structure):
+    """``JafPoseFlowParams`` (include/jafpro_b200.h)."""
+    _fields_ = [
+        ("tgt_cam", _vp), ("tgt_verts", _vp), ("src_cam", _vp), ("src_verts", _vp), ("faces_idx", _vp),
+        ("V", C.c_int32), ("F", C.c_int32), ("eye_z", _f), ("near_", _f), ("far_", _f), ("reserved", C.c_int32),
+        ("T", _vp), ("fim", _vp), ("workspace", _vp),
+    ]
+
+
 # name -> (restype, argtypes); kept in the order of include/jafpro_b200.h
 SIGNATURES = {
     "jaf_version": (_i, []),
@@ -39,12 +48,16 @@ SIGNATURES = {
     "jaf_project_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "jaf_raster_workspace_bytes": (_sz, [_i, _i]),
     "jaf_raster_fim_wim": (_i, [_vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "jaf_forward_face_index_map": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _vp, _vp]),
     "jaf_render_fim_wim": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "jaf_flow_compose": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "jaf_cal_flow": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "jaf_cal_flow_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "jaf_warp_fuse": (_i, [C.POINTER(WarpFuseParams)]),
+    "jaf_warp_fuse_from_poses_supported": (_i, [_i, _i, _i, _i]),
+    "jaf_warp_fuse_from_poses": (_i, [C.POINTER(WarpFuseParams), C.POINTER(PoseFlowParams)]),
     "jaf_warp_fuse_host": (_i, [C.POINTER(WarpFuseParams), _i]),
+    "jaf_warp_fuse_from_poses_host": (_i, [C.POINTER(WarpFuseParams), C.POINTER(PoseFlowParams), _i, _vp]),
     "jaf_warp_image": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "jaf_mask_blend": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_softmax_fuse": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -54,6 +67,7 @@ SIGNATURES = {
     "jaf_convlstm_pack_weight": (_i, [_vp, _i, _i, _vp, _vp]),
     "jaf_convlstm_step_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_convlstm_gpack_bytes": (_sz, [_i, _i, _i]),
+    "jaf_convlstm_grouped_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "jaf_convlstm_gpack_weight": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "jaf_convlstm_step_grouped": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_flow_warp_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

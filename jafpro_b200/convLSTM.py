@@ -29,22 +29,38 @@ class ConvLSTMCell(nn.Module):
     # torch's cuDNN convolutions default to TF32 (~1e-3).  Set to False for the exact-fp32 CUDA-core kernel (~1e-6).
     tensor_cores = True
 
+    def invalidate_packed_weights(self):
+        """Drop the packed copy of ``conv.weight`` (call after an in-place update through ``.data``, which does not
+        bump the parameter's version counter: EMA, ``w.data.copy_``, ``.data.normal_``)."""
+        self._wpack_key = None
+
     def _packed(self):
         w = self.conv.weight
+        # repacked whenever the parameter object, its version or its device changes, and always in training mode
+        # (an optimizer step bumps the version; a `.data` write does not — see invalidate_packed_weights)
         key = (w.data_ptr(), w._version, w.device)
-        if getattr(self, "_wpack_key", None) != key:
+        if self.training or getattr(self, "_wpack_key", None) != key:
             self._wpack = ops.convlstm_gpack_weight(w.detach()[None].contiguous(), self.input_dim, self.hidden_dim)
             self._wpack_key = key
         return self._wpack
 
+    def _tensor_core_ok(self, B, H, W):
+        return (self.tensor_cores and tuple(self.kernel_size) == (3, 3)
+                and ops.convlstm_grouped_supported(1, B, self.input_dim, self.hidden_dim, H, W))
+
     def forward(self, input, prev_state):
         h_prev, c_prev = prev_state
-        if (self.tensor_cores and tuple(self.kernel_size) == (3, 3) and self.hidden_dim % 4 == 0
-                and self.hidden_dim <= 128 and (self.hidden_dim <= 64 or self.hidden_dim % 8 == 0)):
+        # forward-only kernels: a training script must not silently lose its gradients (the reference trains these
+        # cells, train/4.convLSTM_flowpro_interval.py:278)
+        ops.forbid_grad(input, h_prev, c_prev, self.conv.weight, self.conv.bias, name="ConvLSTMCell input / parameter")
+        B, _, H, W = input.shape
+        if self._tensor_core_ok(B, H, W):
             b = None if self.conv.bias is None else self.conv.bias.detach()[None].contiguous()
             h, c = ops.convlstm_step_grouped(input.contiguous()[None], h_prev.contiguous()[None], c_prev.contiguous()[None],
                                              self._packed(), b, self.input_dim, self.hidden_dim)
             return h[0], c[0]
+        # every other cell the reference constructor accepts (5x5 kernels, odd channel counts, cells too wide for
+        # the shared-memory plan of the tensor-core kernel): the exact-fp32 CUDA-core kernel
         return ops.convlstm_step(input.contiguous(), h_prev.contiguous(), c_prev.contiguous(),
                                  self.conv.weight.contiguous(), self.conv.bias)
 
@@ -128,6 +144,7 @@ class ConvLSTMCellTC(nn.Module):
 
     def forward(self, x_nhwc, prev_state):
         h, c = prev_state
+        ops.forbid_grad(x_nhwc, h, c, name="ConvLSTMCellTC input")
         return ops.convlstm_step_tc(x_nhwc, h, c, self.wpack, self.bias, self.input_dim, self.hidden_dim)
 
 

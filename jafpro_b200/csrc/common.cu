@@ -33,6 +33,23 @@ int cuda_status(cudaError_t e, const char* what) {
   return JAF_ERR_CUDA;
 }
 
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+
+int sm_count(int dev) {
+  static volatile int cached[kMaxDevices] = {};
+  if (dev < 0 || dev >= kMaxDevices) return 0;
+  int v = cached[dev];
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached[dev] = v;
+  }
+  return v;
+}
+
 int finish_launch(const char* what, int launches) {
   g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
   return cuda_status(cudaGetLastError(), what);

@@ -18,6 +18,24 @@ int cuda_status(cudaError_t e, const char* what);
 // report the kernel that actually ran instead of guessing from the shapes.
 void note_kernel(const char* fmt, ...);
 
+// Per-device state.  Function attributes (dynamic shared memory), __constant__ symbols and SM counts belong to a
+// DEVICE, not to the process: a process that touches a second GPU (nn.DataParallel, test/conv_pro_test.py:114-141)
+// must set them again there.  current_device() < 0 on error; sm_count() is cached per device.
+constexpr int kMaxDevices = 64;
+int current_device();
+int sm_count(int dev);
+// `if (!once.done(dev)) { ...set attributes on dev...; once.mark(dev); }` — idempotent work, so a race between two
+// threads on the same device only repeats it.
+struct PerDeviceOnce {
+  volatile unsigned char flags[kMaxDevices] = {};
+  bool done(int dev) const { return dev >= 0 && dev < kMaxDevices && flags[dev] != 0; }
+  void mark(int dev) { if (dev >= 0 && dev < kMaxDevices) flags[dev] = 1; }
+};
+
+// raster.cu: z-buffer keys [B,S,S] u64 of the projected poses into `workspace` (jaf_raster_workspace_bytes)
+int raster_keys_from_poses(const float* cam, const float* verts, const int* fidx, int B, int V, int F, int is,
+                           float eye_z, float near_, float far_, void* workspace, cudaStream_t st, int* launches);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 

@@ -449,22 +449,10 @@ int jaf_convlstm_gpack_weight(const float* weight, int G, int Cin, int Ch, void*
   return jaf::finish_launch("k_gpack_weight");
 }
 
-int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, const void* wpack, const float* bias,
-                              int G, int B, int Cin, int Ch, int H, int W, float* h_out, float* c_out, void* stream) {
-  JAF_REQUIRE(x && h && c && wpack && h_out && c_out, "null pointer");
-  JAF_REQUIRE(G > 0 && B > 0 && H > 0 && W > 0, "bad sizes");
-  JAF_REQUIRE(grouped_shape_ok(Cin, Ch), "Ch must be a multiple of 4 and at most 128");
-  JAF_REQUIRE(((uintptr_t)wpack & 15) == 0, "wpack must be 16-byte aligned");
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    JAF_CUDA(cudaGetDevice(&dev));
-    JAF_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-  }
-  GArgs a;
-  a.x = x; a.h = h; a.c = c; a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
-  a.h_out = h_out; a.c_out = c_out;
+// Launch plan of one grouped step (shared by the launcher and jaf_convlstm_grouped_supported): fills `a`, the launch
+// shape and the dynamic shared memory.  Returns JAF_OK, or JAF_ERR_UNSUPPORTED when the cell does not fit the SM.
+static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_count, GArgs& a, bool& half, size_t& smem,
+                        long& grid) {
   a.G = G; a.B = B; a.Cin = Cin; a.Ch = Ch; a.H = H; a.W = W;
   // vertical bands of ~25 columns: the halo of a flattened tile is two padded rows, so narrow bands keep it short
   // (W = 200: 2 x 28 rows instead of 2 x 203) at the price of two extra columns per band row
@@ -516,15 +504,19 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
     MT = 0;
     for (int m = 1; m <= 8; ++m) {
       const long R = (long)m * 128 + 2L * a.Wp + 2;
-      const long smem = 4L * a.Ctp * R + (long)kRing * KS * 64 * a.Ns + 256 + 128;
-      if ((long)m * a.Ns <= col_cap && smem <= smem_cap && m <= tiles_total) MT = m;
+      const long sm = 4L * a.Ctp * R + (long)kRing * KS * 64 * a.Ns + 256 + 128;
+      if ((long)m * a.Ns <= col_cap && sm <= smem_cap && m <= tiles_total) MT = m;
     }
   };
   int ks_full, mt_full, ks_half, mt_half;
   plan(kMaxSmem, 512, 28 * 1024, ks_full, mt_full);
   plan(kHalfSmem, 256, 10 * 1024, ks_half, mt_half);
-  JAF_REQUIRE(mt_full >= 1, "cell does not fit shared memory (W or channel count too large)");
-  bool half = mt_half >= 1 && (long)G * CS * jaf::ceil_div(tiles_total, mt_half) > sm_count;
+  if (mt_full < 1) {
+    jaf::set_error("jaf_convlstm_step_grouped: cell does not fit shared memory (Cin=%d Ch=%d W=%d); use "
+                   "jaf_convlstm_step_f32", Cin, Ch, W);
+    return JAF_ERR_UNSUPPORTED;
+  }
+  half = mt_half >= 1 && (long)G * CS * jaf::ceil_div(tiles_total, mt_half) > sm_count;
   if (forced_mode == 1) half = false;
   if (forced_mode == 2 && mt_half >= 1) half = true;
   int MT = half ? mt_half : mt_full;
@@ -536,15 +528,57 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
   a.MT = MT;
   a.R = MT * 128 + 2 * a.Wp + 2;
   a.a_half = (uint32_t)(a.Ctp / 8) * (uint32_t)a.R * 16u;
-  JAF_REQUIRE((uint32_t)a.R * 16u < (1u << 18), "row window too large for the descriptor");
+  if (!((uint32_t)a.R * 16u < (1u << 18))) {
+    jaf::set_error("jaf_convlstm_step_grouped: row window too large for the descriptor");
+    return JAF_ERR_UNSUPPORTED;
+  }
   a.tiles_per_group = jaf::ceil_div(tiles_total, MT);
   uint32_t cols = 32;
   while (cols < (uint32_t)(MT * a.Ns)) cols <<= 1;
   a.tmem_cols = cols;
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Nsub >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const size_t smem = 2 * (size_t)a.a_half + (size_t)kRing * a.stage_bytes + 256 + 128;
-  const long grid = (long)G * CS * a.tiles_per_group;
-  JAF_REQUIRE(grid < (1L << 31), "too many tiles");
+  smem = 2 * (size_t)a.a_half + (size_t)kRing * a.stage_bytes + 256 + 128;
+  grid = (long)G * CS * a.tiles_per_group;
+  if (grid >= (1L << 31)) {
+    jaf::set_error("jaf_convlstm_step_grouped: too many tiles");
+    return JAF_ERR_UNSUPPORTED;
+  }
+  return JAF_OK;
+}
+
+int jaf_convlstm_grouped_supported(int G, int B, int Cin, int Ch, int H, int W) {
+  if (G <= 0 || B <= 0 || H <= 0 || W <= 0 || !grouped_shape_ok(Cin, Ch)) return 0;
+  int sms = jaf::sm_count(jaf::current_device());
+  if (sms <= 0) sms = 148;  // no device yet: plan for a B200
+  GArgs a;
+  bool half;
+  size_t smem;
+  long grid;
+  return plan_grouped(G, B, Cin, Ch, H, W, sms, a, half, smem, grid) == JAF_OK ? 1 : 0;
+}
+
+int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, const void* wpack, const float* bias,
+                              int G, int B, int Cin, int Ch, int H, int W, float* h_out, float* c_out, void* stream) {
+  JAF_REQUIRE(x && h && c && wpack && h_out && c_out, "null pointer");
+  JAF_REQUIRE(G > 0 && B > 0 && H > 0 && W > 0, "bad sizes");
+  JAF_REQUIRE(grouped_shape_ok(Cin, Ch), "Ch must be a multiple of 4 and at most 128");
+  JAF_REQUIRE(((uintptr_t)wpack & 15) == 0, "wpack must be 16-byte aligned");
+  static jaf::PerDeviceOnce attr_once;  // the shared-memory attribute is per device
+  const int dev = jaf::current_device();
+  const int sm_count = jaf::sm_count(dev);
+  JAF_REQUIRE(sm_count > 0, "no current CUDA device");
+  if (!attr_once.done(dev)) {
+    JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_once.mark(dev);
+  }
+  GArgs a;
+  a.x = x; a.h = h; a.c = c; a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
+  a.h_out = h_out; a.c_out = c_out;
+  bool half;
+  size_t smem;
+  long grid;
+  const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, half, smem, grid);
+  if (st != JAF_OK) return st;
   k_convlstm_grouped<<<(unsigned)grid, half ? kThreadsHalf : kThreads, smem, jaf::as_stream(stream)>>>(a);
   return jaf::finish_launch("k_convlstm_grouped");
 }

@@ -397,14 +397,13 @@ int jaf_convlstm_step_tc(const void* x, const void* h, const float* c, const voi
   a.num_n_blocks = (4 * Ch) / BN;
   a.num_tiles = a.num_m_tiles * a.num_n_blocks;
 
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0;
-    JAF_CUDA(cudaGetDevice(&dev));
-    JAF_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  static jaf::PerDeviceOnce attr_once;  // the shared-memory attribute is per device
+  const int dev = jaf::current_device();
+  const int sm_count = jaf::sm_count(dev);
+  JAF_REQUIRE(sm_count > 0, "no current CUDA device");
+  if (!attr_once.done(dev)) {
     JAF_CUDA(cudaFuncSetAttribute(k_convlstm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr_once.mark(dev);
   }
   const int grid = a.num_tiles < sm_count ? a.num_tiles : sm_count;
   k_convlstm_tc<<<grid, NUM_THREADS, SMEM_BYTES, jaf::as_stream(stream)>>>(mx, mh, mw, a);

@@ -17,10 +17,11 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "raster_math.cuh"
 
 namespace {
 
-constexpr unsigned long long kEmptyKey = ~0ull;
+using namespace jaf_raster;
 constexpr int kBigBox = 64;     // boxes above this many pixels are walked by the whole warp
 constexpr int kHugeBox = 2048;  // boxes above this go to a queue that a follow-up launch spreads over the GPU
 constexpr int kHugeCap = 1024;  // queue capacity (entries beyond it are walked by their warp)
@@ -35,94 +36,6 @@ struct HugeQueue {
   unsigned int pad[15];
   HugeEntry e[kHugeCap];
 };
-
-// ---- a1-a3: src/nmr.py:10-28 (s*(X+t)), :271 (y *= -1), NR/look_at.py:59 (v - eye; the rotation
-// is exactly the identity for SMPLRenderer's eye), NR/vertices_to_faces.py:19-22 (gather).
-__device__ __forceinline__ void project_vertex(const float* __restrict__ p, float s, float tx, float ty,
-                                               float eye_z, float* o) {
-  o[0] = __fmul_rn(s, __fadd_rn(p[0], tx));
-  o[1] = -__fmul_rn(s, __fadd_rn(p[1], ty));
-  o[2] = __fsub_rn(p[2], eye_z);
-}
-
-__device__ __forceinline__ void load_face_projected(const float* __restrict__ cam, const float* __restrict__ verts,
-                                                    const int* __restrict__ fidx, int b, int fn, int V,
-                                                    float eye_z, float* f) {
-  const float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int v = fidx[fn * 3 + k];
-    project_vertex(verts + ((size_t)b * V + v) * 3, s, tx, ty, eye_z, f + 3 * k);
-  }
-}
-
-// ---- rasterize_cuda_kernel.cu:40 / :111
-__device__ __forceinline__ bool face_is_back(const float* f) {
-  return __fmul_rn(__fsub_rn(f[7], f[1]), __fsub_rn(f[3], f[0])) <
-         __fmul_rn(__fsub_rn(f[4], f[1]), __fsub_rn(f[6], f[0]));
-}
-
-// ---- rasterize_cuda_kernel.cu:44-62.  Returns the (pixel-space) denominator; also reports the
-// pixel-space vertex positions for the bounding box.
-__device__ __forceinline__ float face_setup(const float* f, int is, float* inv, float* px, float* py) {
-  const float isf = (float)is;
-#pragma unroll
-  for (int n = 0; n < 3; ++n) {
-    px[n] = __fmul_rn(__fadd_rn(__fmaf_rn(f[3 * n + 0], isf, isf), -1.0f), 0.5f);
-    py[n] = __fmul_rn(__fadd_rn(__fmaf_rn(f[3 * n + 1], isf, isf), -1.0f), 0.5f);
-  }
-  inv[0] = __fsub_rn(py[1], py[2]);
-  inv[1] = __fsub_rn(px[2], px[1]);
-  inv[2] = __fmaf_rn(px[1], py[2], -__fmul_rn(px[2], py[1]));
-  inv[3] = __fsub_rn(py[2], py[0]);
-  inv[4] = __fsub_rn(px[0], px[2]);
-  inv[5] = __fmaf_rn(px[2], py[0], -__fmul_rn(px[0], py[2]));
-  inv[6] = __fsub_rn(py[0], py[1]);
-  inv[7] = __fsub_rn(px[1], px[0]);
-  inv[8] = __fmaf_rn(px[0], py[1], -__fmul_rn(px[1], py[0]));
-  const float den = __fmaf_rn(px[1], inv[3], __fmaf_rn(px[2], inv[6], __fmul_rn(px[0], inv[0])));
-#pragma unroll
-  for (int k = 0; k < 9; ++k) inv[k] = __fdiv_rn(inv[k], den);
-  return den;
-}
-
-// ---- rasterize_cuda_kernel.cu:96-97, :115-137.  true => the face is a z-buffer candidate at (xi, yi).
-__device__ __forceinline__ bool pixel_test(const float* f, const float* inv, int xi, int yi, int is,
-                                           float near_, float far_, float* w, float* zp_out) {
-  // :96-97 `(2. * yi + 1 - is) / is` in double, rounded to float.  For is <= 4096 the numerator is a small
-  // integer and a correctly rounded fp32 division gives the same bits (no double-rounding case exists for
-  // quotients of integers below 2^13; checked exhaustively in tools/), without the fp64 divide.
-  float yp, xp;
-  if (is <= 4096) {
-    yp = __fdiv_rn((float)(2 * yi + 1 - is), (float)is);
-    xp = __fdiv_rn((float)(2 * xi + 1 - is), (float)is);
-  } else {
-    yp = (float)((2. * yi + 1 - is) / is);
-    xp = (float)((2. * xi + 1 - is) / is);
-  }
-  if (__fmul_rn(__fsub_rn(yp, f[1]), __fsub_rn(f[3], f[0])) < __fmul_rn(__fsub_rn(xp, f[0]), __fsub_rn(f[4], f[1])))
-    return false;
-  if (__fmul_rn(__fsub_rn(yp, f[4]), __fsub_rn(f[6], f[3])) < __fmul_rn(__fsub_rn(xp, f[3]), __fsub_rn(f[7], f[4])))
-    return false;
-  if (__fmul_rn(__fsub_rn(yp, f[7]), __fsub_rn(f[0], f[6])) < __fmul_rn(__fsub_rn(xp, f[6]), __fsub_rn(f[1], f[7])))
-    return false;
-  const float xif = (float)xi, yif = (float)yi;
-  float w_sum = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    float wk = __fadd_rn(__fmaf_rn(xif, inv[3 * k + 0], __fmul_rn(yif, inv[3 * k + 1])), inv[3 * k + 2]);
-    wk = (float)fmin(fmax((double)wk, 0.), 1.);  // :129, double min/max (NaN -> 0)
-    w[k] = wk;
-    w_sum = __fadd_rn(w_sum, wk);
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) w[k] = __fdiv_rn(w[k], w_sum);
-  const float s = __fadd_rn(__fadd_rn(__fdiv_rn(w[0], f[2]), __fdiv_rn(w[1], f[5])), __fdiv_rn(w[2], f[8]));
-  const float zp = __frcp_rn(s);  // :136 `1. / s`: double reciprocal of a float == correctly rounded fp32
-  *zp_out = zp;
-  // :137 skip if zp <= near || far <= zp; :142 accept only if zp < depth_min (<= far).  NaN fails.
-  return (zp > near_) && (zp < far_);
-}
 
 // Order-preserving float -> uint map so atomicMin on the packed key orders by depth first.
 __device__ __forceinline__ unsigned int float_order_bits(float z) {
@@ -282,7 +195,8 @@ k_raster_resolve(const unsigned long long* __restrict__ zbuf, const float* __res
                  const float* __restrict__ cam, const float* __restrict__ verts, const int* __restrict__ fidx,
                  const float* __restrict__ src_cam, const float* __restrict__ src_verts, int B, int V, int F,
                  int is, float eye_z, float near_, float far_, int flip_rows, int* __restrict__ fim,
-                 float* __restrict__ wim, float* __restrict__ depth, float* __restrict__ T, int Ksrc) {
+                 float* __restrict__ wim, float* __restrict__ depth, float* __restrict__ T, int Ksrc,
+                 int keep_bg = 0, float* __restrict__ face_inv_map = nullptr) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)B * is * is) return;
   const int b = (int)(i / ((long)is * is));
@@ -305,6 +219,24 @@ k_raster_resolve(const unsigned long long* __restrict__ zbuf, const float* __res
     }
     face_setup(f, is, inv, px, py);
     pixel_test(f, inv, xi, yi, is, near_, far_, w, &zp);
+    if (face_inv_map) {  // rasterize_cuda_kernel.cu:163-167 (return_depth)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) face_inv_map[o * 9 + k] = inv[k];
+    }
+  }
+  if (keep_bg) {
+    // the extension's own contract (rasterize_cuda_kernel.cu:156-168): the caller pre-fills the outputs
+    // (NR/rasterize.py:50-52) and only pixels covered by a face are written
+    if (fn >= 0) {
+      if (fim) fim[o] = fn;
+      if (wim) {
+        wim[o * 3 + 0] = w[0];
+        wim[o * 3 + 1] = w[1];
+        wim[o * 3 + 2] = w[2];
+      }
+      if (depth) depth[o] = zp;
+    }
+    return;
   }
   if (fim) fim[o] = fn;
   if (wim) {
@@ -366,6 +298,21 @@ k_project_gather(const float* __restrict__ cam, const float* __restrict__ verts,
   for (int k = 0; k < 9; ++k) out[i * 9 + k] = f[k];
 }
 
+// ---- kernel_1's visible output (rasterize_cuda_kernel.cu:24-67): the per-face inverse matrices; culled faces are
+// left as the caller filled them (zeros, NR/rasterize.py:164)
+__global__ void __launch_bounds__(256)
+k_faces_inv(const float* __restrict__ faces_xyz, long n, int is, float* __restrict__ faces_inv) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float f[9], inv[9], px[3], py[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) f[k] = faces_xyz[i * 9 + k];
+  if (face_is_back(f)) return;
+  face_setup(f, is, inv, px, py);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) faces_inv[i * 9 + k] = inv[k];
+}
+
 // ---- a9 standalone: src/nmr.py:617-659 on explicit fim / wim tensors
 __global__ void __launch_bounds__(256)
 k_flow_compose(const float* __restrict__ src_pts, int stride, int negate_y, const int* __restrict__ fim,
@@ -399,14 +346,18 @@ template <bool PROJECT>
 int run_pass1(const float* faces_xyz, const float* cam, const float* verts, const int* fidx, int B, int V, int F,
               int is, float eye_z, float near_, float far_, void* workspace, float* faces_out, cudaStream_t st,
               int* launches) {
-  static const bool margin_set = [] {
-    if (const char* e = getenv("JAF_RASTER_MARGIN")) {
-      const float v = (float)atof(e);
-      cudaMemcpyToSymbol(c_margin_base, &v, sizeof(float));
+  // debug knob; a __constant__ symbol exists once per device, so it is set on every device that rasterises
+  static const char* margin_env = getenv("JAF_RASTER_MARGIN");
+  if (margin_env != nullptr) {
+    static jaf::PerDeviceOnce margin_once;
+    const int dev = jaf::current_device();
+    if (!margin_once.done(dev)) {
+      const float v = (float)atof(margin_env);
+      JAF_CUDA(cudaMemcpyToSymbolAsync(c_margin_base, &v, sizeof(float), 0, cudaMemcpyHostToDevice, st));
+      JAF_CUDA(cudaStreamSynchronize(st));
+      margin_once.mark(dev);
     }
-    return true;
-  }();
-  (void)margin_set;
+  }
   auto* zb = static_cast<unsigned long long*>(workspace);
   auto* hq = reinterpret_cast<HugeQueue*>(static_cast<char*>(workspace) + zbuf_bytes(B, is));
   JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)B * is * is * 8, st));
@@ -426,6 +377,19 @@ int check_raster_args(int B, int F, int is) {
 }
 
 }  // namespace
+
+namespace jaf {
+// Pass 1 of the rasteriser on projected poses (z-buffer keys only), for callers that resolve the keys themselves
+// (the pose-driven fused warp kernel).
+int raster_keys_from_poses(const float* cam, const float* verts, const int* fidx, int B, int V, int F, int is,
+                           float eye_z, float near_, float far_, void* workspace, cudaStream_t st, int* launches) {
+  if (!check_raster_args(B, F, is) || V <= 0) {
+    set_error("raster_keys_from_poses: bad sizes");
+    return JAF_ERR_INVALID;
+  }
+  return run_pass1<true>(nullptr, cam, verts, fidx, B, V, F, is, eye_z, near_, far_, workspace, nullptr, st, launches);
+}
+}  // namespace jaf
 
 extern "C" {
 
@@ -462,6 +426,32 @@ int jaf_raster_fim_wim(const float* faces_xyz, int B, int F, int image_size, flo
       zb, faces_xyz, nullptr, nullptr, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_, flip_rows,
       fim, wim, depth, nullptr, 0);
   return jaf::finish_launch("jaf_raster_fim_wim", launches + 1);
+}
+
+int jaf_forward_face_index_map(const float* faces, int32_t* face_index_map, float* weight_map, float* depth_map,
+                               float* face_inv_map, float* faces_inv, int B, int F, int image_size, float near_,
+                               float far_, int return_depth, void* workspace, void* stream) {
+  JAF_REQUIRE((faces || F == 0) && face_index_map && weight_map && depth_map && workspace, "null pointer");
+  JAF_REQUIRE(!return_depth || face_inv_map, "return_depth needs face_inv_map [B,S,S,3,3]");
+  JAF_REQUIRE(check_raster_args(B, F, image_size), "bad sizes");
+  if (B == 0) return JAF_OK;
+  cudaStream_t st = jaf::as_stream(stream);
+  auto* zb = static_cast<unsigned long long*>(workspace);
+  const long npix = (long)B * image_size * image_size;
+  int launches = 0;
+  if (faces_inv != nullptr && (long)B * F > 0) {
+    k_faces_inv<<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(faces, (long)B * F, image_size, faces_inv);
+    ++launches;
+  }
+  {
+    const int st1 = run_pass1<false>(faces, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_, workspace,
+                                     nullptr, st, &launches);
+    if (st1 != JAF_OK) return st1;
+  }
+  k_raster_resolve<false, false><<<jaf::ceil_div(npix, 256), 256, 0, st>>>(
+      zb, faces, nullptr, nullptr, nullptr, nullptr, nullptr, B, 0, F, image_size, 0.f, near_, far_, 0, face_index_map,
+      weight_map, depth_map, nullptr, 0, 1, return_depth ? face_inv_map : nullptr);
+  return jaf::finish_launch("jaf_forward_face_index_map", launches + 1);
 }
 
 int jaf_render_fim_wim(const float* cam, const float* verts, const int32_t* faces_idx, int B, int V, int F,

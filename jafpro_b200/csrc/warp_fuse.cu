@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "raster_math.cuh"
 
 namespace {
 
@@ -81,6 +82,18 @@ struct WFArgs {
   float* out_rgb;
   void* out_feat;
   float* warped_rgb;
+  // pose-driven flavour (jaf_warp_fuse_from_poses): the transfer flows are composed per tile from the target pose's
+  // z-buffer keys and the poses, in shared memory, instead of being read from `grid`
+  const unsigned long long* zkeys;  // [B,S,S] (raster rows, i.e. not flipped)
+  const float* tgt_cam;             // [B,3]
+  const float* tgt_verts;           // [B,V,3]
+  const float* src_cam;             // [R,K,3]
+  const float* src_verts;           // [R,K,V,3]
+  const int* fidx;                  // [F,3]
+  int V;
+  float eye_z, near_, far_;
+  int* fim_out;                     // [B,H,W] or nullptr
+  float* T_out;                     // [B,K,H,W,2] or nullptr
 };
 
 // =====================================================================================
@@ -248,17 +261,24 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
 // One output pixel of the RGB planes (planar fp32, the reference layout): softmax in the reference's
 // sequential order, ATen's tap order, acc += w_k * warped_k (the visibility-skipping flavour is bit-identical to
 // k_warp_fuse_generic; the pipelined one replaces the K softmax divisions by one reciprocal, <= 1 ulp).
+// s_grid != nullptr: the flows of this tile live in shared memory (s_grid[k * s_kstride + s_pix], composed from the
+// poses by the kernel itself) and the pixel's visibility is known (s_vis 0 / 1) instead of coming from fim / vis.
 template <int KT, bool SKIP, bool PIPE = (KT <= 4)>  // PIPE: hand-pipelined flavour (needs ~2*KT + 45 registers)
 __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restrict__ rgb_base,
                                           const float2* __restrict__ b_grid, const float* __restrict__ b_logit,
                                           const float* __restrict__ b_vis, const int* __restrict__ b_fim,
                                           const float* __restrict__ b_mask, const float* __restrict__ b_fake,
                                           const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
-                                          unsigned HW, unsigned HWs, unsigned Ws) {
+                                          unsigned HW, unsigned HWs, unsigned Ws, const float2* s_grid = nullptr,
+                                          unsigned s_kstride = 0, unsigned s_pix = 0, int s_vis = 1) {
+  auto grid_at = [&](int k) -> float2 {
+    if (s_grid != nullptr) return s_grid[(unsigned)k * s_kstride + s_pix];
+    return __ldg(b_grid + ((unsigned)k * HW + pix));
+  };
   float2 gxy0[KT];
   if constexpr (!SKIP && PIPE) {
 #pragma unroll
-    for (int k = 0; k < KT; ++k) gxy0[k] = __ldg(b_grid + ((unsigned)k * HW + pix));
+    for (int k = 0; k < KT; ++k) gxy0[k] = grid_at(k);
   }
   constexpr bool kEarly = !SKIP && PIPE;
   float tm = 1.f;
@@ -266,7 +286,8 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
   if constexpr (SKIP) {
     // pixel-level visibility (fim): a background pixel contributes nothing whatever the logits are — write the empty
     // result (or the blend with it) without touching logits, flows or references
-    if (b_fim != nullptr && b_vis == nullptr && __ldg(b_fim + pix) == -1) {
+    if ((s_grid != nullptr && s_vis == 0) ||
+        (s_grid == nullptr && b_fim != nullptr && b_vis == nullptr && __ldg(b_fim + pix) == -1)) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float ov = 0.f;
@@ -295,7 +316,7 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
     aw[k] = expf(aw[k] - m);
     ssum += aw[k];
   }
-  const float vf = b_fim ? ((__ldg(b_fim + pix) != -1) ? 1.f : 0.f) : 1.f;
+  const float vf = (s_grid != nullptr) ? (float)s_vis : (b_fim ? ((__ldg(b_fim + pix) != -1) ? 1.f : 0.f) : 1.f);
   float acc[3] = {0.f, 0.f, 0.f};
   if constexpr (!SKIP && PIPE) {  // beyond 4 references the taps no longer fit the register budget
     // hand-pipelined like rgb_pixel_lean: all K sample positions first, then the gathers of reference k+1 in flight
@@ -345,7 +366,7 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
     const float v = b_vis ? __ldg(b_vis + ((unsigned)k * HW + pix)) : vf;
     const float w = (aw[k] / ssum) * v;
     if (!SKIP || w != 0.f) {  // without a visibility input nothing is skipped: no branch, loads of all k overlap
-      const float2 gxy = __ldg(b_grid + ((unsigned)k * HW + pix));
+      const float2 gxy = grid_at(k);
       const HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
       const unsigned ok = (unsigned)(k * 3) * HWs + (unsigned)t.off;
 #pragma unroll
@@ -386,10 +407,19 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
 // Phase B, RGB.  The same threads re-walk the tile one thread per pixel (coalesced planar fp32 reads:
 //   one or two lines per warp-wide load), re-reading the tile's flow / logit lines from L2.  Softmax in
 //   the reference's sequential order, ATen's accumulation order: bit-identical to the generic kernel.
-template <int LPP, int KT, int MINB, bool SKIP, int ROWS_REQ = 1>
+//
+// POSES (pose-driven flavour, SURVEY §7 step 4: "the [B,H,W,2] grid never round-trips HBM").  A phase 0 precedes the two
+// phases: one thread per tile pixel reads the target pose's z-buffer key, recomputes the winning face's barycentric
+// weights with the rasteriser's pinned arithmetic (rows a5/a6) and composes the transfer flow into every reference
+// pose (row a9, src/nmr.py:617-659 with src/cal_flow.py:30-31) — the work of k_raster_resolve<.,COMPOSE>, but the K flows
+// of the tile land in SHARED memory, where phases A and B read them.  The flow tensor T [B,K,H,W,2] and the face-index
+// map are written to HBM only when the caller passes pointers (bit-identical to jaf_cal_flow_multi's).  A tile without
+// a single covered pixel (80 % of the tiles of a DanceVideo frame) is finished by a vectorised zero fill.
+template <int LPP, int KT, int MINB, bool SKIP, int ROWS_REQ = 1, bool POSES = false>
 __global__ void __launch_bounds__(256, MINB)
 k_warp_fuse_nhwc(const WFArgs a) {
   static_assert(KT <= LPP, "one lane of the pixel group per reference");
+  static_assert(!POSES || SKIP, "the pose-driven flavour carries pixel-level visibility");
   // ROWS = 2: the group's spare lanes prepare the NEXT row as well, so one pass of sample-position /
   // softmax arithmetic serves two output rows
   constexpr int ROWS = (ROWS_REQ >= 2 && LPP >= 2 * KT) ? 2 : 1;
@@ -413,8 +443,92 @@ k_warp_fuse_nhwc(const WFArgs a) {
   const float* __restrict__ b_logit = a.logits ? a.logits + bK : nullptr;
   const float* __restrict__ b_vis = a.vis ? a.vis + bK : nullptr;
   const int* __restrict__ b_fim = (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr;
-  const float2* __restrict__ b_grid = reinterpret_cast<const float2*>(a.grid) + bK;
+  const float2* __restrict__ b_grid = POSES ? nullptr : reinterpret_cast<const float2*>(a.grid) + bK;
   const float* __restrict__ b_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
+
+  // =========================== phase 0 (POSES): flows of the tile from the poses ===========================
+  extern __shared__ __align__(16) unsigned char wf_smem[];
+  const unsigned tile_px = (unsigned)TW * (unsigned)a.rows_per_cta;
+  float2* __restrict__ s_T = reinterpret_cast<float2*>(wf_smem);                       // [KT][tile_px]
+  unsigned char* __restrict__ s_vis = wf_smem + (size_t)KT * tile_px * sizeof(float2);  // [tile_px]
+  if constexpr (POSES) {
+    using namespace jaf_raster;
+    const int S = a.H;  // the target raster IS the output frame (H == W == raster size, checked by the host)
+    int any_vis = 0;
+    for (unsigned p = threadIdx.x; p < tile_px; p += 256) {
+      const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
+      int fn = -1;
+      float w[3] = {0.f, 0.f, 0.f};
+      const bool inside = x < (int)W && y < y_end;
+      if (inside) {
+        const int yi = S - 1 - y;  // NR/rasterize.py:334-338: output row y is raster row S-1-y
+        const unsigned long long key = __ldg(a.zkeys + ((size_t)b * S + yi) * S + x);
+        if (key != kEmptyKey) {
+          fn = (int)(unsigned int)(key & 0xffffffffull);
+          float f[9], inv[9], px[3], py[3], zp;
+          load_face_projected(a.tgt_cam, a.tgt_verts, a.fidx, b, fn, a.V, a.eye_z, f);
+          face_setup(f, S, inv, px, py);
+          pixel_test(f, inv, x, yi, S, a.near_, a.far_, w, &zp);
+        }
+      }
+      int vi[3] = {0, 0, 0};
+      if (fn >= 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vi[k] = __ldg(a.fidx + fn * 3 + k);
+      }
+#pragma unroll
+      for (int ks = 0; ks < KT; ++ks) {
+        float ftx = -2.0f, fty = -2.0f;  // src/nmr.py:627
+        if (fn >= 0) {
+          const size_t sb = r * KT + ks;
+          const float sc = __ldg(a.src_cam + sb * 3 + 0), ctx = __ldg(a.src_cam + sb * 3 + 1),
+                      cty = __ldg(a.src_cam + sb * 3 + 2);
+          float ax[3], ay[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float* pv = a.src_verts + (sb * a.V + vi[k]) * 3;
+            ax[k] = __fmul_rn(sc, __fadd_rn(__ldg(pv), ctx));
+            ay[k] = __fmul_rn(sc, __fadd_rn(__ldg(pv + 1), cty));  // -(-(s*(Y+ty))): raster flip then cal_flow.py:31
+          }
+          ftx = __fadd_rn(__fadd_rn(__fmul_rn(ax[0], w[0]), __fmul_rn(ax[1], w[1])), __fmul_rn(ax[2], w[2]));
+          fty = __fadd_rn(__fadd_rn(__fmul_rn(ay[0], w[0]), __fmul_rn(ay[1], w[1])), __fmul_rn(ay[2], w[2]));
+        }
+        s_T[(unsigned)ks * tile_px + p] = make_float2(ftx, fty);
+        if (inside && a.T_out != nullptr)
+          reinterpret_cast<float2*>(a.T_out)[((size_t)b * KT + ks) * HW + (unsigned)y * W + (unsigned)x] = make_float2(ftx, fty);
+      }
+      s_vis[p] = fn >= 0 ? 1 : 0;
+      any_vis |= fn >= 0;
+      if (inside && a.fim_out != nullptr) a.fim_out[(size_t)b * HW + (unsigned)y * W + (unsigned)x] = fn;
+    }
+    if (__syncthreads_or(any_vis) == 0) {
+      // nothing of the body in this tile: every output is the empty result — vectorised fill, no row loop
+      const unsigned rows = (unsigned)(y_end - y_begin);
+      const unsigned wpx = min((unsigned)TW, W - (unsigned)tx * TW);           // tile width inside the frame
+      if (a.out_feat != nullptr) {
+        const unsigned per_row = wpx * LPP;                                      // uint4 per tile row
+        uint4* o_base = reinterpret_cast<uint4*>(a.out_feat) + ((size_t)b * HW + (size_t)y_begin * W + (size_t)tx * TW) * LPP;
+        for (unsigned i = threadIdx.x; i < rows * per_row; i += 256) {
+          const unsigned ry = i / per_row, rx = i - ry * per_row;
+          st_stream_u128(o_base + (size_t)ry * W * LPP + rx, make_uint4(0u, 0u, 0u, 0u));
+        }
+      }
+      if (a.rgb != nullptr && a.out_rgb != nullptr) {
+        const bool blend = a.fake != nullptr && a.conf != nullptr;
+        for (unsigned i = threadIdx.x; i < 3u * rows * wpx; i += 256) {
+          const unsigned c = i / (rows * wpx), q = i - c * rows * wpx;
+          const unsigned pix = (unsigned)(y_begin + q / wpx) * W + (unsigned)tx * TW + q % wpx;
+          float ov = 0.f;
+          if (blend) {
+            const float wc = __ldg(a.conf + (size_t)b * HW + pix);
+            ov = __ldg(a.fake + ((size_t)b * 3 + c) * HW + pix) * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+          }
+          st_stream_f32(a.out_rgb + ((size_t)b * 3 + c) * HW + pix, ov);
+        }
+      }
+      return;
+    }
+  }
 
   // =========================== phase A: features ===========================
   {
@@ -437,9 +551,11 @@ k_warp_fuse_nhwc(const WFArgs a) {
       const bool pin = xin && (y + rr < y_end);
       float lg = 0.f, v = 1.f;
       float2 gxy = make_float2(0.f, 0.f);
+      // tile-local pixel index of (row slot rr, this lane's column): where phase 0 left the flows and visibility
+      const unsigned lp = (unsigned)(y + rr - y_begin) * TW + (unsigned)(warp * PPW + g);
       if constexpr (SKIP) {
-        if (b_fim != nullptr) {  // uniform.  Pixel-level visibility: look at the face-index map first
-          if (pin) v = (ld_stream_s32(b_fim + (pix + (unsigned)rr * W)) != -1) ? 1.f : 0.f;
+        if (POSES || b_fim != nullptr) {  // uniform.  Pixel-level visibility: look at the face-index map first
+          if (pin) v = POSES ? (float)s_vis[lp] : ((ld_stream_s32(b_fim + (pix + (unsigned)rr * W)) != -1) ? 1.f : 0.f);
           if (__ballot_sync(FULL, pin && v != 0.f) == 0u) {
             // every pixel this warp owns in these rows is background: empty output, no flow / logit / reference read
             if (xin) {
@@ -452,7 +568,8 @@ k_warp_fuse_nhwc(const WFArgs a) {
         }
       }
       if (pin) {
-        gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
+        if constexpr (POSES) gxy = s_T[(unsigned)kk * tile_px + lp];
+        else gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
         if (b_logit) lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
         if (b_vis) v = ld_stream_f32(b_vis + (lane_in + pix));
         if (!SKIP && b_fim) v = (ld_stream_s32(b_fim + (pix + (unsigned)rr * W)) != -1) ? 1.f : 0.f;
@@ -545,7 +662,11 @@ k_warp_fuse_nhwc(const WFArgs a) {
     for (int p = threadIdx.x; p < npx; p += 256) {
       const int x = tx * TW + p % TW, y = y_begin + p / TW;
       if (x >= (int)W) continue;
-      rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
+      if constexpr (POSES)
+        rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws,
+                            s_T, tile_px, (unsigned)p, (int)s_vis[p]);
+      else
+        rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
     }
   }
 }
@@ -1158,6 +1279,7 @@ struct WFTune {
   int wide_minb8;   // JAF_WF_WIDE_MINB8: the same for K = 5..8
   int wide_rows;    // JAF_WF_WIDE_ROWS_PER_CTA: rows of a wide tile (64 columns)
   int rgb_merge;    // JAF_WF_RGB_MERGE: RGB planes inside the feature row loop (1) or as a second pass (0)
+  int minb_poses;   // JAF_WF_MINB_POSES: CTAs/SM of the pose-driven kernel, K <= 4 (4 or 5)
 };
 const WFTune& wf_tune() {
   static const WFTune t = [] {
@@ -1174,7 +1296,10 @@ const WFTune& wf_tune() {
     v.wide_minb8 = wf_env("JAF_WF_WIDE_MINB8", 3) == 4 ? 4 : 3;
     v.wide_rows = wf_env("JAF_WF_WIDE_ROWS_PER_CTA", 16);
     if (v.wide_rows < 1) v.wide_rows = 16;
-    v.rgb_merge = wf_env("JAF_WF_RGB_MERGE", 1);
+    // measured on B200 (profiles/r02_bench_ab.jsonl): merged 93.8 k frames/s dense / 83.7 k hard, two-pass 94.8 k / 89.9 k:
+    // the scalar RGB taps issued from the 4-lane groups cost more L1 wavefronts and issue slots than the second pass
+    v.rgb_merge = wf_env("JAF_WF_RGB_MERGE", 0);
+    v.minb_poses = wf_env("JAF_WF_MINB_POSES", 5) == 4 ? 4 : 5;
     return v;
   }();
   return t;
@@ -1306,7 +1431,7 @@ extern "C" int jaf_warp_fuse(const JafWarpFuseParams* p) {
   if (p->B == 0) return JAF_OK;
   cudaStream_t st = jaf::as_stream(p->stream);
 
-  WFArgs a;
+  WFArgs a = {};
   a.B = p->B; a.K = p->K; a.H = p->H; a.W = p->W; a.Hs = p->Hs; a.Ws = p->Ws; a.C = p->C;
   a.align_corners = p->align_corners; a.mask_c = p->tgt_mask ? p->mask_c : 1;
   a.rows_per_cta = 0; a.tiles_x = 0; a.tiles_y = 0;
@@ -1370,14 +1495,102 @@ extern "C" int jaf_warp_fuse(const JafWarpFuseParams* p) {
   return jaf::finish_launch("jaf_warp_fuse", launches);
 }
 
+namespace {
+
+// The pose-driven flavour exists for the headline layout: channels-last bf16 features with C = 64, K <= 8.
+bool poses_supported(int C, int K, int feat_layout, int feat_dtype) {
+  return C == 64 && K >= 1 && K <= 8 && feat_layout == JAF_LAYOUT_NHWC && feat_dtype == JAF_DTYPE_BF16;
+}
+
+template <int KV>
+void launch_poses_k(const WFArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+  constexpr int R = KV <= 4 ? 2 : 1;
+  // JAF_WF_MINB_POSES: 5 CTAs/SM (48 registers, the row loop spills a few loop invariants) or 4 (64, no spills)
+  const int mb = (KV <= 4 && wf_tune().minb_poses == 5) ? 5 : 4;
+  jaf::note_kernel("k_warp_fuse_nhwc<LPP=8,K=%d,MINB=%d,SKIP=1,ROWS=%d,POSES=1>", KV, mb, R);
+  if constexpr (KV <= 4) {
+    if (mb == 5) {
+      k_warp_fuse_nhwc<8, KV, 5, true, R, true><<<grid, 256, smem, st>>>(a);
+      return;
+    }
+  }
+  k_warp_fuse_nhwc<8, KV, 4, true, R, true><<<grid, 256, smem, st>>>(a);
+}
+
+}  // namespace
+
+extern "C" int jaf_warp_fuse_from_poses_supported(int C, int K, int feat_layout, int feat_dtype) {
+  return poses_supported(C, K, feat_layout, feat_dtype) ? 1 : 0;
+}
+
+extern "C" int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPoseFlowParams* q) {
+  JAF_REQUIRE(p != nullptr && q != nullptr, "null params");
+  JAF_REQUIRE(p->B >= 0 && p->K >= 1 && p->H > 0 && p->W == p->H && p->Hs > 1 && p->Ws > 1,
+              "bad sizes (the output frame is the target raster: H == W)");
+  JAF_REQUIRE(q->tgt_cam && q->tgt_verts && q->src_cam && q->src_verts && q->faces_idx && q->workspace, "null pose input");
+  JAF_REQUIRE(q->V > 0 && q->F >= 0, "bad mesh sizes");
+  JAF_REQUIRE(p->feat && p->out_feat, "features are required");
+  JAF_REQUIRE(!p->tgt_mask || p->mask_c == 1 || p->mask_c == 3, "mask_c must be 1 or 3");
+  JAF_REQUIRE((long)p->Hs * p->Ws < (1L << 29) && (long)p->H * p->W < (1L << 29), "image too large");
+  JAF_REQUIRE(!p->warped_rgb, "per-reference warps are not available in the pose-driven flavour");
+  JAF_REQUIRE(!q->T || (reinterpret_cast<uintptr_t>(q->T) & 7u) == 0, "T must be 8-byte aligned");
+  JAF_REQUIRE((reinterpret_cast<uintptr_t>(p->feat) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p->out_feat) & 15u) == 0,
+              "features must be 16-byte aligned");
+  if (!poses_supported(p->C, p->K, p->feat_layout, p->feat_dtype)) {
+    jaf::set_error("jaf_warp_fuse_from_poses: this build fuses C = 64 channels-last bf16 features with K <= 8; use "
+                   "jaf_cal_flow_multi + jaf_warp_fuse for other shapes");
+    return JAF_ERR_UNSUPPORTED;
+  }
+  if (p->B == 0) return JAF_OK;
+  cudaStream_t st = jaf::as_stream(p->stream);
+  int launches = 0;
+  const int st1 = jaf::raster_keys_from_poses(q->tgt_cam, q->tgt_verts, q->faces_idx, p->B, q->V, q->F, p->H, q->eye_z,
+                                              q->near_, q->far_, q->workspace, st, &launches);
+  if (st1 != JAF_OK) return st1;
+
+  WFArgs a = {};
+  a.B = p->B; a.K = p->K; a.H = p->H; a.W = p->W; a.Hs = p->Hs; a.Ws = p->Ws; a.C = p->C;
+  a.align_corners = p->align_corners; a.mask_c = p->tgt_mask ? p->mask_c : 1;
+  const bool fuse_rgb = p->rgb && p->out_rgb;
+  a.rgb = fuse_rgb ? p->rgb : nullptr; a.out_rgb = fuse_rgb ? p->out_rgb : nullptr;
+  a.feat = p->feat; a.out_feat = p->out_feat; a.ref_index = p->ref_index; a.logits = p->logits;
+  a.tgt_mask = p->tgt_mask; a.fake = p->fake; a.conf = p->conf;
+  a.zkeys = static_cast<const unsigned long long*>(q->workspace);
+  a.tgt_cam = q->tgt_cam; a.tgt_verts = q->tgt_verts; a.src_cam = q->src_cam; a.src_verts = q->src_verts;
+  a.fidx = q->faces_idx; a.V = q->V; a.eye_z = q->eye_z; a.near_ = q->near_; a.far_ = q->far_;
+  a.fim_out = q->fim; a.T_out = q->T;
+  const int tw = 32;  // 8-lane groups: 4 pixel columns per warp, 8 warps
+  a.tiles_x = (a.W + tw - 1) / tw;
+  const int rows_dflt = wf_tune().rows_per_cta > 0 ? wf_tune().rows_per_cta : 16;
+  a.rows_per_cta = a.H < rows_dflt ? a.H : rows_dflt;
+  a.tiles_y = (a.H + a.rows_per_cta - 1) / a.rows_per_cta;
+  const long grid = (long)a.tiles_x * a.tiles_y * a.B;
+  JAF_REQUIRE(grid <= 0x7fffffffL, "too many tiles");
+  const size_t tile_px = (size_t)tw * a.rows_per_cta;
+  const size_t smem = (size_t)a.K * tile_px * sizeof(float2) + tile_px;
+  JAF_REQUIRE(smem <= 48 * 1024, "tile does not fit shared memory (JAF_WF_ROWS_PER_CTA too large)");
+  switch (a.K) {
+    case 1: launch_poses_k<1>(a, (unsigned)grid, smem, st); break;
+    case 2: launch_poses_k<2>(a, (unsigned)grid, smem, st); break;
+    case 3: launch_poses_k<3>(a, (unsigned)grid, smem, st); break;
+    case 4: launch_poses_k<4>(a, (unsigned)grid, smem, st); break;
+    case 5: launch_poses_k<5>(a, (unsigned)grid, smem, st); break;
+    case 6: launch_poses_k<6>(a, (unsigned)grid, smem, st); break;
+    case 7: launch_poses_k<7>(a, (unsigned)grid, smem, st); break;
+    default: launch_poses_k<8>(a, (unsigned)grid, smem, st); break;
+  }
+  return jaf::finish_launch("jaf_warp_fuse_from_poses", launches + 1);
+}
+
 extern "C" int jaf_tuning_info(char* buf, int n) {
   const WFTune& t = wf_tune();
   char tmp[512];
   const int len = snprintf(tmp, sizeof(tmp),
                            "JAF_WF_WIDE=%d JAF_WF_WIDE_MINB=%d JAF_WF_WIDE_MINB8=%d JAF_WF_WIDE_ROWS_PER_CTA=%d "
-                           "JAF_WF_RGB_MERGE=%d JAF_WF_MINB=%d JAF_WF_MINB_SKIP=%d JAF_WF_ROWS=%d JAF_WF_ROWS_PER_CTA=%d",
-                           t.wide, t.wide_minb, t.wide_minb8, t.wide_rows, t.rgb_merge, t.minb_dense, t.minb_skip, t.rows,
-                           t.rows_per_cta);
+                           "JAF_WF_RGB_MERGE=%d JAF_WF_MINB=%d JAF_WF_MINB_SKIP=%d JAF_WF_MINB_POSES=%d JAF_WF_ROWS=%d "
+                           "JAF_WF_ROWS_PER_CTA=%d",
+                           t.wide, t.wide_minb, t.wide_minb8, t.wide_rows, t.rgb_merge, t.minb_dense, t.minb_skip,
+                           t.minb_poses, t.rows, t.rows_per_cta);
   if (buf != nullptr && n > 0) snprintf(buf, (size_t)n, "%s", tmp);
   return len + 1;
 }

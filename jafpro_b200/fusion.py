@@ -5,7 +5,12 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .ops import warp_fuse, warp_fuse_host  # noqa: F401  (re-exported: the public entry points)
+from .ops import warp_fuse, warp_fuse_from_poses_host, warp_fuse_host  # noqa: F401  (re-exported: the public entry points)
+
+
+def _eye_z(renderer):
+    from .nmr import SMPLRenderer
+    return SMPLRenderer._eye_z_f32(renderer)  # also serves the reference's own SMPLRenderer (it only has `.eye`)
 
 
 def softmax_fuse(x_con, mask_logits):
@@ -27,7 +32,7 @@ def reference_visibility(renderer, src_cams, src_vertices, fim_tgt):
     S = renderer.image_size
     _, fim_src, _ = ops.render_fim_wim(src_cams.reshape(B * K, 3).contiguous(),
                                        src_vertices.reshape(B * K, -1, 3).contiguous(), renderer.faces, S,
-                                       eye_z=renderer._eye_z, return_faces=False)
+                                       eye_z=_eye_z(renderer), return_faces=False)
     _, vis = ops.face_visibility(fim_src.reshape(B, K, S, S), fim_tgt.contiguous(), renderer.faces.shape[-2])
     return vis
 
@@ -41,9 +46,15 @@ def warp_fuse_from_poses(renderer, src_cams, src_vertices, tgt_cam, tgt_vertices
     get_vis_f2pts rule (the face under the target pixel must be visible in reference k).  `renderer` is a jafpro_b200.nmr.SMPLRenderer.
     src_cams [B,K,3], src_vertices [B,K,V,3], tgt_cam [B,3], tgt_vertices [B,V,3]; references as in warp_fuse.
     Returns (out_rgb, out_feat, T, fim)."""
+    if not per_reference_visibility and feat is not None:
+        # one pass: the flows are composed inside the warp kernel (T and fim are emitted because this API returns them)
+        return ops.warp_fuse_from_poses(src_cams.contiguous(), src_vertices.contiguous(), tgt_cam.contiguous(),
+                                        tgt_vertices.contiguous(), renderer.faces, renderer.image_size, rgb=rgb, feat=feat,
+                                        logits=logits, tgt_mask=tgt_mask, ref_index=ref_index, align_corners=align_corners,
+                                        eye_z=_eye_z(renderer), return_flow=True)
     T, fim, _ = ops.cal_flow_multi(src_cams.contiguous(), src_vertices.contiguous(), tgt_cam.contiguous(),
                                    tgt_vertices.contiguous(), renderer.faces, renderer.image_size,
-                                   eye_z=renderer._eye_z, return_wim=False)
+                                   eye_z=_eye_z(renderer), return_wim=False)
     vis = reference_visibility(renderer, src_cams, src_vertices, fim) if per_reference_visibility else None
     out_rgb, out_feat = ops.warp_fuse(T, rgb=rgb, feat=feat, logits=logits, vis=vis, fim=None if vis is not None else fim,
                                       tgt_mask=tgt_mask, ref_index=ref_index, align_corners=align_corners)

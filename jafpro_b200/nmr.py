@@ -56,11 +56,24 @@ class SMPLRenderer(nn.Module):
         self.eye = [0, 0, -(1. / np.tan(np.radians(self.viewing_angle)) + 1)]  # :177
         self._eye_z = float(np.float32(self.eye[2]))
 
+    def _eye_z_f32(self):
+        """float32 z of the look_at eye.  Derived from ``self.eye`` when the attribute cache is missing, so that these
+        methods also work when they are bound onto the REFERENCE's SMPLRenderer, which only has
+        ``eye`` (src/nmr.py:177)."""
+        ez = getattr(self, "_eye_z", None)
+        if ez is None:
+            ez = float(np.float32(self.eye[2]))
+            try:
+                self._eye_z = ez
+            except Exception:  # pragma: no cover - exotic __setattr__
+                pass
+        return ez
+
     # ---- src/nmr.py:263-278
     def render_fim_wim(self, cam, vertices, faces=None):
         if faces is None:
-            f3, fim, wim = ops.render_fim_wim(cam.contiguous(), vertices.contiguous(), self.faces, self.image_size,
-                                              eye_z=self._eye_z)
+            f3, fim, wim = ops.render_fim_wim(cam.contiguous(), vertices.contiguous(), self.faces.int(), self.image_size,
+                                              eye_z=SMPLRenderer._eye_z_f32(self))
             return f3, fim, wim
         proj_verts = self.proj_func(vertices, cam)
         proj_verts[:, :, 1] *= -1
@@ -99,5 +112,5 @@ class SMPLRenderer(nn.Module):
     # ---- src/cal_flow.py:28-35 as one fused call (no source raster, no [B,F,3,3] round trip)
     def cal_flow(self, src_cam, src_vertices, tgt_cam, tgt_vertices, return_maps=False):
         return ops.cal_flow(src_cam.contiguous(), src_vertices.contiguous(), tgt_cam.contiguous(),
-                            tgt_vertices.contiguous(), self.faces, self.image_size, eye_z=self._eye_z,
-                            return_maps=return_maps)
+                            tgt_vertices.contiguous(), self.faces.int(), self.image_size,
+                            eye_z=SMPLRenderer._eye_z_f32(self), return_maps=return_maps)

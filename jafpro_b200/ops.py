@@ -20,11 +20,26 @@ DEFAULT_NEAR, DEFAULT_FAR = 0.1, 100.0  # NR/rasterize.py:10-11 (what src/nmr.py
 _workspaces: dict = {}
 
 
+def forbid_grad(*tensors, name: str = "input"):
+    """The kernels behind this package are FORWARD-ONLY (the reference runs the flow / warp / fusion path under
+    ``torch.no_grad()`` at inference, test/conv_pro_test.py:190).  Outputs are plain tensors without a grad_fn, so a
+    drop-in that silently accepted tensors which require grad would stop a training script from learning
+    (train/4.convLSTM_flowpro_interval.py:278 trains exactly these cells).  Fail loudly instead."""
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                raise RuntimeError(
+                    f"jafpro_b200 is forward-only: {name} requires grad while autograd is enabled. Call it under "
+                    "torch.no_grad() / torch.inference_mode() (inference), or keep the reference's torch "
+                    "implementation for training.")
+
+
 def _check(t, name, dtype=None):
     if t is None:
         return None
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
+    forbid_grad(t, name=name)
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
     if not t.is_contiguous():
@@ -177,6 +192,7 @@ def _feat_layout(feat):
         raise RuntimeError("features must be float32 or bfloat16")
     if not feat.is_cuda:
         raise RuntimeError("feat must be a CUDA tensor")
+    forbid_grad(feat, name="feat")
     dt = 0 if feat.dtype == torch.float32 else 1
     if feat.dim() != 5:
         raise RuntimeError("feat must be [R, K, C, H, W]")
@@ -271,6 +287,82 @@ def warp_fuse(grid, rgb=None, feat=None, *, logits=None, vis=None, fim=None, tgt
     return out_rgb, out_feat
 
 
+def warp_fuse_from_poses(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx, image_size: int, rgb=None, feat=None, *,
+                         logits=None, tgt_mask=None, fake=None, conf=None, ref_index=None, align_corners: bool = False,
+                         eye_z: float = EYE_Z, near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR,
+                         return_flow: bool = False, out_rgb=None, out_feat=None):
+    """Rows a7-a12 from the poses in one pass (``jaf_warp_fuse_from_poses``): the transfer flows of the K reference
+    poses into every target pose are composed inside the warp kernel, in shared memory; visibility is "the target
+    pixel is on the body".  src_cam [R,K,3], src_vertices [R,K,V,3] (indexed like the reference sets: ref_index[b] or
+    b), tgt_cam [B,3], tgt_vertices [B,V,3]; references / logits / masks as in `warp_fuse`.
+    -> (out_rgb|None, out_feat) and, with return_flow, also (T [B,K,S,S,2], fim [B,S,S]) — bit-identical to
+    `cal_flow_multi`.  Shapes the fused kernel does not serve take `cal_flow_multi` + `warp_fuse` (same results)."""
+    sc, sv = _check(src_cam, "src_cam", torch.float32), _check(src_vertices, "src_vertices", torch.float32)
+    tc, tv = _check(tgt_cam, "tgt_cam", torch.float32), _check(tgt_vertices, "tgt_vertices", torch.float32)
+    faces_idx = _check(faces_idx, "faces", torch.int32)
+    if sv.dim() != 4 or sc.dim() != 3 or sv.shape[:2] != sc.shape[:2] or tv.dim() != 3:
+        raise RuntimeError("expected src_cam [R,K,3], src_vertices [R,K,V,3], tgt_cam [B,3], tgt_vertices [B,V,3]")
+    B, V, _ = tv.shape
+    R, K = sv.shape[:2]
+    S = int(image_size)
+    dev = tv.device
+    if feat is None:
+        raise RuntimeError("warp_fuse_from_poses needs feat (use cal_flow_multi + warp_fuse for RGB-only calls)")
+    layout, dt, Cc, Hs, Ws = _feat_layout(feat)
+    if feat.shape[0] != R or feat.shape[1] != K:
+        raise RuntimeError("feat must be [R, K, C, Hs, Ws] with the R, K of the source poses")
+    if ref_index is None and R != B:
+        raise RuntimeError("without ref_index the source poses / reference sets need one entry per target frame")
+    if not _lib.lib().jaf_warp_fuse_from_poses_supported(Cc, K, layout, dt):
+        idx = ref_index.long() if ref_index is not None else None
+        T, fim, _ = cal_flow_multi(sc if idx is None else sc[idx].contiguous(), sv if idx is None else sv[idx].contiguous(),
+                                   tc, tv, faces_idx, S, eye_z, near, far, return_wim=False)
+        o = warp_fuse(T, rgb=rgb, feat=feat, logits=logits, fim=fim, tgt_mask=tgt_mask, fake=fake, conf=conf,
+                      ref_index=ref_index, align_corners=align_corners, out_rgb=out_rgb, out_feat=out_feat)
+        return (o[0], o[1], T, fim) if return_flow else o
+    q = _lib.WarpFuseParams()
+    q.B, q.K, q.H, q.W, q.Hs, q.Ws, q.C = B, K, S, S, Hs, Ws, Cc
+    q.align_corners = int(bool(align_corners))
+    q.feat_layout, q.feat_dtype = layout, dt
+    if rgb is not None:
+        rgb = _check(rgb, "rgb", torch.float32)
+        if tuple(rgb.shape) != (R, K, 3, Hs, Ws):
+            raise RuntimeError("rgb must be [R, K, 3, Hs, Ws]")
+        if out_rgb is None:
+            out_rgb = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
+        q.rgb, q.out_rgb = rgb.data_ptr(), _check(out_rgb, "out_rgb", torch.float32).data_ptr()
+    if out_feat is None:
+        out_feat = torch.empty((B, S, S, Cc), dtype=feat.dtype, device=dev).permute(0, 3, 1, 2)
+    q.feat, q.out_feat = feat.data_ptr(), out_feat.data_ptr()
+    keep = []
+    for name, t, dtype, shape in (("logits", logits, torch.float32, (B, K, S, S)), ("fake", fake, torch.float32, (B, 3, S, S)),
+                                  ("conf", conf, torch.float32, (B, 1, S, S)), ("ref_index", ref_index, torch.int32, (B,))):
+        if t is not None:
+            t = _check(t, name, dtype)
+            if tuple(t.shape) != shape:
+                raise RuntimeError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+            setattr(q, name, t.data_ptr())
+            keep.append(t)
+    if tgt_mask is not None:
+        tgt_mask = _check(tgt_mask, "tgt_mask", torch.float32)
+        if tgt_mask.dim() != 4 or tgt_mask.shape[0] != B or tgt_mask.shape[1] not in (1, 3) or tuple(tgt_mask.shape[2:]) != (S, S):
+            raise RuntimeError("tgt_mask must be [B, 1 or 3, S, S]")
+        q.tgt_mask, q.mask_c = tgt_mask.data_ptr(), tgt_mask.shape[1]
+    T = torch.empty((B, K, S, S, 2), dtype=torch.float32, device=dev) if return_flow else None
+    fim = torch.empty((B, S, S), dtype=torch.int32, device=dev) if return_flow else None
+    pq = _lib.PoseFlowParams()
+    pq.tgt_cam, pq.tgt_verts, pq.src_cam, pq.src_verts = tc.data_ptr(), tv.data_ptr(), sc.data_ptr(), sv.data_ptr()
+    pq.faces_idx, pq.V, pq.F = faces_idx.data_ptr(), V, faces_idx.shape[-2]
+    pq.eye_z, pq.near_, pq.far_ = eye_z, near, far
+    pq.T, pq.fim = _ptr(T), _ptr(fim)
+    with _on(dev):
+        ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, S))
+        pq.workspace = ws.data_ptr()
+        q.stream = _stream()
+        _lib.check(_lib.lib().jaf_warp_fuse_from_poses(C.byref(q), C.byref(pq)), "warp_fuse_from_poses")
+    return (out_rgb, out_feat, T, fim) if return_flow else (out_rgb, out_feat)
+
+
 class FrameGraph:
     """Capture a fixed call sequence of this module once into a CUDA graph and replay it with one launch.
 
@@ -298,44 +390,159 @@ class FrameGraph:
         return self.out
 
 
+def _host(t, name, dtype=None, shape=None):
+    """Host-side argument check of the *_host entry points: raw pointers go straight into pipelined memcpys, so a
+    wrong dtype / stride / shape would read or write out of bounds."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or t.is_cuda:
+        raise RuntimeError(f"{name} must be a host tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    forbid_grad(t, name=name)
+    return t
+
+
+def _host_refs(q, K, rgb, feat, feat_channels_last, B, ref_index):
+    """Fills the reference-set fields of a host-side parameter block -> (R, C)."""
+    R = Cc = None
+    if rgb is not None:
+        rgb = _host(rgb, "rgb", torch.float32)
+        if rgb.dim() != 5 or rgb.shape[1] != K or rgb.shape[2] != 3:
+            raise RuntimeError("rgb must be [R, K, 3, Hs, Ws]")
+        R = rgb.shape[0]
+        q.Hs, q.Ws = rgb.shape[-2:]
+        q.rgb = rgb.data_ptr()
+    if feat is not None:
+        feat = _host(feat, "feat")
+        if feat.dtype not in (torch.float32, torch.bfloat16) or feat.dim() != 5 or feat.shape[1] != K:
+            raise RuntimeError("feat must be a float32 / bfloat16 [R,K,C,Hs,Ws] (or dense [R,K,Hs,Ws,C]) host tensor")
+        if feat_channels_last:
+            fh, fw, Cc = feat.shape[-3:]
+        else:
+            Cc, fh, fw = feat.shape[-3:]
+        if rgb is not None and ((fh, fw) != tuple(rgb.shape[-2:]) or feat.shape[0] != R):
+            raise RuntimeError("rgb and feat must share the reference count and size")
+        R = feat.shape[0]
+        q.Hs, q.Ws, q.C = fh, fw, Cc
+        q.feat_layout = int(feat_channels_last)
+        q.feat_dtype = 0 if feat.dtype == torch.float32 else 1
+        q.feat = feat.data_ptr()
+    if R is None:
+        raise RuntimeError("need rgb and/or feat")
+    if ref_index is not None:
+        ref_index = _host(ref_index, "ref_index", torch.int32, (B,))
+        if int(ref_index.min()) < 0 or int(ref_index.max()) >= R:
+            raise RuntimeError("ref_index out of range")
+        q.ref_index = ref_index.data_ptr()
+    elif R != B:
+        raise RuntimeError("without ref_index the reference tensors need one set per target frame")
+    return R, Cc
+
+
 def warp_fuse_host(grid, rgb=None, feat=None, *, feat_channels_last: bool = False, logits=None, vis=None, fim=None,
-                   tgt_mask=None, ref_index=None, align_corners: bool = False, frames_per_chunk: int = 0,
-                   out_rgb=None, out_feat=None):
+                   tgt_mask=None, fake=None, conf=None, ref_index=None, align_corners: bool = False,
+                   frames_per_chunk: int = 0, out_rgb=None, out_feat=None):
     """``jaf_warp_fuse_host``: every tensor lives in HOST memory (pin it for full PCIe speed); the
     library pipelines H2D, the kernel and D2H itself.  feat is [R,K,C,Hs,Ws], or dense
     [R,K,Hs,Ws,C] when feat_channels_last.  Returns (out_rgb, out_feat) host tensors."""
-    if grid.is_cuda:
-        raise RuntimeError("warp_fuse_host takes host tensors")
+    grid = _host(grid, "grid", torch.float32)
+    if grid.dim() != 5 or grid.shape[-1] != 2:
+        raise RuntimeError("grid must be [B, K, H, W, 2]")
     B, K, H, W, _ = grid.shape
     q = _lib.WarpFuseParams()
     q.B, q.K, q.H, q.W = B, K, H, W
     q.align_corners = int(bool(align_corners))
     q.grid = grid.data_ptr()
+    _, Cc = _host_refs(q, K, rgb, feat, feat_channels_last, B, ref_index)
     if rgb is not None:
-        q.Hs, q.Ws = rgb.shape[-2:]
         if out_rgb is None:
             out_rgb = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
-        q.rgb, q.out_rgb = rgb.data_ptr(), out_rgb.data_ptr()
+        q.out_rgb = _host(out_rgb, "out_rgb", torch.float32, (B, 3, H, W)).data_ptr()
     if feat is not None:
-        if feat_channels_last:
-            q.Hs, q.Ws, q.C = feat.shape[-3:]
-            shape = (B, H, W, q.C)
-        else:
-            q.C, q.Hs, q.Ws = feat.shape[-3:]
-            shape = (B, q.C, H, W)
-        q.feat_layout = int(feat_channels_last)
-        q.feat_dtype = 0 if feat.dtype == torch.float32 else 1
+        shape = (B, H, W, Cc) if feat_channels_last else (B, Cc, H, W)
         if out_feat is None:
             out_feat = torch.empty(shape, dtype=feat.dtype).pin_memory()
-        q.feat, q.out_feat = feat.data_ptr(), out_feat.data_ptr()
-    for name, t in (("logits", logits), ("vis", vis), ("fim", fim), ("ref_index", ref_index)):
+        q.out_feat = _host(out_feat, "out_feat", feat.dtype, shape).data_ptr()
+    for name, t, dtype, shape in (("logits", logits, torch.float32, (B, K, H, W)), ("vis", vis, torch.float32, (B, K, H, W)),
+                                  ("fim", fim, torch.int32, (B, H, W)), ("fake", fake, torch.float32, (B, 3, H, W)),
+                                  ("conf", conf, torch.float32, (B, 1, H, W))):
         if t is not None:
-            if t.is_cuda or not t.is_contiguous():
-                raise RuntimeError(f"{name} must be a contiguous host tensor")
-            setattr(q, name, t.data_ptr())
+            setattr(q, name, _host(t, name, dtype, shape).data_ptr())
     if tgt_mask is not None:
+        tgt_mask = _host(tgt_mask, "tgt_mask", torch.float32)
+        if tgt_mask.dim() != 4 or tgt_mask.shape[0] != B or tgt_mask.shape[1] not in (1, 3) or tuple(tgt_mask.shape[2:]) != (H, W):
+            raise RuntimeError("tgt_mask must be [B, 1 or 3, H, W]")
         q.tgt_mask, q.mask_c = tgt_mask.data_ptr(), tgt_mask.shape[1]
     _lib.check(_lib.lib().jaf_warp_fuse_host(C.byref(q), int(frames_per_chunk)), "warp_fuse_host")
+    return out_rgb, out_feat
+
+
+def warp_fuse_from_poses_host(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx, image_size: int, rgb=None, feat=None, *,
+                              feat_channels_last: bool = True, logits=None, tgt_mask=None, fake=None, conf=None,
+                              ref_index=None, align_corners: bool = False, eye_z: float = EYE_Z,
+                              near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR, frames_per_chunk: int = 0,
+                              out_rgb=None, out_feat=None, out_feat_device=None):
+    """``jaf_warp_fuse_from_poses_host``: the pose-driven operation with HOST tensors.  Per target frame only the pose
+    (cam [B,3], vertices [B,V,3]), its logits and masks go up and the fused RGB frame comes down; the K references
+    (rgb [R,K,3,Hs,Ws], feat dense [R,K,Hs,Ws,C] bf16) and reference poses (src_cam [R,K,3], src_vertices [R,K,V,3]) of a
+    video are uploaded once (ref_index [B]).  out_feat_device: a CUDA tensor [B,S,S,C] that receives the fused features
+    on the device (they then never cross PCIe); otherwise they are downloaded into out_feat (host).
+    Returns (out_rgb host, out_feat host | out_feat_device)."""
+    tc, tv = _host(tgt_cam, "tgt_cam", torch.float32), _host(tgt_vertices, "tgt_vertices", torch.float32)
+    sc, sv = _host(src_cam, "src_cam", torch.float32), _host(src_vertices, "src_vertices", torch.float32)
+    faces_idx = _host(faces_idx, "faces", torch.int32)
+    if tv.dim() != 3 or sv.dim() != 4 or sc.dim() != 3 or sv.shape[:2] != sc.shape[:2] or tc.shape != (tv.shape[0], 3):
+        raise RuntimeError("expected src_cam [R,K,3], src_vertices [R,K,V,3], tgt_cam [B,3], tgt_vertices [B,V,3]")
+    B, V, _ = tv.shape
+    R, K = sv.shape[:2]
+    S = int(image_size)
+    q = _lib.WarpFuseParams()
+    q.B, q.K, q.H, q.W = B, K, S, S
+    q.align_corners = int(bool(align_corners))
+    Rr, Cc = _host_refs(q, K, rgb, feat, feat_channels_last, B, ref_index)
+    if feat is None or Rr != R:
+        raise RuntimeError("feat is required and the reference sets must match the source poses (R)")
+    if not _lib.lib().jaf_warp_fuse_from_poses_supported(Cc, K, q.feat_layout, q.feat_dtype):
+        raise RuntimeError("warp_fuse_from_poses_host serves channels-last bf16 features with C = 64, K <= 8")
+    if rgb is not None:
+        if out_rgb is None:
+            out_rgb = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
+        q.out_rgb = _host(out_rgb, "out_rgb", torch.float32, (B, 3, S, S)).data_ptr()
+    dptr = None
+    if out_feat_device is not None:
+        od = _check(out_feat_device, "out_feat_device", feat.dtype)
+        if tuple(od.shape) != (B, S, S, Cc):
+            raise RuntimeError("out_feat_device must be a CUDA tensor [B, S, S, C]")
+        dptr, out_feat = od.data_ptr(), od
+    else:
+        if out_feat is None:
+            out_feat = torch.empty((B, S, S, Cc), dtype=feat.dtype).pin_memory()
+        q.out_feat = _host(out_feat, "out_feat", feat.dtype, (B, S, S, Cc)).data_ptr()
+    for name, t, dtype, shape in (("logits", logits, torch.float32, (B, K, S, S)), ("fake", fake, torch.float32, (B, 3, S, S)),
+                                  ("conf", conf, torch.float32, (B, 1, S, S))):
+        if t is not None:
+            setattr(q, name, _host(t, name, dtype, shape).data_ptr())
+    if tgt_mask is not None:
+        tgt_mask = _host(tgt_mask, "tgt_mask", torch.float32)
+        if tgt_mask.dim() != 4 or tgt_mask.shape[0] != B or tgt_mask.shape[1] not in (1, 3) or tuple(tgt_mask.shape[2:]) != (S, S):
+            raise RuntimeError("tgt_mask must be [B, 1 or 3, S, S]")
+        q.tgt_mask, q.mask_c = tgt_mask.data_ptr(), tgt_mask.shape[1]
+    pq = _lib.PoseFlowParams()
+    pq.tgt_cam, pq.tgt_verts, pq.src_cam, pq.src_verts = tc.data_ptr(), tv.data_ptr(), sc.data_ptr(), sv.data_ptr()
+    pq.faces_idx, pq.V, pq.F = faces_idx.data_ptr(), V, faces_idx.shape[-2]
+    pq.eye_z, pq.near_, pq.far_ = eye_z, near, far
+    if out_feat_device is not None:
+        with _on(out_feat_device.device):
+            _lib.check(_lib.lib().jaf_warp_fuse_from_poses_host(C.byref(q), C.byref(pq), int(frames_per_chunk), dptr),
+                       "warp_fuse_from_poses_host")
+    else:
+        _lib.check(_lib.lib().jaf_warp_fuse_from_poses_host(C.byref(q), C.byref(pq), int(frames_per_chunk), None),
+                   "warp_fuse_from_poses_host")
     return out_rgb, out_feat
 
 
@@ -446,6 +653,11 @@ def convlstm_gpack_weight(weight, Cin: int, Ch: int):
         _lib.check(_lib.lib().jaf_convlstm_gpack_weight(_ptr(weight), G, Cin, Ch, _ptr(wpack), _stream()),
                    "convlstm_gpack_weight")
     return wpack
+
+
+def convlstm_grouped_supported(G: int, B: int, Cin: int, Ch: int, H: int, W: int) -> bool:
+    """True when `convlstm_step_grouped` can run this cell (channel counts AND the shared-memory plan fit)."""
+    return bool(_lib.lib().jaf_convlstm_grouped_supported(G, B, Cin, Ch, H, W))
 
 
 def convlstm_step_grouped(x, h, c, wpack, bias, Cin: int, Ch: int):

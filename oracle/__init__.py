@@ -278,6 +278,27 @@ class RefRaster:
         self._lib = C.CDLL(path)
         self._lib.jaf_ref_forward_face_index_map.restype = C.c_int
 
+    def raw(self, faces_xyz, image_size: int, near: float = 0.1, far: float = 100.0, return_depth: bool = False):
+        """The extension call itself (NR/rasterize.py:161-169) on outputs pre-filled like NR/rasterize.py:50-69,164,
+        rows NOT flipped -> (fim, wim, depth, face_inv_map, faces_inv)."""
+        import torch
+        faces = faces_xyz.contiguous().clone()
+        B, F = faces.shape[:2]
+        dev = faces.device
+        fim = torch.full((B, image_size, image_size), -1, dtype=torch.int32, device=dev)
+        wim = torch.zeros((B, image_size, image_size, 3), dtype=torch.float32, device=dev)
+        depth = torch.full((B, image_size, image_size), float(far), dtype=torch.float32, device=dev)
+        finv_map = torch.zeros((B, image_size, image_size, 3, 3) if return_depth else (1,), dtype=torch.float32, device=dev)
+        faces_inv = torch.zeros_like(faces)
+        torch.cuda.synchronize()
+        rc = self._lib.jaf_ref_forward_face_index_map(
+            C.c_void_p(faces.data_ptr()), C.c_void_p(faces_inv.data_ptr()), C.c_void_p(fim.data_ptr()),
+            C.c_void_p(wim.data_ptr()), C.c_void_p(depth.data_ptr()), C.c_void_p(finv_map.data_ptr()),
+            B, F, image_size, C.c_float(near), C.c_float(far), int(bool(return_depth)))
+        if rc != 0:
+            raise RuntimeError(f"reference rasteriser failed: cuda error {-rc}")
+        return fim, wim, depth, finv_map, faces_inv
+
     def __call__(self, faces_xyz, image_size: int, near: float = 0.1, far: float = 100.0,
                  flip_rows: bool = True):
         """faces_xyz: CUDA float32 tensor [B,F,3,3].  Follows NR/rasterize.py:37-69,:161-169,:334-338."""

@@ -32,6 +32,14 @@ def _cu(a, dtype=None):
     return t if dtype is None else t.to(dtype)
 
 
+@pytest.fixture(autouse=True)
+def _inference_only():
+    """The path is forward-only and the drop-ins refuse tensors that require grad while autograd is on (the
+    reference runs it under torch.no_grad(), test/conv_pro_test.py:190)."""
+    with torch.no_grad():
+        yield
+
+
 def _bits(t):
     return t.detach().cpu().contiguous().view(torch.int32).numpy()
 
@@ -672,6 +680,262 @@ def test_convlstm_grouped_module_matches_per_part_lstms():
     cell.tensor_cores = False
     o_half_exact, _ = lstms[1](x[1])
     assert float((o_half - o_half_exact).abs().max()) <= 1e-4 and not torch.equal(o_half, o_tc)
+
+
+@pytest.mark.parametrize("K,S,with_rgb", [(4, 64, True), (2, 96, True), (8, 64, False), (1, 40, True)])
+def test_warp_fuse_from_poses_is_the_two_call_path_bit_for_bit(K, S, with_rgb):
+    """jaf_warp_fuse_from_poses composes the transfer flows per tile in shared memory: outputs, and the optional T / fim,
+    must equal jaf_cal_flow_multi + jaf_warp_fuse(fim) exactly (same pinned arithmetic, no flow round trip)."""
+    B, C = 3, 64
+    _, faces_idx = load_smpl_template()
+    f_idx = _cu(faces_idx)
+    cam, verts = synth.smpl_poses(B * (K + 1), seed=40 + K, device=DEV)
+    tc, tv = cam[:B].contiguous(), verts[:B].contiguous()
+    sc, sv = cam[B:].reshape(B, K, 3).contiguous(), verts[B:].reshape(B, K, -1, 3).contiguous()
+    rgb, feat = synth.reference_sets(B, K, C, S, S, seed=41, device=DEV)
+    logits = torch.randn(B, K, S, S, device=DEV)
+    mask = (torch.rand(B, 1, S, S, device=DEV) > 0.1).float()
+    T, fim, _ = ops.cal_flow_multi(sc, sv, tc, tv, f_idx, S, return_wim=False)
+    assert int((fim != -1).sum()) > 0
+    r2, f2 = ops.warp_fuse(T, rgb=rgb if with_rgb else None, feat=feat, logits=logits, fim=fim, tgt_mask=mask)
+    n0 = _lib.launch_count()
+    r1, f1, T1, fim1 = ops.warp_fuse_from_poses(sc, sv, tc, tv, f_idx, S, rgb=rgb if with_rgb else None, feat=feat,
+                                                logits=logits, tgt_mask=mask, return_flow=True)
+    assert _lib.launch_count() - n0 == 3, "scatter + huge + ONE fused warp kernel (no resolve / compose pass)"
+    assert "POSES=1" in _lib.last_kernel()
+    assert torch.equal(fim1, fim) and np.array_equal(_bits(T1), _bits(T))
+    assert np.array_equal(_bf16_bits(f1.permute(0, 2, 3, 1).contiguous()), _bf16_bits(f2.permute(0, 2, 3, 1).contiguous()))
+    if with_rgb:
+        assert np.array_equal(_bits(r1), _bits(r2))
+    # without the optional outputs nothing changes; shared reference sets / poses through ref_index; confidence blend
+    r3, f3 = ops.warp_fuse_from_poses(sc, sv, tc, tv, f_idx, S, rgb=rgb if with_rgb else None, feat=feat, logits=logits,
+                                      tgt_mask=mask)
+    assert torch.equal(f3, f1) and (not with_rgb or torch.equal(r3, r1))
+    if with_rgb:
+        ridx = torch.tensor([1, 1, 0], dtype=torch.int32, device=DEV)
+        fake, conf = torch.randn(B, 3, S, S, device=DEV), torch.rand(B, 1, S, S, device=DEV)
+        r4, f4 = ops.warp_fuse_from_poses(sc[:2].contiguous(), sv[:2].contiguous(), tc, tv, f_idx, S, rgb=rgb[:2].contiguous(),
+                                          feat=feat[:2], logits=logits, fake=fake, conf=conf, ref_index=ridx)
+        idx = ridx.long()
+        T5, fim5, _ = ops.cal_flow_multi(sc[idx].contiguous(), sv[idx].contiguous(), tc, tv, f_idx, S, return_wim=False)
+        r5, f5 = ops.warp_fuse(T5, rgb=rgb[:2].contiguous(), feat=feat[:2], logits=logits, fim=fim5, fake=fake, conf=conf,
+                               ref_index=ridx)
+        assert torch.equal(r4, r5) and torch.equal(f4, f5)
+
+
+def test_warp_fuse_from_poses_host_matches_the_device_path():
+    """e2e entry point of the pose-driven operation: poses / references / logits in HOST memory, fused RGB back to the
+    host, fused features either downloaded or left device-resident; chunked and pipelined inside the library."""
+    B, K, C, S = 7, 4, 64, 64
+    _, faces_idx = load_smpl_template()
+    cam, verts = synth.smpl_poses(B + 2 * K, seed=77)
+    tc, tv = cam[:B].contiguous(), verts[:B].contiguous()
+    sc, sv = cam[B:].reshape(2, K, 3).contiguous(), verts[B:].reshape(2, K, -1, 3).contiguous()
+    rgb, feat = synth.reference_sets(2, K, C, S, S, seed=78)
+    feat_dense = feat.permute(0, 1, 3, 4, 2).contiguous()
+    logits = torch.randn(B, K, S, S)
+    mask = (torch.rand(B, 1, S, S) > 0.1).float()
+    ridx = torch.tensor([0, 0, 0, 1, 1, 1, 1], dtype=torch.int32)
+    f_idx = torch.from_numpy(faces_idx)
+    pin = lambda t: t.contiguous().pin_memory()
+    d_rgb, d_feat = ops.warp_fuse_from_poses(sc.to(DEV), sv.to(DEV), tc.to(DEV), tv.to(DEV), f_idx.to(DEV), S, rgb=rgb.to(DEV),
+                                             feat=feat.to(DEV), logits=logits.to(DEV), tgt_mask=mask.to(DEV),
+                                             ref_index=ridx.to(DEV))
+    o_rgb, o_feat = ops.warp_fuse_from_poses_host(pin(sc), pin(sv), pin(tc), pin(tv), f_idx, S, rgb=pin(rgb), feat=pin(feat_dense),
+                                                  logits=pin(logits), tgt_mask=pin(mask), ref_index=ridx, frames_per_chunk=2)
+    assert torch.equal(o_rgb, d_rgb.cpu())
+    assert torch.equal(o_feat, d_feat.permute(0, 2, 3, 1).contiguous().cpu())
+    # device-resident feature output, pageable inputs, automatic chunking
+    dev_feat = torch.empty(B, S, S, C, dtype=torch.bfloat16, device=DEV)
+    o2, f2 = ops.warp_fuse_from_poses_host(sc, sv, tc, tv, f_idx, S, rgb=rgb, feat=feat_dense, logits=logits, tgt_mask=mask,
+                                           ref_index=ridx, out_feat_device=dev_feat)
+    assert f2 is dev_feat and torch.equal(o2, d_rgb.cpu())
+    assert torch.equal(dev_feat, d_feat.permute(0, 2, 3, 1).contiguous())
+    # one set of references / reference poses per target frame (no ref_index)
+    cam2, verts2 = synth.smpl_poses(3 * (K + 1), seed=79)
+    rgb3, feat3 = synth.reference_sets(3, K, C, S, S, seed=80)
+    a = dict(sc=cam2[3:].reshape(3, K, 3).contiguous(), sv=verts2[3:].reshape(3, K, -1, 3).contiguous(), tc=cam2[:3].contiguous(),
+             tv=verts2[:3].contiguous())
+    o3, f3 = ops.warp_fuse_from_poses_host(a["sc"], a["sv"], a["tc"], a["tv"], f_idx, S, rgb=rgb3,
+                                           feat=feat3.permute(0, 1, 3, 4, 2).contiguous(), frames_per_chunk=2)
+    d3, df3 = ops.warp_fuse_from_poses(a["sc"].to(DEV), a["sv"].to(DEV), a["tc"].to(DEV), a["tv"].to(DEV), f_idx.to(DEV), S,
+                                       rgb=rgb3.to(DEV), feat=feat3.to(DEV))
+    assert torch.equal(o3, d3.cpu()) and torch.equal(f3, df3.permute(0, 2, 3, 1).contiguous().cpu())
+    # argument validation of the host entry points (raw pointers feed pipelined memcpys)
+    with pytest.raises(RuntimeError):
+        ops.warp_fuse_host(torch.zeros(1, 1, 8, 8, 2), rgb=torch.zeros(1, 1, 3, 8, 8, dtype=torch.float64))
+    with pytest.raises(RuntimeError):
+        ops.warp_fuse_host(torch.zeros(1, 1, 8, 8, 2), rgb=torch.zeros(1, 1, 3, 8, 16)[..., ::2])
+    with pytest.raises(RuntimeError):
+        ops.warp_fuse_host(torch.zeros(2, 1, 8, 8, 2), rgb=torch.zeros(1, 1, 3, 8, 8))   # one set for two frames, no ref_index
+    with pytest.raises(RuntimeError):
+        ops.warp_fuse_host(torch.zeros(1, 1, 8, 8, 2), rgb=torch.zeros(1, 1, 3, 8, 8), logits=torch.zeros(1, 1, 8, 9))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_host_pipeline_runs_on_every_device_of_the_process():
+    """One pipeline per device (the reference wraps float_estimate in nn.DataParallel, test/conv_pro_test.py:140-141)."""
+    grid = synth.dense_flows(3, 2, 32, 32, seed=1)
+    rgb, _ = synth.reference_sets(3, 2, 0, 32, 32, seed=2)
+    outs = []
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            outs.append(ops.warp_fuse_host(grid, rgb=rgb)[0].clone())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_frame_graph_replays_the_batch_1_sequence_bit_identically():
+    """SURVEY §7 hard part 4: the per-frame loop of test/conv_pro_test.py:255-278 (cal_flow -> warp_image -> mask / blend)
+    at batch 1, captured once into a CUDA graph — same bits as the eager calls, one launch per replay."""
+    S, T = 64, 5
+    _, faces_idx = load_smpl_template()
+    f_idx = _cu(faces_idx)
+    cam, verts = synth.smpl_poses(T + 1, seed=31, device=DEV)
+    src = torch.randn(1, 1, 3, S, S, device=DEV)
+    fake, conf = torch.randn(T, 3, S, S, device=DEV), torch.rand(T, 1, S, S, device=DEV)
+    outs = [torch.empty(1, 3, S, S, device=DEV) for _ in range(T)]
+
+    def sequence():
+        for t in range(T):
+            flow, fim, _ = ops.cal_flow(cam[T:], verts[T:], cam[t:t + 1], verts[t:t + 1], f_idx, S, return_maps=True)
+            ops.warp_fuse(flow[:, None], rgb=src, fim=fim, fake=fake[t:t + 1], conf=conf[t:t + 1], out_rgb=outs[t])
+        return outs
+
+    eager = [o.clone() for o in sequence()]
+    for o in outs:
+        o.zero_()
+    g = ops.FrameGraph(sequence)
+    for o in outs:
+        o.zero_()
+    n0 = _lib.launch_count()
+    res = g.replay()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == n0, "a replay goes through cudaGraphLaunch, not through the library's launch paths"
+    for a, b in zip(eager, res):
+        assert torch.equal(a, b)
+    # new inputs are written into the captured tensors
+    verts[0].add_(0.01)
+    e2 = [o.clone() for o in sequence()]
+    g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(e2, outs)) and not torch.equal(e2[0], eager[0])
+
+
+def test_warp_fuse_from_poses_other_shapes_take_the_two_call_path():
+    B, K, C, S = 2, 2, 32, 48   # C = 32: not served by the fused kernel
+    _, faces_idx = load_smpl_template()
+    cam, verts = synth.smpl_poses(B * (K + 1), seed=7, device=DEV)
+    tc, tv = cam[:B].contiguous(), verts[:B].contiguous()
+    sc, sv = cam[B:].reshape(B, K, 3).contiguous(), verts[B:].reshape(B, K, -1, 3).contiguous()
+    rgb, feat = synth.reference_sets(B, K, C, S, S, seed=8, device=DEV)
+    r1, f1, T1, fim1 = ops.warp_fuse_from_poses(sc, sv, tc, tv, _cu(faces_idx), S, rgb=rgb, feat=feat, return_flow=True)
+    T, fim, _ = ops.cal_flow_multi(sc, sv, tc, tv, _cu(faces_idx), S, return_wim=False)
+    r2, f2 = ops.warp_fuse(T, rgb=rgb, feat=feat, fim=fim)
+    assert torch.equal(T1, T) and torch.equal(fim1, fim) and torch.equal(r1, r2) and torch.equal(f1, f2)
+
+
+def test_convlstm_cell_falls_back_when_the_tensor_core_plan_does_not_fit():
+    """Cin = Ch = 128 passes the channel-count rule of the grouped kernel but its row window + weight ring exceed the
+    SM's shared memory: the cell must take the exact-fp32 kernel instead of raising (the reference constructor accepts
+    any cell)."""
+    from jafpro_b200.convLSTM import ConvLSTMCell
+    assert not ops.convlstm_grouped_supported(1, 1, 128, 128, 16, 16)
+    assert ops.convlstm_grouped_supported(24, 1, 24, 24, 100, 100)
+    torch.manual_seed(3)
+    cell = ConvLSTMCell((16, 16), 128, 128, (3, 3), True).to(DEV)
+    x, h, c = (torch.randn(1, 128, 16, 16, device=DEV) for _ in range(3))
+    h2, c2 = cell(x, (h, c))
+    cc = F.conv2d(torch.cat((x, h), 1).double(), cell.conv.weight.double(), cell.conv.bias.double(), padding=1)
+    i, f, o, g = torch.split(cc, 128, dim=1)
+    c_r = torch.sigmoid(f) * c.double() + torch.sigmoid(i) * torch.tanh(g)
+    h_r = torch.sigmoid(o) * torch.tanh(c_r)
+    assert float((c2.double() - c_r).abs().max()) <= 1e-4 and float((h2.double() - h_r).abs().max()) <= 1e-4
+
+
+def test_drop_ins_refuse_autograd():
+    """Forward-only kernels: with autograd on, a parameter / input that requires grad raises instead of silently
+    returning outputs without a grad_fn."""
+    from jafpro_b200.convLSTM import ConvLSTMCell
+    cell = ConvLSTMCell((8, 8), 4, 4, (3, 3), True).to(DEV)
+    x, h, c = (torch.randn(1, 4, 8, 8, device=DEV) for _ in range(3))
+    cell(x, (h, c))  # no_grad (fixture): fine
+    with torch.enable_grad():
+        with pytest.raises(RuntimeError, match="forward-only"):
+            cell(x, (h, c))
+        g = torch.zeros(1, 1, 8, 8, 2, device=DEV)
+        img = torch.randn(1, 1, 3, 8, 8, device=DEV, requires_grad=True)
+        with pytest.raises(RuntimeError, match="forward-only"):
+            ops.warp_fuse(g, rgb=img)
+        with pytest.raises(RuntimeError, match="forward-only"):
+            ops.grid_sample_border(img[:, 0], g[:, 0])
+        for p in cell.parameters():
+            p.requires_grad_(False)
+        cell(x, (h, c))  # frozen parameters: allowed with autograd on
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_convlstm_kernels_on_a_second_device():
+    """Per-device state (dynamic shared-memory attribute, SM count) is set on every device a process uses
+    (nn.DataParallel, test/conv_pro_test.py:114-141)."""
+    from jafpro_b200.convLSTM import ConvLSTMCell, ConvLSTMCellTC
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        torch.manual_seed(0)
+        cell = ConvLSTMCell((50, 50), 24, 24, (3, 3), True).to(dev)
+        x, h, c = (torch.randn(2, 24, 50, 50, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(3))
+        h2, _ = cell(x, (h, c))
+        tc = ConvLSTMCellTC(64, 64, torch.randn(256, 128, 3, 3, generator=torch.Generator().manual_seed(9)).to(dev), None)
+        xb = torch.randn(1, 64, 64, 64, generator=torch.Generator().manual_seed(4)).to(dev).to(torch.bfloat16)
+        hb, cb = torch.zeros(1, 64, 64, 64, device=dev, dtype=torch.bfloat16), torch.zeros(1, 64, 64, 64, device=dev)
+        h3, _ = tc(xb, (hb, cb))
+        outs.append((h2.cpu(), h3.float().cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_forward_face_index_map_has_the_extensions_contract():
+    """jafpro_b200.cuda_rasterize.forward_face_index_map: the pybind signature of NR/cuda/rasterize_cuda.cpp:70-95 with
+    caller-prefilled outputs filled in place, rows not flipped — against the reference kernels compiled unmodified."""
+    import jafpro_b200.cuda_rasterize as rasterize_cuda
+    try:
+        ref = oracle.RefRaster()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libjaf_ref_raster.so not built")
+    _, faces_idx = load_smpl_template()
+    cam, verts = synth.smpl_poses(2, seed=11, device=DEV)
+    faces = ops.project_gather(cam, verts, _cu(faces_idx))
+    S, far = 128, 100.0
+    for return_depth in (0, 1):
+        rfim, rwim, rdepth, rfinv_map, rfaces_inv = ref.raw(faces, S, 0.1, far, return_depth=bool(return_depth))
+        B, Fn = faces.shape[:2]
+        fim = torch.full((B, S, S), -1, dtype=torch.int32, device=DEV)          # NR/rasterize.py:50-52
+        wim = torch.zeros((B, S, S, 3), device=DEV)
+        depth = torch.full((B, S, S), far, device=DEV)
+        finv_map = torch.zeros((B, S, S, 3, 3) if return_depth else (1,), device=DEV)
+        faces_inv = torch.zeros_like(faces)                                     # NR/rasterize.py:164
+        out = rasterize_cuda.forward_face_index_map(faces.clone(), fim, wim, depth, finv_map, faces_inv, S, 0.1, far,
+                                                    0, 0, return_depth)
+        assert out[0] is fim and out[1] is wim and out[2] is depth and out[3] is finv_map   # same handles (:650)
+        assert torch.equal(fim, rfim)
+        assert np.array_equal(_bits(wim), _bits(rwim)) and np.array_equal(_bits(depth), _bits(rdepth))
+        assert np.array_equal(_bits(faces_inv), _bits(rfaces_inv))
+        if return_depth:
+            assert np.array_equal(_bits(finv_map), _bits(rfinv_map))
+    # in-place contract: background pixels keep whatever the caller put there
+    fim2 = torch.full((B, S, S), -7, dtype=torch.int32, device=DEV)
+    wim2 = torch.full((B, S, S, 3), 0.25, device=DEV)
+    depth2 = torch.full((B, S, S), 42.0, device=DEV)
+    rasterize_cuda.forward_face_index_map(faces, fim2, wim2, depth2, torch.zeros(1, device=DEV), torch.zeros_like(faces),
+                                          S, 0.1, far, 0, 0, 0)
+    bg = rfim == -1
+    assert bool((fim2[bg] == -7).all()) and bool((wim2[bg] == 0.25).all()) and bool((depth2[bg] == 42.0).all())
+    assert torch.equal(fim2[~bg], rfim[~bg])
+    # CHECK_INPUT behaviour (rasterize_cuda.cpp:66-68)
+    with pytest.raises(RuntimeError):
+        rasterize_cuda.forward_face_index_map(faces.cpu(), fim, wim, depth, finv_map, faces_inv, S, 0.1, far, 0, 0, 0)
+    with pytest.raises(RuntimeError):
+        rasterize_cuda.forward_face_index_map(faces.transpose(0, 1), fim, wim, depth, finv_map, faces_inv, S, 0.1, far,
+                                              0, 0, 0)
 
 
 # ------------------------------------------------------------------ row F: per-reference visibility (get_vis_f2pts rule)

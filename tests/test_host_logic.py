@@ -109,3 +109,70 @@ def test_bind_to_gpu_cpus_is_a_no_op_without_nvml():
     if not torch.cuda.is_available():
         assert jdist.bind_to_gpu_cpus(0) is False
     assert os.sched_getaffinity(0) == before or torch.cuda.is_available()
+
+
+def test_hard_and_perm_flows_cover_the_frame():
+    g = synth.hard_flows(2, 3, 64, 64, seed=2, block=16, max_disp_px=16.0)
+    assert tuple(g.shape) == (2, 3, 64, 64, 2) and bool(torch.isfinite(g).all())
+    d = (g - synth.identity_grid(64, 64)[None, None]).abs() * 32          # pixels
+    assert 2.0 < float(d.mean()) < 40.0                                    # far from the identity, bounded
+    assert float((g.abs() > 1).any(-1).float().mean()) < 0.05              # (almost) every sample lands in the frame
+    # piecewise-affine: inside a cell the flow is exactly affine along x (second difference ~ 0)
+    row = g[0, 0, 5, :16, 0]
+    assert float((row[2:] - 2 * row[1:-1] + row[:-2]).abs().max()) < 1e-5
+    p = synth.perm_flows(1, 2, 16, 16, seed=3)
+    px = ((p[0, 0, ..., 0] * 16 + 16 - 1) / 2).round().long() + 16 * ((p[0, 0, ..., 1] * 16 + 16 - 1) / 2).round().long()
+    assert sorted(px.flatten().tolist()) == list(range(256))               # a permutation of the source pixels
+
+
+def test_bench_visible_pixel_bytes_never_exceed_dense_bytes():
+    import bench
+    K, S, C, B = 4, 256, 64, 10
+    dense = bench.wf_alg_bytes_dense(K, S, C) * B
+    full = bench.wf_alg_bytes_visible(K, S, C, B, B * S * S)
+    some = bench.wf_alg_bytes_visible(K, S, C, B, B * S * S // 8)
+    assert full == dense + B * S * S * 4        # every pixel visible: the dense bytes + the face-index map
+    assert some < dense / 3
+
+
+def test_drop_ins_refuse_autograd_before_touching_the_gpu():
+    """Forward-only contract (CPU part): a tensor / parameter that requires grad raises while autograd is enabled."""
+    import pytest
+    from jafpro_b200 import ops
+    from jafpro_b200.convLSTM import ConvLSTMCell
+    cell = ConvLSTMCell((4, 4), 2, 4, (3, 3), True)
+    x, h, c = torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, 4), torch.zeros(1, 4, 4, 4)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        cell(x, (h, c))
+    with pytest.raises(RuntimeError, match="forward-only"):
+        ops.warp_fuse(torch.zeros(1, 1, 4, 4, 2, requires_grad=True), rgb=torch.zeros(1, 1, 3, 4, 4))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA tensor"):   # without grad: the usual CPU-tensor error
+        ops.warp_fuse(torch.zeros(1, 1, 4, 4, 2, requires_grad=True), rgb=torch.zeros(1, 1, 3, 4, 4))
+
+
+def test_patched_reference_renderer_has_all_it_needs(monkeypatch):
+    """INTEGRATION.md §3 binds jafpro_b200.nmr.SMPLRenderer's methods onto the REFERENCE class, whose instances only
+    carry what src/nmr.py:104-177 sets (eye, faces, image_size, proj_func ...; no _eye_z).  The bound methods must work
+    with exactly that attribute set."""
+    import jafpro_b200.nmr as jnmr
+    from jafpro_b200 import ops
+
+    class RefRendererStub:                       # attribute set of the reference SMPLRenderer (src/nmr.py:104-177)
+        def __init__(self):
+            self.image_size = 256
+            self.faces = torch.zeros(5, 3, dtype=torch.int32)
+            self.eye = [0, 0, -(1. / np.tan(np.radians(30)) + 1)]
+            self.proj_func = jnmr.orthographic_proj_withz_idrot
+
+    RefRendererStub.render_fim_wim = lambda self, cam, v, faces=None: jnmr.SMPLRenderer.render_fim_wim(self, cam, v, faces)
+    RefRendererStub.cal_bc_transform = jnmr.SMPLRenderer.cal_bc_transform
+    seen = {}
+
+    def fake_render(cam, verts, faces_idx, image_size, eye_z=None, **kw):
+        seen.update(eye_z=eye_z, image_size=image_size, faces_dtype=faces_idx.dtype)
+        return None, None, None
+    monkeypatch.setattr(ops, "render_fim_wim", fake_render)
+    r = RefRendererStub()
+    r.render_fim_wim(torch.zeros(1, 3), torch.zeros(1, 7, 3))
+    assert seen["eye_z"] == float(np.float32(-(1. / np.tan(np.radians(30)) + 1)))
+    assert seen["image_size"] == 256 and seen["faces_dtype"] == torch.int32
