@@ -365,7 +365,9 @@ int run_pass1(const float* faces_xyz, const float* cam, const float* verts, cons
   if (F > 0) {
     k_raster_scatter<PROJECT><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(faces_xyz, cam, verts, fidx, B, V, F, is,
                                                                             eye_z, near_, far_, zb, faces_out, hq);
-    k_raster_huge<PROJECT><<<dim3(kHugeRun, kHugeChunks), 256, 0, st>>>(faces_xyz, cam, verts, fidx, V, F, is, eye_z,
+    // ~0.2 deferred faces per frame: a batch-1 call (the reference's per-frame loop) launches 4 x 32 CTAs, not 128 x 32
+    const int huge_x = B * 2 < kHugeRun ? (B * 2 < 4 ? 4 : B * 2) : kHugeRun;
+    k_raster_huge<PROJECT><<<dim3(huge_x, kHugeChunks), 256, 0, st>>>(faces_xyz, cam, verts, fidx, V, F, is, eye_z,
                                                                       near_, far_, zb, hq, 0);
     *launches += 2;
   }

@@ -396,6 +396,35 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
   }
 }
 
+// A tile without a single visible pixel: every output is the empty result (0, or the confidence blend with 0).
+// Vectorised fill by the whole CTA, no row loop, no flow / logit / reference read.
+template <int LPP, int TW>
+__device__ __forceinline__ void fill_empty_tile(const WFArgs& a, int b, int tx, int y_begin, int y_end, unsigned W, unsigned HW) {
+  const unsigned rows = (unsigned)(y_end - y_begin);
+  const unsigned wpx = min((unsigned)TW, W - (unsigned)tx * TW);  // tile width inside the frame
+  if (a.out_feat != nullptr) {
+    const unsigned per_row = wpx * LPP;                            // uint4 per tile row
+    uint4* o_base = reinterpret_cast<uint4*>(a.out_feat) + ((size_t)b * HW + (size_t)y_begin * W + (size_t)tx * TW) * LPP;
+    for (unsigned i = threadIdx.x; i < rows * per_row; i += 256) {
+      const unsigned ry = i / per_row, rx = i - ry * per_row;
+      st_stream_u128(o_base + (size_t)ry * W * LPP + rx, make_uint4(0u, 0u, 0u, 0u));
+    }
+  }
+  if (a.rgb != nullptr && a.out_rgb != nullptr) {
+    const bool blend = a.fake != nullptr && a.conf != nullptr;
+    for (unsigned i = threadIdx.x; i < 3u * rows * wpx; i += 256) {
+      const unsigned c = i / (rows * wpx), q = i - c * rows * wpx;
+      const unsigned pix = (unsigned)(y_begin + q / wpx) * W + (unsigned)tx * TW + q % wpx;
+      float ov = 0.f;
+      if (blend) {
+        const float wc = __ldg(a.conf + (size_t)b * HW + pix);
+        ov = __ldg(a.fake + ((size_t)b * 3 + c) * HW + pix) * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+      }
+      st_stream_f32(a.out_rgb + ((size_t)b * 3 + c) * HW + pix, ov);
+    }
+  }
+}
+
 // Two phases per CTA tile (a strip of TW = 8 * 32/LPP pixel columns x rows_per_cta rows):
 //
 // Phase A, features.  A group of LPP = C/8 lanes owns one pixel column; lane j owns channels 8j..8j+7 and
@@ -501,32 +530,23 @@ k_warp_fuse_nhwc(const WFArgs a) {
       any_vis |= fn >= 0;
       if (inside && a.fim_out != nullptr) a.fim_out[(size_t)b * HW + (unsigned)y * W + (unsigned)x] = fn;
     }
-    if (__syncthreads_or(any_vis) == 0) {
-      // nothing of the body in this tile: every output is the empty result — vectorised fill, no row loop
-      const unsigned rows = (unsigned)(y_end - y_begin);
-      const unsigned wpx = min((unsigned)TW, W - (unsigned)tx * TW);           // tile width inside the frame
-      if (a.out_feat != nullptr) {
-        const unsigned per_row = wpx * LPP;                                      // uint4 per tile row
-        uint4* o_base = reinterpret_cast<uint4*>(a.out_feat) + ((size_t)b * HW + (size_t)y_begin * W + (size_t)tx * TW) * LPP;
-        for (unsigned i = threadIdx.x; i < rows * per_row; i += 256) {
-          const unsigned ry = i / per_row, rx = i - ry * per_row;
-          st_stream_u128(o_base + (size_t)ry * W * LPP + rx, make_uint4(0u, 0u, 0u, 0u));
-        }
-      }
-      if (a.rgb != nullptr && a.out_rgb != nullptr) {
-        const bool blend = a.fake != nullptr && a.conf != nullptr;
-        for (unsigned i = threadIdx.x; i < 3u * rows * wpx; i += 256) {
-          const unsigned c = i / (rows * wpx), q = i - c * rows * wpx;
-          const unsigned pix = (unsigned)(y_begin + q / wpx) * W + (unsigned)tx * TW + q % wpx;
-          float ov = 0.f;
-          if (blend) {
-            const float wc = __ldg(a.conf + (size_t)b * HW + pix);
-            ov = __ldg(a.fake + ((size_t)b * 3 + c) * HW + pix) * wc + ov * (1.0f - wc);  // src/flow_net.py:98
-          }
-          st_stream_f32(a.out_rgb + ((size_t)b * 3 + c) * HW + pix, ov);
-        }
-      }
+    if (__syncthreads_or(any_vis) == 0) {  // nothing of the body in this tile
+      fill_empty_tile<LPP, TW>(a, b, tx, y_begin, y_end, W, HW);
       return;
+    }
+  } else if constexpr (SKIP) {
+    // pixel-level visibility from a face-index map: the same whole-tile early-out (80 % of the tiles of a DanceVideo
+    // frame hold no body pixel); the map's lines are read again, from L2, by the row loop of the other tiles
+    if (b_fim != nullptr) {  // uniform
+      int any_vis = 0;
+      for (unsigned p = threadIdx.x; p < tile_px; p += 256) {
+        const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
+        if (x < (int)W && y < y_end) any_vis |= __ldg(b_fim + (unsigned)y * W + (unsigned)x) != -1;
+      }
+      if (__syncthreads_or(any_vis) == 0) {
+        fill_empty_tile<LPP, TW>(a, b, tx, y_begin, y_end, W, HW);
+        return;
+      }
     }
   }
 
