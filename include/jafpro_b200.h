@@ -371,6 +371,20 @@ int jaf_transfer_texture(const uint8_t* tex, int tex_batched, int rows, int cols
 int jaf_iuv_part_stats(const uint8_t* iuv, int B, int H, int W, int32_t* counts, int64_t* sumx,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * SURVEY §8f rank 4  DensePose texture extraction
+ * replaces: get_texture(im, IUV, tex_size=32, final_size=200) (src/utils.py:232-255): per part 1..24 scatter the part's
+ *   pixels into a tex_size^2 map (row = int((255-V)*(tex_size-1)/255.), col = int(U*(tex_size-1)/255.), last pixel in
+ *   row-major order wins), cv2.resize(..., INTER_LINEAR) to final_size^2 on float64 data, [:, :, ::-1] / 255.
+ * im, iuv [B,H,W,3] u8 (im in cv2.imread's BGR order); parts out [B,24,final_size,final_size,3] f64 (zeros for a part
+ * without pixels); workspace: jaf_get_texture_workspace_bytes(B, tex_size).  The resize is the half-pixel-centre
+ * bilinear of cv::resize evaluated in fp64 with exactly rounded coefficients; OpenCV builds differ in how they round
+ * theirs (generic path: float; IPP path: double), so agreement with cv2 is <= 1e-12, not bitwise.
+ * --------------------------------------------------------------------------------- */
+size_t jaf_get_texture_workspace_bytes(int B, int tex_size);
+int jaf_get_texture(const uint8_t* im, const uint8_t* iuv, int B, int H, int W, int tex_size, int final_size,
+                    double* parts, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

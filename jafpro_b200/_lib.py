@@ -77,6 +77,8 @@ SIGNATURES = {
     "jaf_texture_parts_scatter": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "jaf_transfer_texture": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "jaf_iuv_part_stats": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "jaf_get_texture_workspace_bytes": (_sz, [_i, _i]),
+    "jaf_get_texture": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

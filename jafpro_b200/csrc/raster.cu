@@ -162,6 +162,111 @@ k_raster_scatter(const float* __restrict__ faces_xyz, const float* __restrict__ 
   }
 }
 
+// ---- pass 1, flattened: the same work as k_raster_scatter with the divergence taken out.
+// One thread per face leaves a warp waiting for its largest box (measured: 2,000 warp instructions per 32 faces for ~110
+// useful pixel tests) and half the lanes idle behind the back-face cull.  Here a CTA of 256 faces (a) culls and compacts
+// the front faces into shared memory, (b) runs the per-face setup on the compacted list (full warps), (c) takes a prefix
+// sum over the box sizes and (d) hands pixel test t of the CTA's concatenated boxes to thread t mod 256 (binary search for
+// the face it belongs to): every lane does one test per step whatever the boxes look like.  Same per-(face, pixel)
+// arithmetic and the same 64-bit atomicMin: identical z-buffer.
+struct FlatFace {
+  float f[9], inv[9];
+  int x_lo, y_lo, bw, b, fn;
+};
+
+template <bool PROJECT>
+__global__ void __launch_bounds__(256)
+k_raster_scatter_flat(const float* __restrict__ faces_xyz, const float* __restrict__ cam,
+                      const float* __restrict__ verts, const int* __restrict__ fidx, int B, int V, int F, int is,
+                      float eye_z, float near_, float far_, unsigned long long* __restrict__ zbuf,
+                      float* __restrict__ faces_out, HugeQueue* __restrict__ huge) {
+  __shared__ FlatFace s_face[256];
+  __shared__ int s_pref[257];   // exclusive prefix sum of the box sizes
+  __shared__ int s_wsum[8];
+  __shared__ unsigned s_n;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  // (a) load / project, cull, compact
+  if (i < (long)B * F) {
+    float f[9];
+    const int b = (int)(i / F), fn = (int)(i % F);
+    if (PROJECT) {
+      load_face_projected(cam, verts, fidx, b, fn, V, eye_z, f);
+      if (faces_out) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) faces_out[i * 9 + k] = f[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[k] = faces_xyz[i * 9 + k];
+    }
+    if (!face_is_back(f)) {
+      FlatFace& e = s_face[atomicAdd(&s_n, 1u)];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) e.f[k] = f[k];
+      e.b = b;
+      e.fn = fn;
+    }
+  }
+  __syncthreads();
+  const int n = (int)s_n;
+  // (b) per-face setup + box on the compacted faces; needle / degenerate faces with (near) full-image boxes are deferred
+  int npx = 0;
+  if ((int)threadIdx.x < n) {
+    FlatFace& e = s_face[threadIdx.x];
+    float f[9], inv[9], px[3], py[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = e.f[k];
+    const float den = face_setup(f, is, inv, px, py);
+    const Box bx = face_box(px, py, den, is);
+    const int bw = bx.x_hi - bx.x_lo + 1, bh = bx.y_hi - bx.y_lo + 1;
+    npx = (bw > 0 && bh > 0) ? bw * bh : 0;
+    if (npx > kHugeBox) {
+      const unsigned slot = atomicAdd(&huge->count, 1u);
+      if (slot < (unsigned)kHugeCap) {
+        HugeEntry en = {e.b, e.fn, bx.x_lo, bx.y_lo, bw, npx, 0, 0};
+        huge->e[slot] = en;
+        npx = 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) e.inv[k] = inv[k];
+    e.x_lo = bx.x_lo;
+    e.y_lo = bx.y_lo;
+    e.bw = bw;
+  }
+  // (c) block-wide exclusive prefix sum of npx
+  int incl = npx;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((int)lane >= d) incl += t;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+    if (w < (int)warp) base += s_wsum[w];
+  s_pref[threadIdx.x] = base + incl - npx;
+  if (threadIdx.x == 255) s_pref[256] = base + incl;
+  __syncthreads();
+  const int total = s_pref[256];
+  // (d) pixel test t -> thread t mod 256
+  for (int t = (int)threadIdx.x; t < total; t += 256) {
+    int lo = 0, hi = n - 1;  // largest j with s_pref[j] <= t (faces with empty boxes share their successor's offset)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_pref[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const FlatFace& e = s_face[lo];
+    const int local = t - s_pref[lo];
+    zbuf_try(zbuf, e.f, e.inv, e.b, e.fn, e.x_lo + local % e.bw, e.y_lo + local / e.bw, is, near_, far_);
+  }
+}
+
 // ---- pass 1b: the deferred huge boxes, each spread over kHugeChunks CTAs
 template <bool PROJECT>
 __global__ void __launch_bounds__(256)
@@ -363,8 +468,16 @@ int run_pass1(const float* faces_xyz, const float* cam, const float* verts, cons
   JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)B * is * is * 8, st));
   JAF_CUDA(cudaMemsetAsync(hq, 0, 64, st));
   if (F > 0) {
-    k_raster_scatter<PROJECT><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(faces_xyz, cam, verts, fidx, B, V, F, is,
-                                                                            eye_z, near_, far_, zb, faces_out, hq);
+    static const bool flat = [] {  // JAF_RASTER_FLAT=0: the one-thread-per-face scatter (A/B runs)
+      const char* e = getenv("JAF_RASTER_FLAT");
+      return e == nullptr || atoi(e) != 0;
+    }();
+    if (flat)
+      k_raster_scatter_flat<PROJECT><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(faces_xyz, cam, verts, fidx, B, V, F,
+                                                                                   is, eye_z, near_, far_, zb, faces_out, hq);
+    else
+      k_raster_scatter<PROJECT><<<jaf::ceil_div((long)B * F, 256), 256, 0, st>>>(faces_xyz, cam, verts, fidx, B, V, F, is,
+                                                                              eye_z, near_, far_, zb, faces_out, hq);
     // ~0.2 deferred faces per frame: a batch-1 call (the reference's per-frame loop) launches 4 x 32 CTAs, not 128 x 32
     const int huge_x = B * 2 < kHugeRun ? (B * 2 < 4 ? 4 : B * 2) : kHugeRun;
     k_raster_huge<PROJECT><<<dim3(huge_x, kHugeChunks), 256, 0, st>>>(faces_xyz, cam, verts, fidx, V, F, is, eye_z,

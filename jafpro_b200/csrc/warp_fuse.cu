@@ -405,6 +405,11 @@ __device__ __forceinline__ void fill_empty_tile(const WFArgs& a, int b, int tx, 
   if (a.out_feat != nullptr) {
     const unsigned per_row = wpx * LPP;                            // uint4 per tile row
     uint4* o_base = reinterpret_cast<uint4*>(a.out_feat) + ((size_t)b * HW + (size_t)y_begin * W + (size_t)tx * TW) * LPP;
+    if (TW * LPP == 256 && wpx == (unsigned)TW) {
+      // a full-width tile row is exactly 256 x 16 bytes: one store per thread and row, no index arithmetic
+      uint4* o_t = o_base + threadIdx.x;
+      for (unsigned ry = 0; ry < rows; ++ry, o_t += (size_t)W * LPP) st_stream_u128(o_t, make_uint4(0u, 0u, 0u, 0u));
+    } else
     for (unsigned i = threadIdx.x; i < rows * per_row; i += 256) {
       const unsigned ry = i / per_row, rx = i - ry * per_row;
       st_stream_u128(o_base + (size_t)ry * W * LPP + rx, make_uint4(0u, 0u, 0u, 0u));
@@ -483,57 +488,88 @@ k_warp_fuse_nhwc(const WFArgs a) {
   if constexpr (POSES) {
     using namespace jaf_raster;
     const int S = a.H;  // the target raster IS the output frame (H == W == raster size, checked by the host)
+    // [p, face] of the covered pixels of the tile, compacted: the expensive part below runs on full warps
+    int2* __restrict__ s_list = reinterpret_cast<int2*>(wf_smem + (((size_t)KT * tile_px * sizeof(float2) + tile_px + 15) & ~(size_t)15));
+    __shared__ unsigned s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    // ---- step 1: z-buffer keys -> coverage.  (fim is written here: it needs nothing else)
     int any_vis = 0;
     for (unsigned p = threadIdx.x; p < tile_px; p += 256) {
       const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
       int fn = -1;
-      float w[3] = {0.f, 0.f, 0.f};
-      const bool inside = x < (int)W && y < y_end;
-      if (inside) {
+      if (x < (int)W && y < y_end) {
         const int yi = S - 1 - y;  // NR/rasterize.py:334-338: output row y is raster row S-1-y
         const unsigned long long key = __ldg(a.zkeys + ((size_t)b * S + yi) * S + x);
         if (key != kEmptyKey) {
           fn = (int)(unsigned int)(key & 0xffffffffull);
-          float f[9], inv[9], px[3], py[3], zp;
-          load_face_projected(a.tgt_cam, a.tgt_verts, a.fidx, b, fn, a.V, a.eye_z, f);
-          face_setup(f, S, inv, px, py);
-          pixel_test(f, inv, x, yi, S, a.near_, a.far_, w, &zp);
+          s_list[atomicAdd(&s_cnt, 1u)] = make_int2((int)p, fn);
         }
-      }
-      int vi[3] = {0, 0, 0};
-      if (fn >= 0) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) vi[k] = __ldg(a.fidx + fn * 3 + k);
-      }
-#pragma unroll
-      for (int ks = 0; ks < KT; ++ks) {
-        float ftx = -2.0f, fty = -2.0f;  // src/nmr.py:627
-        if (fn >= 0) {
-          const size_t sb = r * KT + ks;
-          const float sc = __ldg(a.src_cam + sb * 3 + 0), ctx = __ldg(a.src_cam + sb * 3 + 1),
-                      cty = __ldg(a.src_cam + sb * 3 + 2);
-          float ax[3], ay[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float* pv = a.src_verts + (sb * a.V + vi[k]) * 3;
-            ax[k] = __fmul_rn(sc, __fadd_rn(__ldg(pv), ctx));
-            ay[k] = __fmul_rn(sc, __fadd_rn(__ldg(pv + 1), cty));  // -(-(s*(Y+ty))): raster flip then cal_flow.py:31
-          }
-          ftx = __fadd_rn(__fadd_rn(__fmul_rn(ax[0], w[0]), __fmul_rn(ax[1], w[1])), __fmul_rn(ax[2], w[2]));
-          fty = __fadd_rn(__fadd_rn(__fmul_rn(ay[0], w[0]), __fmul_rn(ay[1], w[1])), __fmul_rn(ay[2], w[2]));
-        }
-        s_T[(unsigned)ks * tile_px + p] = make_float2(ftx, fty);
-        if (inside && a.T_out != nullptr)
-          reinterpret_cast<float2*>(a.T_out)[((size_t)b * KT + ks) * HW + (unsigned)y * W + (unsigned)x] = make_float2(ftx, fty);
+        if (a.fim_out != nullptr) a.fim_out[(size_t)b * HW + (unsigned)y * W + (unsigned)x] = fn;
       }
       s_vis[p] = fn >= 0 ? 1 : 0;
       any_vis |= fn >= 0;
-      if (inside && a.fim_out != nullptr) a.fim_out[(size_t)b * HW + (unsigned)y * W + (unsigned)x] = fn;
     }
     if (__syncthreads_or(any_vis) == 0) {  // nothing of the body in this tile
+      if (a.T_out != nullptr) {            // the optional flow output still gets its sentinel (src/nmr.py:627)
+        for (unsigned p = threadIdx.x; p < tile_px; p += 256) {
+          const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
+          if (x < (int)W && y < y_end) {
+#pragma unroll
+            for (int ks = 0; ks < KT; ++ks)
+              reinterpret_cast<float2*>(a.T_out)[((size_t)b * KT + ks) * HW + (unsigned)y * W + (unsigned)x] = make_float2(-2.0f, -2.0f);
+          }
+        }
+      }
       fill_empty_tile<LPP, TW>(a, b, tx, y_begin, y_end, W, HW);
       return;
     }
+    // ---- step 2: uncovered pixels of a tile that does hold body pixels: the sentinel flow
+    for (unsigned p = threadIdx.x; p < tile_px; p += 256) {
+      if (s_vis[p]) continue;
+      const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
+      const bool inside = x < (int)W && y < y_end;
+#pragma unroll
+      for (int ks = 0; ks < KT; ++ks) {
+        s_T[(unsigned)ks * tile_px + p] = make_float2(-2.0f, -2.0f);
+        if (inside && a.T_out != nullptr)
+          reinterpret_cast<float2*>(a.T_out)[((size_t)b * KT + ks) * HW + (unsigned)y * W + (unsigned)x] = make_float2(-2.0f, -2.0f);
+      }
+    }
+    // ---- step 3: covered pixels: barycentric weights of the winning face (rows a5/a6), K composed flows (row a9)
+    const unsigned cnt = s_cnt;
+    for (unsigned i = threadIdx.x; i < cnt; i += 256) {
+      const int2 e = s_list[i];
+      const unsigned p = (unsigned)e.x;
+      const int fn = e.y;
+      const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
+      const int yi = S - 1 - y;
+      float f[9], inv[9], px[3], py[3], zp, w[3];
+      load_face_projected(a.tgt_cam, a.tgt_verts, a.fidx, b, fn, a.V, a.eye_z, f);
+      face_setup(f, S, inv, px, py);
+      pixel_test(f, inv, x, yi, S, a.near_, a.far_, w, &zp);
+      int vi[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) vi[k] = __ldg(a.fidx + fn * 3 + k);
+#pragma unroll
+      for (int ks = 0; ks < KT; ++ks) {
+        const size_t sb = r * KT + ks;
+        const float sc = __ldg(a.src_cam + sb * 3 + 0), ctx = __ldg(a.src_cam + sb * 3 + 1), cty = __ldg(a.src_cam + sb * 3 + 2);
+        float ax[3], ay[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float* pv = a.src_verts + (sb * a.V + vi[k]) * 3;
+          ax[k] = __fmul_rn(sc, __fadd_rn(__ldg(pv), ctx));
+          ay[k] = __fmul_rn(sc, __fadd_rn(__ldg(pv + 1), cty));  // -(-(s*(Y+ty))): raster flip then cal_flow.py:31
+        }
+        const float ftx = __fadd_rn(__fadd_rn(__fmul_rn(ax[0], w[0]), __fmul_rn(ax[1], w[1])), __fmul_rn(ax[2], w[2]));
+        const float fty = __fadd_rn(__fadd_rn(__fmul_rn(ay[0], w[0]), __fmul_rn(ay[1], w[1])), __fmul_rn(ay[2], w[2]));
+        s_T[(unsigned)ks * tile_px + p] = make_float2(ftx, fty);
+        if (a.T_out != nullptr)
+          reinterpret_cast<float2*>(a.T_out)[((size_t)b * KT + ks) * HW + (unsigned)y * W + (unsigned)x] = make_float2(ftx, fty);
+      }
+    }
+    __syncthreads();
   } else if constexpr (SKIP) {
     // pixel-level visibility from a face-index map: the same whole-tile early-out (80 % of the tiles of a DanceVideo
     // frame hold no body pixel); the map's lines are read again, from L2, by the row loop of the other tiles
@@ -1587,7 +1623,8 @@ extern "C" int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPos
   const long grid = (long)a.tiles_x * a.tiles_y * a.B;
   JAF_REQUIRE(grid <= 0x7fffffffL, "too many tiles");
   const size_t tile_px = (size_t)tw * a.rows_per_cta;
-  const size_t smem = (size_t)a.K * tile_px * sizeof(float2) + tile_px;
+  // K flows + coverage flag per tile pixel, and the compacted list of covered pixels
+  const size_t smem = (((size_t)a.K * tile_px * sizeof(float2) + tile_px + 15) & ~(size_t)15) + tile_px * sizeof(int2);
   JAF_REQUIRE(smem <= 48 * 1024, "tile does not fit shared memory (JAF_WF_ROWS_PER_CTA too large)");
   switch (a.K) {
     case 1: launch_poses_k<1>(a, (unsigned)grid, smem, st); break;

@@ -837,6 +837,20 @@ def transfer_texture(tex, iuv, im=None, rows: int = 4, cols: int = 6):
     return out
 
 
+def get_texture(im, iuv, tex_size: int = 32, final_size: int = 200):
+    """get_texture (src/utils.py:232-255) for a batch: im, iuv [B,H,W,3] uint8 -> parts [B,24,final,final,3] float64."""
+    im, iuv = _check(im, "im", torch.uint8), _check(iuv, "IUV", torch.uint8)
+    if iuv.dim() != 4 or iuv.shape[-1] != 3 or im.shape != iuv.shape:
+        raise RuntimeError("expected im and IUV [B,H,W,3]")
+    B, H, W, _ = iuv.shape
+    parts = torch.empty((B, 24, final_size, final_size, 3), dtype=torch.float64, device=iuv.device)
+    with _on(iuv.device):
+        ws = torch.empty(_lib.lib().jaf_get_texture_workspace_bytes(B, tex_size), dtype=torch.uint8, device=iuv.device)
+        _lib.check(_lib.lib().jaf_get_texture(_ptr(im), _ptr(iuv), B, H, W, int(tex_size), int(final_size), _ptr(parts),
+                                              _ptr(ws), _stream()), "get_texture")
+    return parts
+
+
 def iuv_part_stats(iuv):
     """iuv [B,H,W,3] uint8 -> (counts [B,32] int32, sumx [B,32] int64): pixels per part id and the sum of their x."""
     iuv = _check(iuv, "IUV", torch.uint8)

@@ -28,3 +28,25 @@ def TransferTexture(TextureIm, IUV, im=None):
     out = ops.transfer_texture(tex, iuv, bg)
     out = out[0] if single else out
     return out.cpu().numpy() if as_numpy else out
+
+
+def get_texture(im, IUV, tex_size=32, final_size=200):
+    """Same call as the reference (src/utils.py:232-255): im (H,W,3) uint8 as cv2.imread returns it, IUV (H,W,3) ->
+    list of 24 arrays (final_size, final_size, 3) float64 in [0, 1], channels reversed.  GPU tensors with a leading
+    batch dimension may be passed instead: the result is then one tensor [B,24,final_size,final_size,3] on the GPU."""
+    as_numpy = isinstance(IUV, np.ndarray)
+
+    def dev(a):
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        return a.to(device="cuda", dtype=torch.uint8).contiguous()
+
+    img, iuv = dev(im), dev(IUV)
+    single = iuv.dim() == 3
+    if single:
+        img, iuv = img[None], iuv[None]
+    parts = ops.get_texture(img, iuv, tex_size, final_size)
+    if as_numpy:
+        parts = parts.cpu().numpy()
+        return [parts[0, p] for p in range(24)] if single else parts
+    return parts[0] if single else parts

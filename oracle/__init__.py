@@ -424,3 +424,40 @@ def flow_warp_pair(feat_fwd, feat_bwd, base_grid, flow, align_corners: bool = Fa
         outs.append(grid_sample_border(np.asarray(feat, np.float32), np.ascontiguousarray(g.transpose(0, 2, 3, 1)),
                                        align_corners))
     return outs[0], outs[1]
+
+
+# --------------------------------------------------------------------------- §8f rank 4
+def get_texture(im, iuv, tex_size: int = 32, final_size: int = 200):
+    """src/utils.py:232-255 restated in numpy: scatter per part (np.where order, last write wins), bilinear resize with
+    half-pixel centres (cv::resize INTER_LINEAR geometry, coefficients as exactly rounded doubles), [:, :, ::-1] / 255.
+    im, iuv [H,W,3] uint8 -> [24, final, final, 3] float64."""
+    im, iuv = np.asarray(im, np.uint8), np.asarray(iuv, np.uint8)
+    sf = float(tex_size) - 1
+    U, V = iuv[:, :, 1], iuv[:, :, 2]
+
+    def coeffs(sn, dn):
+        d = np.arange(dn, dtype=np.int64)
+        f = ((2 * d + 1) * sn - dn).astype(np.float64) / np.float64(2 * dn)
+        s = np.floor(f).astype(np.int64)
+        f = f - s
+        lo, hi = s < 0, s >= sn - 1
+        s = np.where(lo, 0, np.where(hi, sn - 1, s))
+        f = np.where(lo | hi, 0.0, f)
+        return s, np.minimum(s + 1, sn - 1), f
+
+    x0, x1, ax = coeffs(tex_size, final_size)
+    out = np.zeros((24, final_size, final_size, 3), np.float64)
+    for part in range(1, 25):
+        x, y = np.where(iuv[:, :, 0] == part)
+        if len(x) == 0:
+            continue
+        a = np.zeros((tex_size, tex_size, 3))
+        rows = ((255 - V[x, y]) * sf / 255.).astype(int)
+        cols = (U[x, y] * sf / 255.).astype(int)
+        for c in range(3):
+            a[rows, cols, c] = im[x, y, c]
+        top = a[x0][:, x0] * (1.0 - ax)[None, :, None] + a[x0][:, x1] * ax[None, :, None]
+        bot = a[x1][:, x0] * (1.0 - ax)[None, :, None] + a[x1][:, x1] * ax[None, :, None]
+        r = top * (1.0 - ax)[:, None, None] + bot * ax[:, None, None]
+        out[part - 1] = r[:, :, ::-1] / 255.
+    return out

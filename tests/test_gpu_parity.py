@@ -1072,6 +1072,28 @@ def test_transfer_texture_and_compute_angle_match_the_reference_functions(golden
     assert float(compute_angle(iuv[2])) == float(d["angles"][2])
 
 
+def test_get_texture_matches_oracle_and_reference_fixture(golden_dir):
+    """DensePose texture extraction (src/utils.py:232-255): scatter kernel + fp64 bilinear resize, against the numpy
+    restatement (same operation order: <= 1e-13) and the reference function's own output (cv2.resize: <= 1e-12)."""
+    from jafpro_b200.utils import get_texture
+    from oracle.inputs import iuv_preprocessing_inputs
+    d = _load(golden_dir, "get_texture.npz")
+    iuv, _, im = iuv_preprocessing_inputs()
+    small = ops.get_texture(_cu(im[[0, 3]]), _cu(iuv[[0, 3]]), 8, 25)          # batched, stays on the GPU
+    assert tuple(small.shape) == (2, 24, 25, 25, 3) and small.dtype == torch.float64
+    assert float(np.abs(_np(small) - d["small"]).max()) <= 1e-12
+    for j, i in enumerate((0, 3)):
+        assert float(np.abs(_np(small[j]) - oracle.get_texture(im[i], iuv[i], 8, 25)).max()) <= 1e-13
+    parts = get_texture(im[1], iuv[1])                                          # the reference's numpy call form
+    assert isinstance(parts, list) and len(parts) == 24 and parts[0].shape == (200, 200, 3)
+    full = np.stack(parts)
+    assert float(np.abs(full[:, ::7, ::7] - d["full_sub"]).max()) <= 1e-12
+    assert float(np.abs(full - oracle.get_texture(im[1], iuv[1])).max()) <= 1e-13
+    # a frame without any body pixel: all-zero parts
+    z = ops.get_texture(_cu(im[:1]), torch.zeros(1, 256, 256, 3, dtype=torch.uint8, device=DEV))
+    assert float(z.abs().max()) == 0.0
+
+
 def test_example_video_pipeline_runs():
     """examples/video_pipeline.py chains every drop-in on one synthetic video; it must keep running end to end."""
     import subprocess

@@ -258,3 +258,17 @@ def test_flow_warp_pair_oracle_matches_torch_composition(h, w, H, W):
     t_b = F.grid_sample(torch.from_numpy(b), (torch.from_numpy(grid) - fs).permute(0, 2, 3, 1), padding_mode="border",
                         align_corners=False)
     assert float(np.abs(o_f - t_f.numpy()).max()) <= 1e-5 and float(np.abs(o_b - t_b.numpy()).max()) <= 1e-5
+
+
+def test_get_texture_oracle_matches_the_reference_function(golden_dir):
+    """Fixture = get_texture (src/utils.py:232-255) executed by tools/make_golden.py with the container's OpenCV.  The
+    restatement rounds the resize coefficients exactly; OpenCV builds differ in theirs, hence 1e-12 instead of bits."""
+    from oracle.inputs import iuv_preprocessing_inputs
+    d = np.load(os.path.join(golden_dir, "get_texture.npz"))
+    iuv, _, im = iuv_preprocessing_inputs()
+    for j, i in enumerate((0, 3)):
+        assert float(np.abs(oracle.get_texture(im[i], iuv[i], 8, 25) - d["small"][j]).max()) <= 1e-12
+    full = oracle.get_texture(im[1], iuv[1])
+    assert float(np.abs(full[:, ::7, ::7] - d["full_sub"]).max()) <= 1e-12
+    assert float(np.abs(full.sum(axis=(1, 2, 3)) - d["full_sum"]).max()) <= 1e-8
+    assert int((d["full_sum"] > 0).sum()) == 12 and float(full.min()) >= 0.0 and float(full.max()) <= 1.0

@@ -27,6 +27,7 @@ Fixtures (all small, float32 unless noted):
                        with forward hooks at the first scale.
   mask_blend.npz       src/flow_net.py Propagation3DFlowNet.forward (:87-99).
   texture_warp.npz     test/conv_pro_test.py texture_warp_pytorch (:41-74), the IUV texture lookup.
+  get_texture.npz      src/utils.py get_texture (:232-255) with this container's OpenCV (cv2.resize INTER_LINEAR on float64).
 """
 import os
 import sys
@@ -267,6 +268,25 @@ def iuv_preprocessing():
     print("iuv_preprocessing: angles", np.round(angles, 3))
 
 
+def get_texture_fixture():
+    """get_texture (src/utils.py:232-255), executed from the reference file itself with the real OpenCV of this container
+    (the function is lifted out with ast: importing src.utils needs matplotlib / tensorflow / moviepy)."""
+    import ast
+    import cv2
+    src = open(os.path.join(REF, "src", "utils.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_texture"][0]
+    ns = {"np": np, "cv2": cv2}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "utils.py", "exec"), ns)
+    sys.path.insert(0, ROOT)
+    from oracle.inputs import iuv_preprocessing_inputs
+    iuv, _, im = iuv_preprocessing_inputs()
+    small = np.stack([np.stack(ns["get_texture"](im[i], iuv[i], tex_size=8, final_size=25)) for i in (0, 3)])
+    full = np.stack(ns["get_texture"](im[1], iuv[1]))                      # defaults: 32 -> 200
+    np.savez_compressed(os.path.join(GOLD, "get_texture.npz"), small=small, full_sub=full[:, ::7, ::7].copy(),
+                        full_sum=full.sum(axis=(1, 2, 3)), cv2_version=np.array(cv2.__version__))
+    print("get_texture:", small.shape, full.shape, "non-empty parts", int((full.sum(axis=(1, 2, 3)) > 0).sum()))
+
+
 def smpl_template():
     """mapper.txt `v` lines (6890 T-pose vertices) + smpl_faces.npy -> jafpro_b200/data/."""
     vs = []
@@ -296,4 +316,5 @@ if __name__ == "__main__":
     softmax_fuse()
     mask_blend()
     texture_warp()
+    get_texture_fixture()   # before iuv_preprocessing(): that one registers stand-ins for modules it does not need
     iuv_preprocessing()
