@@ -1094,6 +1094,37 @@ def test_get_texture_matches_oracle_and_reference_fixture(golden_dir):
     assert float(z.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("num_inputs", [4, 3, 1])
+def test_shard_loader_equals_the_reference_dataset_item(golden_dir, tmp_path, num_inputs):
+    """jafpro_b200.shards.load_test_item on a packed shard == Fusion_dataset_smpl_test.__getitem__ (src/data.py:471-602)
+    on the same synthetic video stored in the reference's PNG + pickle layout: every returned array has the reference's
+    dtype, shape and bytes (fixture: SHA-256 digests written by tools/make_golden.py running the reference loader)."""
+    import hashlib
+    import json
+    from jafpro_b200 import shards
+    from oracle.inputs import synthetic_video
+    rec = json.load(open(os.path.join(golden_dir, "dataset_item.json")))
+    v = synthetic_video()
+    path = str(tmp_path / "v.jafshard")
+    shards.pack_video(path, v, "Synth_video_0_1", [f"frame_{t}.png" for t in range(v["img"].shape[0])])
+    src_data, tgt_data, data_255, smpl_data, vid_name, names, pro_frames = shards.load_test_item(
+        shards.VideoShard(path), num_inputs=num_inputs, output_mask=True, device=DEV)
+    pre = f"n{num_inputs}/"
+    assert [int(x) for x in pro_frames] == rec[pre + "pro_frames"]
+    assert vid_name == rec[pre + "vid_name"] and names == rec[pre + "img_names"]
+    flat = {"src_%d" % i: a for i, a in enumerate(src_data)}
+    flat.update({"tgt_%d" % i: a for i, a in enumerate(tgt_data)})
+    flat.update({"u255_%d" % i: a for i, a in enumerate(data_255)})
+    flat.update({"smpl_%d" % i: a for i, a in enumerate(smpl_data)})
+    assert sorted(pre + k for k in flat) == sorted(k for k in rec if k.startswith(pre) and k.split("/")[1][:3] in ("src", "tgt", "u25", "smp"))
+    for k, t in flat.items():
+        assert t.is_cuda
+        a = np.ascontiguousarray(t.cpu().numpy())
+        dtype, shape, digest = rec[pre + k]
+        assert str(a.dtype) == dtype and list(a.shape) == shape, (k, a.dtype, a.shape)
+        assert hashlib.sha256(a.tobytes()).hexdigest() == digest, k
+
+
 def test_example_video_pipeline_runs():
     """examples/video_pipeline.py chains every drop-in on one synthetic video; it must keep running end to end."""
     import subprocess

@@ -176,3 +176,59 @@ def test_patched_reference_renderer_has_all_it_needs(monkeypatch):
     r.render_fim_wim(torch.zeros(1, 3), torch.zeros(1, 7, 3))
     assert seen["eye_z"] == float(np.float32(-(1. / np.tan(np.radians(30)) + 1)))
     assert seen["image_size"] == 256 and seen["faces_dtype"] == torch.int32
+
+
+def test_video_shard_round_trip_and_directory_converter(tmp_path):
+    """The packed shard format (jafpro_b200/shards.py): raw arrays come back bit for bit, payloads are 256-byte aligned,
+    and converting the reference's on-disk layout (PNG files + pose_shape.pkl, src/utils.py:26-58) gives the same shard
+    content as packing the arrays directly."""
+    import pickle
+    import pytest
+    from jafpro_b200 import shards
+    from oracle.inputs import synthetic_video
+    v = synthetic_video(T=3, seed=2)
+    names = [f"frame_{t}.png" for t in range(3)]
+    path = str(tmp_path / "v.jafshard")
+    shards.pack_video(path, v, "Synth_video_0_1", names)
+    sh = shards.VideoShard(path)
+    assert sh.num_frames == 3 and sh.meta["vid_name"] == "Synth_video_0_1" and sh.meta["img_names"] == names
+    for k in list(shards.VIDEO_ARRAYS) + list(shards.SMPL_ARRAYS):
+        assert np.array_equal(sh[k], v[k]) and sh[k].dtype == v[k].dtype
+        assert (sh._base + sh._table[k]["offset"]) % shards.ALIGN == 0
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad"
+        bad.write_bytes(b"not a shard at all")
+        shards.VideoShard(str(bad))
+    cv2 = pytest.importorskip("cv2")
+    vid, msk = tmp_path / "data" / "Synth_video_0_1", tmp_path / "mask" / "Synth_video_0_1"
+    vid.mkdir(parents=True)
+    msk.mkdir(parents=True)
+    for t in range(3):
+        cv2.imwrite(str(vid / f"frame_{t}.png"), v["img"][t])
+        cv2.imwrite(str(vid / f"frame_{t}_IUV.png"), v["iuv"][t])
+        cv2.imwrite(str(vid / f"frame_{t}_text.png"), v["text"][t])
+        cv2.imwrite(str(vid / f"frame_{t}_mask.png"), v["text_mask"][t])
+        cv2.imwrite(str(msk / f"frame_{t}_mask.png"), v["real_mask"][t])
+    with open(tmp_path / "pose_shape.pkl", "wb") as fh:
+        pickle.dump({k: v[k] for k in shards.SMPL_ARRAYS}, fh)
+    path2 = str(tmp_path / "v2.jafshard")
+    shards.pack_video_dir(path2, str(vid), str(tmp_path / "pose_shape.pkl"), str(msk))
+    sh2 = shards.VideoShard(path2)
+    for k in list(shards.VIDEO_ARRAYS) + list(shards.SMPL_ARRAYS):
+        assert np.array_equal(sh2[k], v[k]), k
+    assert sh2.meta["img_names"] == names
+
+
+def test_reference_frame_selection_rule():
+    """select_reference_frames restates src/data.py:505-527 (argmax / argsort thirds / argmin, clipped to 0..30)."""
+    from jafpro_b200.shards import select_reference_frames
+    angle = np.array([10.0, -40.0, 65.0, 3.0, -5.0, 30.0, -60.0])
+    pro, fr = select_reference_frames(angle, 4)
+    order = np.argsort(angle)
+    assert list(pro) == [2, order[7 // 3], order[14 // 3], 6] and list(fr) == list(pro)
+    assert list(select_reference_frames(angle, 1)[0]) == [3]
+    assert list(select_reference_frames(angle, 3)[0]) == [2, order[3], 6]
+    assert len(select_reference_frames(angle, 5)[0]) == 5
+    big = np.arange(40, dtype=np.float64)
+    assert list(select_reference_frames(big, 1)[1]) == [0] and list(select_reference_frames(-big, 1)[1]) == [0]
+    assert list(select_reference_frames(big, 4)[1])[0] == 30     # np.clip(frames, 0, 30), src/data.py:527

@@ -27,6 +27,8 @@ Fixtures (all small, float32 unless noted):
                        with forward hooks at the first scale.
   mask_blend.npz       src/flow_net.py Propagation3DFlowNet.forward (:87-99).
   texture_warp.npz     test/conv_pro_test.py texture_warp_pytorch (:41-74), the IUV texture lookup.
+  dataset_item.json    src/data.py Fusion_dataset_smpl_test.__getitem__ (:471-602) on a synthetic video written in the
+                       reference's on-disk layout: shapes, dtypes and SHA-256 of every returned array.
   get_texture.npz      src/utils.py get_texture (:232-255) with this container's OpenCV (cv2.resize INTER_LINEAR on float64).
 """
 import os
@@ -287,6 +289,65 @@ def get_texture_fixture():
     print("get_texture:", small.shape, full.shape, "non-empty parts", int((full.sum(axis=(1, 2, 3)) > 0).sum()))
 
 
+def dataset_item():
+    """Fusion_dataset_smpl_test.__getitem__ (src/data.py:471-602) executed on a synthetic video written to disk in the
+    reference's own layout (PNG files + pose_shape.pkl); the fixture keeps shapes, dtypes and SHA-256 digests of every
+    returned array (the arrays themselves are ~100 MB)."""
+    import hashlib
+    import pickle
+    import tempfile
+    import cv2
+    sys.path.insert(0, ROOT)
+    from oracle.inputs import synthetic_video
+    for name in ("matplotlib", "matplotlib.pyplot", "tensorflow", "moviepy", "moviepy.editor"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__getattr__ = lambda attr: None
+            m.__path__ = []
+            sys.modules[name] = m
+    if not hasattr(np, "int"):
+        np.int = int  # the reference targets numpy < 1.24 (src/data.py:511)
+    from src.data import Fusion_dataset_smpl_test
+    v = synthetic_video()
+    T = v["img"].shape[0]
+    rec = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        vid = os.path.join(tmp, "data", "test", "Synth_video_0_1")
+        msk = os.path.join(tmp, "mask", "test", "Synth_video_0_1")
+        smp = os.path.join(tmp, "smpl", "test", "Synth_video_0_1")
+        for d_ in (vid, msk, smp, os.path.join(tmp, "log_result")):
+            os.makedirs(d_)
+        for t in range(T):
+            cv2.imwrite(os.path.join(vid, f"frame_{t}.png"), v["img"][t])
+            cv2.imwrite(os.path.join(vid, f"frame_{t}_IUV.png"), v["iuv"][t])
+            cv2.imwrite(os.path.join(vid, f"frame_{t}_text.png"), v["text"][t])
+            cv2.imwrite(os.path.join(vid, f"frame_{t}_mask.png"), v["text_mask"][t])
+            cv2.imwrite(os.path.join(msk, f"frame_{t}_mask.png"), v["real_mask"][t])
+        with open(os.path.join(smp, "pose_shape.pkl"), "wb") as fh:
+            pickle.dump({k: v[k] for k in ("cams", "pose", "shape", "vertices")}, fh)
+        for n_in in (4, 3, 1):
+            ds = object.__new__(Fusion_dataset_smpl_test)   # __init__ only parses options: set what __getitem__ reads
+            ds.vid_list = [vid]
+            ds.smpl_dir, ds.mask_dir = os.path.join(tmp, "smpl", "test"), os.path.join(tmp, "mask", "test")
+            ds.num_inputs, ds.output_mask = n_in, True
+            ds.log_file_dir = os.path.join(tmp, "log_result", "chosen_frame_train.txt")
+            src_data, tgt_data, data_255, smpl_data, vid_name, names, pro_frames = ds[0]
+            flat = {"src_%d" % i: a for i, a in enumerate(src_data)}
+            flat.update({"tgt_%d" % i: a for i, a in enumerate(tgt_data)})
+            flat.update({"u255_%d" % i: a for i, a in enumerate(data_255)})
+            flat.update({"smpl_%d" % i: a for i, a in enumerate(smpl_data)})
+            for k, a in flat.items():
+                a = np.ascontiguousarray(a)
+                rec[f"n{n_in}/{k}"] = [str(a.dtype), list(a.shape), hashlib.sha256(a.tobytes()).hexdigest()]
+            rec[f"n{n_in}/pro_frames"] = [int(x) for x in pro_frames]
+            rec[f"n{n_in}/vid_name"] = vid_name
+            rec[f"n{n_in}/img_names"] = list(names)
+    import json
+    with open(os.path.join(GOLD, "dataset_item.json"), "w") as fh:
+        json.dump(rec, fh, indent=1, sort_keys=True)
+    print("dataset_item:", {k: v_ for k, v_ in rec.items() if k.endswith("pro_frames")})
+
+
 def smpl_template():
     """mapper.txt `v` lines (6890 T-pose vertices) + smpl_faces.npy -> jafpro_b200/data/."""
     vs = []
@@ -317,4 +378,5 @@ if __name__ == "__main__":
     mask_blend()
     texture_warp()
     get_texture_fixture()   # before iuv_preprocessing(): that one registers stand-ins for modules it does not need
+    dataset_item()
     iuv_preprocessing()
