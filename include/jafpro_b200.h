@@ -310,6 +310,16 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
                               const float* bias, int G, int B, int Cin, int Ch, int H, int W,
                               float* h_out, float* c_out, void* stream);
 
+/* The recurrence over the K references in ONE call (src/convLSTM.py:131-134 `for t in range(seq_len)`; driven per
+ * pyramid level by src/networks.py:1346-1355): T grouped steps launched back to back, step t reading x_seq[:, :, t] and
+ * h_seq[:, :, t-1] in place and writing h_seq[:, :, t] — no per-step slicing, stacking or host round trip.
+ * x_seq [G,B,T,Cin,H,W]; h0, c0 [G,B,Ch,H,W] (zeros for the reference's default state); h_seq out [G,B,T,Ch,H,W]
+ * (= the batch_first layer output of ConvLSTM.forward, one per cell); c_last out [G,B,Ch,H,W]; c_tmp: workspace of the
+ * same size (unused for T == 1).  Results are bit-identical to T calls of jaf_convlstm_step_grouped. */
+int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const float* c0, const void* wpack,
+                                  const float* bias, int G, int B, int T, int Cin, int Ch, int H, int W,
+                                  float* h_seq, float* c_last, float* c_tmp, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * SURVEY §8f rank 3  bidirectional multi-scale feature warp of SpatioTempoCRN
  * replaces, per pyramid level (src/crn_model.py:457-566):

@@ -70,6 +70,7 @@ SIGNATURES = {
     "jaf_convlstm_grouped_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "jaf_convlstm_gpack_weight": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "jaf_convlstm_step_grouped": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "jaf_convlstm_sequence_grouped": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "jaf_flow_warp_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "jaf_texture_warp": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "jaf_texture_parts_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -187,12 +187,12 @@ class ConvLSTMGrouped(nn.Module):
         """input [G,B,T,Cin,H,W] (the batch_first stacks x*_con of networks.py:1340-1344, one per part)
         -> (outputs [G,B,T,Ch,H,W], (h_last, c_last)); zero initial state like ConvLSTM.forward."""
         G, B, T, _, H, W = input.shape
+        ops.forbid_grad(input, name="ConvLSTMGrouped input")
         if hidden_state is None:
             z = torch.zeros(G, B, self.hidden_dim, H, W, device=input.device)
-            hidden_state = (z, z.clone())
+            hidden_state = (z, z)
         h, c = hidden_state
-        outs = []
-        for t in range(T):
-            h, c = self.step(input[:, :, t], (h, c))
-            outs.append(h)
-        return torch.stack(outs, dim=2), (h, c)
+        # the whole recurrence in one C call: T launches back to back, steps read / write the sequence tensors in place
+        out, c_last = ops.convlstm_sequence_grouped(input.contiguous(), h.contiguous(), c.contiguous(), self.wpack, self.bias,
+                                                    self.input_dim, self.hidden_dim)
+        return out, (out[:, :, -1], c_last)

@@ -48,6 +48,9 @@ struct GArgs {
   float* h_out;
   float* c_out;
   int G, B, Cin, Ch, H, W;
+  // elements between consecutive (cell, batch) items of x, h and h_out: Cin*H*W / Ch*H*W for plain [G,B,C,H,W]
+  // tensors, T times that for the time-step slices of a [G,B,T,C,H,W] sequence (jaf_convlstm_sequence_grouped)
+  long xs, hs, hos;
   int nb, Wb;        // vertical bands per image and their width: each band is flattened on its own (short halo)
   int Wp, HpWp;      // padded row pitch of a band (Wb + 2), padded band size (H + 2) * Wp
   long Q;            // B * nb * HpWp flattened padded positions per group
@@ -290,8 +293,8 @@ k_convlstm_grouped(const GArgs a) {
           inside = x >= 0 && x < a.W && yp >= 1 && yp <= a.H;
           pix = (size_t)(yp - 1) * a.W + (size_t)x;
         }
-        const float* xb = a.x + ((size_t)g * a.B + b) * a.Cin * HW + pix;
-        const float* hb = a.h + ((size_t)g * a.B + b) * a.Ch * HW + pix;
+        const float* xb = a.x + ((size_t)g * a.B + b) * (size_t)a.xs + pix;
+        const float* hb = a.h + ((size_t)g * a.B + b) * (size_t)a.hs + pix;
         float v[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -328,7 +331,7 @@ k_convlstm_grouped(const GArgs a) {
         // two items per pass so that two sets of TMEM / global loads overlap.  The packed row order puts the four
         // gates of a block of four channels in 16 consecutive accumulator columns: one tcgen05.ld per item.
         float acc[2][16], cv[2][4];
-        size_t base[2];
+        size_t base[2], hbase[2];
         bool valid[2];
         int c0[2];
 #pragma unroll
@@ -336,6 +339,7 @@ k_convlstm_grouped(const GArgs a) {
           const int it = it0 + nsets * u;
           valid[u] = false;
           base[u] = 0;
+          hbase[u] = 0;
           c0[u] = 0;
           if (it < nitems) {  // warp-uniform
             const int m = it / nblk, jb = it - m * nblk;
@@ -350,6 +354,7 @@ k_convlstm_grouped(const GArgs a) {
               const int x = (un - b * a.nb) * a.Wb + xp - 1;
               ok = xp >= 1 && xp <= a.Wb && x < a.W && yp >= 1 && yp <= a.H;
               base[u] = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)x;
+              hbase[u] = ((size_t)g * a.B + b) * (size_t)a.hos + (size_t)(yp - 1) * a.W + (size_t)x;
             }
             valid[u] = ok;
             tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(m * a.Ns + jb * 16), acc[u]);
@@ -376,7 +381,7 @@ k_convlstm_grouped(const GArgs a) {
             const float cn = fg * cv[u][e] + ig * g_;  // src/convLSTM.py:53
             const float hn = og * tanh_f(cn);          // :54
             a.c_out[base[u] + (size_t)ch * HW] = cn;
-            a.h_out[base[u] + (size_t)ch * HW] = hn;
+            a.h_out[hbase[u] + (size_t)ch * HW] = hn;
           }
         }
       }
@@ -454,6 +459,8 @@ int jaf_convlstm_gpack_weight(const float* weight, int G, int Cin, int Ch, void*
 static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_count, GArgs& a, bool& half, size_t& smem,
                         long& grid) {
   a.G = G; a.B = B; a.Cin = Cin; a.Ch = Ch; a.H = H; a.W = W;
+  a.xs = (long)Cin * H * W;
+  a.hs = a.hos = (long)Ch * H * W;
   // vertical bands of ~25 columns: the halo of a flattened tile is two padded rows, so narrow bands keep it short
   // (W = 200: 2 x 28 rows instead of 2 x 203) at the price of two extra columns per band row
   static const int band_target = [] {
@@ -581,6 +588,48 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
   if (st != JAF_OK) return st;
   k_convlstm_grouped<<<(unsigned)grid, half ? kThreadsHalf : kThreads, smem, jaf::as_stream(stream)>>>(a);
   return jaf::finish_launch("k_convlstm_grouped");
+}
+
+int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const float* c0, const void* wpack, const float* bias,
+                                  int G, int B, int T, int Cin, int Ch, int H, int W, float* h_seq, float* c_last,
+                                  float* c_tmp, void* stream) {
+  JAF_REQUIRE(x_seq && h0 && c0 && wpack && h_seq && c_last, "null pointer");
+  JAF_REQUIRE(T == 1 || c_tmp, "c_tmp [G,B,Ch,H,W] is required for T > 1");
+  JAF_REQUIRE(G > 0 && B > 0 && T > 0 && H > 0 && W > 0, "bad sizes");
+  JAF_REQUIRE(grouped_shape_ok(Cin, Ch), "Ch must be a multiple of 4 and at most 128");
+  JAF_REQUIRE(((uintptr_t)wpack & 15) == 0, "wpack must be 16-byte aligned");
+  static jaf::PerDeviceOnce attr_once;
+  const int dev = jaf::current_device();
+  const int sm_count = jaf::sm_count(dev);
+  JAF_REQUIRE(sm_count > 0, "no current CUDA device");
+  if (!attr_once.done(dev)) {
+    JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_once.mark(dev);
+  }
+  GArgs a;
+  a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
+  bool half;
+  size_t smem;
+  long grid;
+  const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, half, smem, grid);
+  if (st != JAF_OK) return st;
+  const long HW = (long)H * W;
+  // the recurrence of src/convLSTM.py:131-134 in one call: step t reads x[:, :, t] and h[:, :, t-1] straight from the
+  // sequence tensors (strided views, no slicing copies) and writes h[:, :, t]; the cell state ping-pongs between two
+  // buffers so that the last step lands in c_last
+  float* cbuf[2] = {(T & 1) ? c_last : c_tmp, (T & 1) ? c_tmp : c_last};
+  for (int t = 0; t < T; ++t) {
+    a.x = x_seq + (long)t * Cin * HW;
+    a.xs = (long)T * Cin * HW;
+    a.h = t == 0 ? h0 : h_seq + (long)(t - 1) * Ch * HW;
+    a.hs = t == 0 ? (long)Ch * HW : (long)T * Ch * HW;
+    a.c = t == 0 ? c0 : cbuf[(t - 1) & 1];
+    a.h_out = h_seq + (long)t * Ch * HW;
+    a.hos = (long)T * Ch * HW;
+    a.c_out = cbuf[t & 1];
+    k_convlstm_grouped<<<(unsigned)grid, half ? kThreadsHalf : kThreads, smem, jaf::as_stream(stream)>>>(a);
+  }
+  return jaf::finish_launch("k_convlstm_grouped (sequence)", T);
 }
 
 }  // extern "C"

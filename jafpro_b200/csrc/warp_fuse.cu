@@ -1350,8 +1350,10 @@ const WFTune& wf_tune() {
     v.wide_minb = wf_env("JAF_WF_WIDE_MINB", 4);
     if (v.wide_minb < 3 || v.wide_minb > 5) v.wide_minb = 4;
     v.wide_minb8 = wf_env("JAF_WF_WIDE_MINB8", 3) == 4 ? 4 : 3;
-    v.wide_rows = wf_env("JAF_WF_WIDE_ROWS_PER_CTA", 16);
-    if (v.wide_rows < 1) v.wide_rows = 16;
+    // 64 x 8 tiles: measured (profiles/r02_bench_ab.jsonl) dense flows 0.710 of peak at 8 rows vs 0.715-0.726 at 16,
+    // piecewise-affine "hard" flows 0.712 vs 0.680, random permutation 0.369 vs 0.285: the small tile is the robust one
+    v.wide_rows = wf_env("JAF_WF_WIDE_ROWS_PER_CTA", 8);
+    if (v.wide_rows < 1) v.wide_rows = 8;
     // measured on B200 (profiles/r02_bench_ab.jsonl): merged 93.8 k frames/s dense / 83.7 k hard, two-pass 94.8 k / 89.9 k:
     // the scalar RGB taps issued from the 4-lane groups cost more L1 wavefronts and issue slots than the second pass
     v.rgb_merge = wf_env("JAF_WF_RGB_MERGE", 0);

@@ -677,6 +677,26 @@ def convlstm_step_grouped(x, h, c, wpack, bias, Cin: int, Ch: int):
     return h2, c2
 
 
+def convlstm_sequence_grouped(x_seq, h0, c0, wpack, bias, Cin: int, Ch: int):
+    """T recurrent steps of G cells in one C call (src/convLSTM.py:131-134): x_seq [G,B,T,Cin,H,W], h0, c0 [G,B,Ch,H,W]
+    -> (h_seq [G,B,T,Ch,H,W], c_last [G,B,Ch,H,W]).  Bit-identical to T calls of `convlstm_step_grouped`."""
+    x, h0, c0 = _check(x_seq, "x_seq", torch.float32), _check(h0, "h0", torch.float32), _check(c0, "c0", torch.float32)
+    if bias is not None:
+        bias = _check(bias, "bias", torch.float32)
+    if x.dim() != 6 or x.shape[3] != Cin or h0.shape != c0.shape or h0.dim() != 5 or h0.shape[2] != Ch or \
+            x.shape[:2] != h0.shape[:2] or x.shape[4:] != h0.shape[3:]:
+        raise RuntimeError("expected x_seq [G,B,T,Cin,H,W] and h0, c0 [G,B,Ch,H,W]")
+    G, B, T, _, H, W = x.shape
+    h_seq = torch.empty((G, B, T, Ch, H, W), dtype=torch.float32, device=x.device)
+    c_last = torch.empty_like(c0)
+    c_tmp = torch.empty_like(c0) if T > 1 else None
+    with _on(x.device):
+        _lib.check(_lib.lib().jaf_convlstm_sequence_grouped(_ptr(x), _ptr(h0), _ptr(c0), _ptr(wpack), _ptr(bias), G, B, T, Cin,
+                                                            Ch, H, W, _ptr(h_seq), _ptr(c_last), _ptr(c_tmp), _stream()),
+                   "convlstm_sequence_grouped")
+    return h_seq, c_last
+
+
 # ----------------------------------------------------------------------------- §8f rank 1
 def texture_warp(tex_parts, iuv, align_corners: bool = False):
     """IUV texture lookup (test/conv_pro_test.py:41-74).  tex_parts [P,3,Ht,Wt] f32, iuv [B,H,W,3] uint8

@@ -834,6 +834,32 @@ def test_warp_fuse_from_poses_other_shapes_take_the_two_call_path():
     assert torch.equal(T1, T) and torch.equal(fim1, fim) and torch.equal(r1, r2) and torch.equal(f1, f2)
 
 
+def test_convlstm_sequence_grouped_is_T_steps_in_one_call():
+    """The recurrence over the K references (src/convLSTM.py:131-134) as ONE C call: bit-identical to T single steps,
+    T launches, no slicing / stacking on the host."""
+    torch.manual_seed(11)
+    G, B, T, Cin, Ch, S = 3, 2, 4, 24, 24, 50
+    x = torch.randn(G, B, T, Cin, S, S, device=DEV)
+    h0, c0 = torch.randn(G, B, Ch, S, S, device=DEV), torch.randn(G, B, Ch, S, S, device=DEV)
+    wgt = torch.randn(G, 4 * Ch, Cin + Ch, 3, 3, device=DEV) * 0.05
+    bias = torch.randn(G, 4 * Ch, device=DEV)
+    wpack = ops.convlstm_gpack_weight(wgt, Cin, Ch)
+    n0 = _lib.launch_count()
+    h_seq, c_last = ops.convlstm_sequence_grouped(x, h0, c0, wpack, bias, Cin, Ch)
+    assert _lib.launch_count() - n0 == T
+    h, c = h0, c0
+    for t in range(T):
+        h, c = ops.convlstm_step_grouped(x[:, :, t].contiguous(), h, c, wpack, bias, Cin, Ch)
+        assert torch.equal(h_seq[:, :, t], h), t
+    assert torch.equal(c_last, c)
+    for T1 in (1, 3):   # odd lengths end in the other ping-pong buffer
+        hs, cl = ops.convlstm_sequence_grouped(x[:, :, :T1].contiguous(), h0, c0, wpack, None, Cin, Ch)
+        h, c = h0, c0
+        for t in range(T1):
+            h, c = ops.convlstm_step_grouped(x[:, :, t].contiguous(), h, c, wpack, None, Cin, Ch)
+        assert torch.equal(hs[:, :, -1], h) and torch.equal(cl, c)
+
+
 def test_convlstm_cell_falls_back_when_the_tensor_core_plan_does_not_fit():
     """Cin = Ch = 128 passes the channel-count rule of the grouped kernel but its row window + weight ring exceed the
     SM's shared memory: the cell must take the exact-fp32 kernel instead of raising (the reference constructor accepts
