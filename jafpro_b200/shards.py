@@ -164,10 +164,13 @@ def load_test_item(shard: VideoShard, num_inputs: int = 4, output_mask: bool = T
     if len(frames) != num_inputs:  # the reference fills `num_inputs` slots from `frames` (src/data.py:537-551)
         raise ValueError("num_inputs = 2 is not served by the reference's frame selection either")
     idx = torch.from_numpy(frames.astype(np.int64)).to(device)
-    norm = lambda t: (t.double() / 255.0 - 0.5) * 2
+    # numpy's `/ 255.0` is an IEEE division; torch's CUDA division by a Python scalar multiplies by the rounded
+    # reciprocal, so the divisor is a device tensor (tensor / tensor is a true division)
+    d255 = torch.full((), 255.0, dtype=torch.float64, device=device)
+    norm = lambda t: (t.double() / d255 - 0.5) * 2
     img, text, text_mask = shard.tensor("img", device), shard.tensor("text", device), shard.tensor("text_mask", device)
     src_iuv255, src_mask_u8 = iuv[idx], text_mask[idx]
-    src_data = [norm(img[idx]), norm(src_iuv255), norm(text[idx]), src_mask_u8.double() / 255.0]
+    src_data = [norm(img[idx]), norm(src_iuv255), norm(text[idx]), src_mask_u8.double() / d255]
     tgt_data = [norm(img), norm(iuv)]
     data_255 = [src_iuv255, iuv]
     if output_mask:
@@ -176,5 +179,5 @@ def load_test_item(shard: VideoShard, num_inputs: int = 4, output_mask: bool = T
         src_data.append(src_common_area)
         src_data.append(TransferTexture(ones, src_iuv255.contiguous()))        # src/data.py:570-572
     smpl_seq = torch.from_numpy(np.concatenate([shard["cams"], shard["pose"], shard["shape"]], axis=1)).to(device)
-    smpl_data = [smpl_seq, shard.tensor("real_mask", device).double() / 255.0, shard.tensor("vertices", device)]
+    smpl_data = [smpl_seq, shard.tensor("real_mask", device).double() / d255, shard.tensor("vertices", device)]
     return src_data, tgt_data, data_255, smpl_data, shard.meta["vid_name"], list(shard.meta["img_names"]), pro_frames
