@@ -1086,6 +1086,177 @@ k_warp_fuse_nhwc_wide2(const WFArgs a) {
   }
 }
 
+// 5..8 references in ROUNDS of four: the softmax terms of all K references are formed first (two logits per lane), but
+// the sample positions / bilinear weights of references 4..7 are built only after references 0..3 have been reduced
+// (their flow sample is prefetched one round ahead).  A lane then holds ONE reference's taps at a time, like the K <= 4
+// kernel, instead of two: 64 registers / 4 CTAs per SM instead of 80 / 3 for k_warp_fuse_nhwc_wide2.  Same arithmetic.
+template <int KT, int MINB, bool SKIP>
+__global__ void __launch_bounds__(256, MINB)
+k_warp_fuse_nhwc_wide2r(const WFArgs a) {
+  static_assert(KT <= 8, "each lane of the 4-lane pixel group prepares at most two references");
+  constexpr int LPP = 4, PPW = 8, TW = 64;
+  constexpr int NP = (KT + LPP - 1) / LPP;  // references prepared per lane: lane j takes k = j, j + 4
+  constexpr int KL = KT < LPP ? KT : LPP;   // lanes of a group that prepare slot 0
+  constexpr bool KPOW2 = (KL & (KL - 1)) == 0 && KT % KL == 0;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned PIXB = 128;  // bytes of one channels-last pixel (64 bf16)
+  int bid = blockIdx.x;
+  const int tx = bid % a.tiles_x;
+  bid /= a.tiles_x;
+  const int ty = bid % a.tiles_y;
+  const int b = bid / a.tiles_y;
+  const int y_begin = ty * a.rows_per_cta;
+  const int y_end = min(a.H, y_begin + a.rows_per_cta);
+  const unsigned W = (unsigned)a.W, Ws = (unsigned)a.Ws;
+  const unsigned HW = (unsigned)a.H * W, HWs = (unsigned)a.Hs * Ws;
+  const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
+  const size_t bK = (size_t)b * KT * HW;
+  const float* __restrict__ b_logit = a.logits ? a.logits + bK : nullptr;
+  const float* __restrict__ b_vis = a.vis ? a.vis + bK : nullptr;
+  const int* __restrict__ b_fim = (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr;
+  const float2* __restrict__ b_grid = reinterpret_cast<const float2*>(a.grid) + bK;
+  const float* __restrict__ b_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
+
+  // =========================== phase A: features ===========================
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPP, j = lane % LPP, gl = g * LPP;
+    const int x = tx * TW + warp * PPW + g;
+    const bool xin = x < (int)W;
+    const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + j * 32;
+    char* __restrict__ o_lane = reinterpret_cast<char*>(a.out_feat) + (size_t)b * HW * PIXB + j * 32;
+    const uint64_t keep = l2_policy_evict_last();
+    unsigned pix = (unsigned)y_begin * W + (unsigned)x;
+#pragma unroll 1
+    for (int y = y_begin; y < y_end; ++y, pix += W) {
+      // ---- softmax terms of all K references (slot n of lane j is reference kk = j % KL + n * LPP)
+      float lg[NP];
+      float vm = 1.f;
+      if (xin) {
+        if (b_fim) vm = (ld_stream_s32(b_fim + pix) != -1) ? 1.f : 0.f;
+        if (b_mask) vm *= ld_stream_f32(b_mask + pix);  // fused*mask == sum_k (alpha_k vis_k mask) warped_k
+      }
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const int kk = j % KL + n * LPP;
+        lg[n] = 0.f;
+        if (xin && kk < KT) {
+          if (b_logit) lg[n] = ld_stream_keep_f32(b_logit + ((unsigned)kk * HW + pix), keep);
+          m = fmaxf(m, lg[n]);
+        }
+      }
+      if constexpr (KPOW2) {
+#pragma unroll
+        for (int s = KL / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
+      } else {
+        float mm = m;
+#pragma unroll
+        for (int k = 0; k < KL; ++k) mm = fmaxf(mm, __shfl_sync(FULL, m, gl + k));
+        m = mm;
+      }
+      float e[NP], esum = 0.f;
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        e[n] = expf(lg[n] - m);
+        if (j % KL + n * LPP < KT) esum += e[n];
+      }
+      float ssum;
+      if constexpr (KPOW2) {
+        ssum = esum;
+#pragma unroll
+        for (int s = 1; s < KL; s <<= 1) ssum += __shfl_xor_sync(FULL, ssum, s);
+      } else {
+        ssum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KL; ++k) ssum += __shfl_sync(FULL, esum, gl + k);
+      }
+
+      float2 acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
+      // ---- rounds of four references; the next round's flow sample is in flight while this round is reduced
+      float2 gnext = make_float2(0.f, 0.f);
+      if (xin && j % KL < KT) gnext = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + ((unsigned)(j % KL) * HW + pix)), keep);
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const int kk = j % KL + n * LPP;
+        const bool act = xin && kk < KT;
+        const float2 gxy = gnext;
+        if (n + 1 < NP) {
+          const int kn = j % KL + (n + 1) * LPP;
+          gnext = make_float2(0.f, 0.f);
+          if (xin && kn < KT) gnext = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + ((unsigned)kn * HW + pix)), keep);
+        }
+        float vv = vm;
+        if (act && b_vis) vv = ld_stream_f32(b_vis + ((unsigned)kk * HW + pix)) * (b_mask ? vm : 1.f);
+        const float aw = act ? __fdividef(e[n], ssum) * vv : 0.f;  // alpha_k * vis_k * mask
+        HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
+        t.nw *= aw;
+        t.ne *= aw;
+        t.sw *= aw;
+        t.se *= aw;
+        const unsigned off = (aw != 0.f) ? (unsigned)t.off : 0u;
+        const bool any = SKIP ? (__ballot_sync(FULL, aw != 0.f) != 0u) : true;
+        if (any) {
+#pragma unroll
+          for (int kq = 0; kq < LPP; ++kq) {
+            const int k = n * LPP + kq;
+            if (k >= KT) break;
+            const int src = gl + kq;
+            const unsigned o0 = __shfl_sync(FULL, off, src) + (unsigned)k * HWs;
+            const char* p0 = f_lane + (size_t)o0 * PIXB;
+            const char* p1 = f_lane + (size_t)(o0 + Ws) * PIXB;
+            U256 q[4];
+            q[0] = ld_gather_u256(p0);
+            q[1] = ld_gather_u256(p0 + PIXB);
+            q[2] = ld_gather_u256(p1);
+            q[3] = ld_gather_u256(p1 + PIXB);
+            float wt[4];
+            wt[0] = __shfl_sync(FULL, t.nw, src);
+            wt[1] = __shfl_sync(FULL, t.ne, src);
+            wt[2] = __shfl_sync(FULL, t.sw, src);
+            wt[3] = __shfl_sync(FULL, t.se, src);
+#pragma unroll
+            for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+              const float2 w2 = make_float2(wt[tp], wt[tp]);
+              const uint32_t wd[8] = {q[tp].lo.x, q[tp].lo.y, q[tp].lo.z, q[tp].lo.w,
+                                      q[tp].hi.x, q[tp].hi.y, q[tp].hi.z, q[tp].hi.w};
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
+            }
+          }
+        }
+      }
+      if (xin) {
+        uint4 o0v, o1v;
+        o0v.x = pack_bf16x2(acc[0].x, acc[0].y); o0v.y = pack_bf16x2(acc[1].x, acc[1].y);
+        o0v.z = pack_bf16x2(acc[2].x, acc[2].y); o0v.w = pack_bf16x2(acc[3].x, acc[3].y);
+        o1v.x = pack_bf16x2(acc[4].x, acc[4].y); o1v.y = pack_bf16x2(acc[5].x, acc[5].y);
+        o1v.z = pack_bf16x2(acc[6].x, acc[6].y); o1v.w = pack_bf16x2(acc[7].x, acc[7].y);
+        uint4* op = reinterpret_cast<uint4*>(o_lane + (size_t)pix * PIXB);
+        st_stream_u128(op, o0v);
+        st_stream_u128(op + 1, o1v);
+      }
+    }
+  }
+
+  // =========================== phase B: RGB ===========================
+  if (a.rgb != nullptr && a.out_rgb != nullptr) {
+    const float* __restrict__ rgb_base = a.rgb + r * KT * 3 * (size_t)HWs;
+    const float* __restrict__ b_fake = (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr;
+    const float* __restrict__ b_conf = (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr;
+    float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
+    const int npx = TW * (y_end - y_begin);
+    for (int p = threadIdx.x; p < npx; p += 256) {
+      const int x = tx * TW + p % TW, y = y_begin + p / TW;
+      if (x >= (int)W) continue;
+      rgb_pixel<KT, SKIP, true>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
+    }
+  }
+}
+
 // RGB-only calls (no feature tensor): one thread per pixel, the same per-pixel code as phase B
 template <int KT, bool SKIP>
 __global__ void __launch_bounds__(256)
@@ -1336,6 +1507,8 @@ struct WFTune {
   int wide_rows;    // JAF_WF_WIDE_ROWS_PER_CTA: rows of a wide tile (64 columns)
   int rgb_merge;    // JAF_WF_RGB_MERGE: RGB planes inside the feature row loop (1) or as a second pass (0)
   int minb_poses;   // JAF_WF_MINB_POSES: CTAs/SM of the pose-driven kernel, K <= 4 (4 or 5)
+  int wide8_rounds; // JAF_WF_WIDE8_ROUNDS: K = 5..8 in rounds of four references (64 registers, 4 CTAs/SM) instead of
+                    // two references per lane (80 registers, 3 CTAs/SM)
 };
 const WFTune& wf_tune() {
   static const WFTune t = [] {
@@ -1358,6 +1531,7 @@ const WFTune& wf_tune() {
     // the scalar RGB taps issued from the 4-lane groups cost more L1 wavefronts and issue slots than the second pass
     v.rgb_merge = wf_env("JAF_WF_RGB_MERGE", 0);
     v.minb_poses = wf_env("JAF_WF_MINB_POSES", 5) == 4 ? 4 : 5;
+    v.wide8_rounds = wf_env("JAF_WF_WIDE8_ROUNDS", 1);
     return v;
   }();
   return t;
@@ -1443,6 +1617,12 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
         const int wide_minb = 4;  // K < 4 carries one occupancy variant
         JAF_W(1, 4) JAF_W(2, 4) JAF_W(3, 4)
       }
+#define JAF_W8R(KV) if (a.K == KV && tn.wide8_rounds != 0) { \
+        jaf::note_kernel("k_warp_fuse_nhwc_wide2r<K=%d,MINB=4,SKIP=%d>", KV, (int)skip); \
+        if (skip) k_warp_fuse_nhwc_wide2r<KV, 4, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide2r<KV, 4, false><<<(unsigned)gridw, 256, 0, st>>>(a); \
+        return true; }
+      JAF_W8R(5) JAF_W8R(6) JAF_W8R(7) JAF_W8R(8)
+#undef JAF_W8R
 #define JAF_W8(KV) if (a.K == KV) { \
         jaf::note_kernel("k_warp_fuse_nhwc_wide2<K=%d,MINB=%d,SKIP=%d>", KV, wide_minb8, (int)skip); \
         if (wide_minb8 == 4) { if (skip) k_warp_fuse_nhwc_wide2<KV, 4, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide2<KV, 4, false><<<(unsigned)gridw, 256, 0, st>>>(a); } \
@@ -1647,9 +1827,9 @@ extern "C" int jaf_tuning_info(char* buf, int n) {
   const int len = snprintf(tmp, sizeof(tmp),
                            "JAF_WF_WIDE=%d JAF_WF_WIDE_MINB=%d JAF_WF_WIDE_MINB8=%d JAF_WF_WIDE_ROWS_PER_CTA=%d "
                            "JAF_WF_RGB_MERGE=%d JAF_WF_MINB=%d JAF_WF_MINB_SKIP=%d JAF_WF_MINB_POSES=%d JAF_WF_ROWS=%d "
-                           "JAF_WF_ROWS_PER_CTA=%d",
+                           "JAF_WF_ROWS_PER_CTA=%d JAF_WF_WIDE8_ROUNDS=%d",
                            t.wide, t.wide_minb, t.wide_minb8, t.wide_rows, t.rgb_merge, t.minb_dense, t.minb_skip,
-                           t.minb_poses, t.rows, t.rows_per_cta);
+                           t.minb_poses, t.rows, t.rows_per_cta, t.wide8_rounds);
   if (buf != nullptr && n > 0) snprintf(buf, (size_t)n, "%s", tmp);
   return len + 1;
 }
