@@ -1086,6 +1086,7 @@ k_warp_fuse_nhwc_wide2(const WFArgs a) {
   }
 }
 
+// (A/B flavour, JAF_WF_WIDE8_ROUNDS=1; measured slower than k_warp_fuse_nhwc_wide2, see wf_tune().)
 // 5..8 references in ROUNDS of four: the softmax terms of all K references are formed first (two logits per lane), but
 // the sample positions / bilinear weights of references 4..7 are built only after references 0..3 have been reduced
 // (their flow sample is prefetched one round ahead).  A lane then holds ONE reference's taps at a time, like the K <= 4
@@ -1531,7 +1532,10 @@ const WFTune& wf_tune() {
     // the scalar RGB taps issued from the 4-lane groups cost more L1 wavefronts and issue slots than the second pass
     v.rgb_merge = wf_env("JAF_WF_RGB_MERGE", 0);
     v.minb_poses = wf_env("JAF_WF_MINB_POSES", 5) == 4 ? 4 : 5;
-    v.wide8_rounds = wf_env("JAF_WF_WIDE8_ROUNDS", 1);
+    // measured (profiles/r02_bench_ab.jsonl, 512^2 K=8): rounds of four 9.6 k frames/s (0.525) vs two references per lane
+    // 11.1 k (0.605): the second round's sample positions serialise behind the first round's reduction, which costs more
+    // than the fourth resident CTA brings
+    v.wide8_rounds = wf_env("JAF_WF_WIDE8_ROUNDS", 0);
     return v;
   }();
   return t;

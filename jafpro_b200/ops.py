@@ -571,7 +571,15 @@ def mask_blend(tsf_image, tgt_smpl_mask=None, fake_tgt=None, weight=None):
     tsf = _check(tsf_image, "tsf_image", torch.float32)
     mask = _check(tgt_smpl_mask, "tgt_smpl_mask", torch.float32)
     fake, w = _check(fake_tgt, "fake_tgt", torch.float32), _check(weight, "weight", torch.float32)
+    if tsf.dim() != 4:
+        raise RuntimeError("tsf_image must be [B, C, H, W]")
     B, Cc, H, W = tsf.shape
+    if mask is not None and (mask.dim() != 4 or mask.shape[0] != B or mask.shape[1] not in (1, Cc) or tuple(mask.shape[2:]) != (H, W)):
+        raise RuntimeError("tgt_smpl_mask must be [B, 1 or C, H, W]")
+    if (fake is None) != (w is None):
+        raise RuntimeError("fake_tgt and weight go together")
+    if w is not None and (tuple(w.shape) != (B, 1, H, W) or fake.shape != tsf.shape):
+        raise RuntimeError("weight must be [B, 1, H, W] and fake_tgt must have tsf_image's shape")
     masked = torch.empty_like(tsf)
     pred = torch.empty_like(tsf) if w is not None else None
     mc = 1 if mask is None else mask.shape[1]
@@ -631,7 +639,15 @@ def convlstm_step_tc(x, h, c, wpack, bias, Cin: int, Ch: int):
     (all channels-last dense) -> (h_next bf16, c_next f32)."""
     x, h = _check(x, "x", torch.bfloat16), _check(h, "h", torch.bfloat16)
     c, bias = _check(c, "c", torch.float32), _check(bias, "bias", torch.float32)
+    if x.dim() != 4 or x.shape[-1] != Cin:
+        raise RuntimeError("x must be [B, H, W, Cin] (channels-last bf16)")
     B, H, W, _ = x.shape
+    if tuple(h.shape) != (B, H, W, Ch) or tuple(c.shape) != (B, H, W, Ch):
+        raise RuntimeError("h and c must be [B, H, W, Ch]")
+    if bias is not None and tuple(bias.shape) != (4 * Ch,):
+        raise RuntimeError("bias must be [4*Ch]")
+    if wpack.numel() != _lib.lib().jaf_convlstm_wpack_bytes(Cin, Ch):
+        raise RuntimeError("wpack was packed for other channel counts")
     h2, c2 = torch.empty_like(h), torch.empty_like(c)
     with _on(x.device):
         _lib.check(_lib.lib().jaf_convlstm_step_tc(_ptr(x), _ptr(h), _ptr(c), _ptr(wpack), _ptr(bias), B, Cin, Ch, H,

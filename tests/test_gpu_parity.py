@@ -414,6 +414,26 @@ def test_full_size_properties_256_k4_c64():
     assert float(np.abs(_np(got[:1]) - o["out_rgb"]).max()) <= 1e-5
 
 
+@pytest.mark.parametrize("S,K,flow", [(256, 4, "dense"), (256, 4, "hard"), (512, 8, "dense"), (512, 8, "hard")])
+def test_full_size_frames_match_the_oracle(S, K, flow):
+    """BASELINE config 2 and config 5 frame shapes (256^2 K=4, 512^2 K=8; C=64) compared with the CPU oracle pixel for
+    pixel at FULL size — RGB planes and bf16 features — on smooth and on hard (piecewise-affine, +-64 px) flows."""
+    B, C = 1, 64
+    rgb, feat = synth.reference_sets(B, K, C, S, S, seed=S + K, device=DEV)
+    gen = synth.hard_flows if flow == "hard" else synth.dense_flows
+    grid = gen(B, K, S, S, seed=17, device=DEV)
+    logits = torch.randn(B, K, S, S, device=DEV)
+    mask = (torch.rand(B, 1, S, S, device=DEV) > 0.05).float()
+    out_rgb, out_feat = ops.warp_fuse(grid, rgb=rgb, feat=feat, logits=logits, tgt_mask=mask)
+    assert ("wide<K=4" if K == 4 else "wide2<K=8") in _lib.last_kernel()
+    fb = _bf16_bits(feat.permute(0, 1, 3, 4, 2).contiguous())
+    o = oracle.warp_fuse(_np(grid), rgb=_np(rgb), feat=fb, feat_layout="nhwc", feat_bf16=True, logits=_np(logits),
+                         tgt_mask=_np(mask))
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 2e-6
+    ok, frac = _bf16_close(_bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
+    assert ok and frac < 2e-3, frac
+
+
 def test_warp_fuse_host_pipeline_matches_device_path():
     """e2e entry point: host buffers in, host buffers out, chunked + pipelined inside the library."""
     B, K, C, H, W = 7, 4, 64, 64, 64
