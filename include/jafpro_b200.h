@@ -192,6 +192,12 @@ int jaf_warp_fuse(const JafWarpFuseParams* p);
  * jaf_cal_flow_multi + jaf_warp_fuse(fim).  Served shapes: jaf_warp_fuse_from_poses_supported() (C = 64 channels-last
  * bf16, K <= 8); others return JAF_ERR_UNSUPPORTED and take the two-call path.
  * --------------------------------------------------------------------------------- */
+/* The z-buffer keys live in the caller's workspace.  A caller that OWNS the workspace between calls can save the
+ * per-call clear (8 B per target pixel): JAF_POSES_LEAVE_CLEAN makes the fused kernel reset every key it consumed, and
+ * JAF_POSES_KEYS_CLEAN on the next call asserts that the first B*S*S keys are still empty (nothing else wrote the
+ * workspace since a LEAVE_CLEAN call of at least that size). */
+#define JAF_POSES_KEYS_CLEAN 1
+#define JAF_POSES_LEAVE_CLEAN 2
 typedef struct JafPoseFlowParams {
   const float* tgt_cam;      /* [B,3] (s,tx,ty)                                      */
   const float* tgt_verts;    /* [B,V,3]                                              */
@@ -200,7 +206,7 @@ typedef struct JafPoseFlowParams {
   const int32_t* faces_idx;  /* [F,3]                                                */
   int32_t V, F;
   float eye_z, near_, far_;  /* as jaf_render_fim_wim                                */
-  int32_t reserved;
+  int32_t flags;             /* JAF_POSES_* (0 = clear the keys on entry, leave them as they fall) */
   float* T;                  /* [B,K,S,S,2] out, or NULL (then it never exists)      */
   int32_t* fim;              /* [B,S,S] out, or NULL                                 */
   void* workspace;           /* jaf_raster_workspace_bytes(B, S)                     */

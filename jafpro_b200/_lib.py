@@ -33,7 +33,7 @@ class PoseFlowParams(C.Structure):
     """``JafPoseFlowParams`` (include/jafpro_b200.h)."""
     _fields_ = [
         ("tgt_cam", _vp), ("tgt_verts", _vp), ("src_cam", _vp), ("src_verts", _vp), ("faces_idx", _vp),
-        ("V", C.c_int32), ("F", C.c_int32), ("eye_z", _f), ("near_", _f), ("far_", _f), ("reserved", C.c_int32),
+        ("V", C.c_int32), ("F", C.c_int32), ("eye_z", _f), ("near_", _f), ("far_", _f), ("flags", C.c_int32),
         ("T", _vp), ("fim", _vp), ("workspace", _vp),
     ]
 

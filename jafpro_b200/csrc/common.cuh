@@ -33,8 +33,10 @@ struct PerDeviceOnce {
 };
 
 // raster.cu: z-buffer keys [B,S,S] u64 of the projected poses into `workspace` (jaf_raster_workspace_bytes)
+// keys_clean: the first B*is*is keys are already empty (the caller vouches for it): skip the clear
 int raster_keys_from_poses(const float* cam, const float* verts, const int* fidx, int B, int V, int F, int is,
-                           float eye_z, float near_, float far_, void* workspace, cudaStream_t st, int* launches);
+                           float eye_z, float near_, float far_, void* workspace, cudaStream_t st, int* launches,
+                           bool keys_clean = false);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }

@@ -35,6 +35,7 @@ struct DevBuf {
 struct Slot {
   DevBuf grid, logits, vis, fim, mask, fake, conf, rgb, feat, out_rgb, out_feat, warped;
   DevBuf tgt_cam, tgt_verts, raster_ws;  // pose-driven entry point
+  size_t clean_keys = 0;                 // leading z-buffer keys of raster_ws known to be empty (self-cleaning kernel)
   cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
 };
 
@@ -190,6 +191,7 @@ int run_pipeline(const JafWarpFuseParams* hp, const JafPoseFlowParams* hq, int f
     if (poses) {
       JAF_TRY(h2d(S.tgt_cam, hq->tgt_cam + (size_t)b0 * 3, (size_t)nb * 12, P.s_in));
       JAF_TRY(h2d(S.tgt_verts, hq->tgt_verts + (size_t)b0 * hq->V * 3, (size_t)nb * hq->V * 12, P.s_in));
+      if (jaf_raster_workspace_bytes(nb, hp->H) > S.raster_ws.cap) S.clean_keys = 0;  // a new buffer holds garbage
       JAF_TRY(S.raster_ws.ensure(jaf_raster_workspace_bytes(nb, hp->H)));
     } else {
       JAF_TRY(h2d(S.grid, hp->grid + (size_t)b0 * K * HW * 2, (size_t)nb * K * HW * 8, P.s_in));
@@ -272,7 +274,12 @@ int run_pipeline(const JafWarpFuseParams* hp, const JafPoseFlowParams* hq, int f
       dq.T = nullptr;
       dq.fim = nullptr;
       dq.workspace = S.raster_ws.p;
+      // the pipeline owns this workspace: the fused kernel leaves the keys empty and the next chunk skips the clear
+      const size_t need = (size_t)nb * hp->H * hp->H;
+      dq.flags = JAF_POSES_LEAVE_CLEAN | (S.clean_keys >= need ? JAF_POSES_KEYS_CLEAN : 0);
+      S.clean_keys = 0;  // not clean again until this call has succeeded
       JAF_TRY(jaf_warp_fuse_from_poses(&d, &dq));
+      S.clean_keys = need;
     } else {
       JAF_TRY(jaf_warp_fuse(&d));
     }

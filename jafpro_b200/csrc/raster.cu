@@ -166,8 +166,8 @@ k_raster_scatter(const float* __restrict__ faces_xyz, const float* __restrict__ 
 // One thread per face leaves a warp waiting for its largest box (measured: 2,000 warp instructions per 32 faces for ~110
 // useful pixel tests) and half the lanes idle behind the back-face cull.  Here a CTA of 256 faces (a) culls and compacts
 // the front faces into shared memory, (b) runs the per-face setup on the compacted list (full warps), (c) takes a prefix
-// sum over the box sizes and (d) hands pixel test t of the CTA's concatenated boxes to thread t mod 256 (binary search for
-// the face it belongs to): every lane does one test per step whatever the boxes look like.  Same per-(face, pixel)
+// sum over the box sizes and (d) splits the CTA's concatenated pixel tests into 256 equal contiguous shares, one per thread
+// (one binary search for the first face, then a linear walk): every lane does one test per step whatever the boxes look like.  Same per-(face, pixel)
 // arithmetic and the same 64-bit atomicMin: identical z-buffer.
 struct FlatFace {
   float f[9], inv[9];
@@ -254,16 +254,24 @@ k_raster_scatter_flat(const float* __restrict__ faces_xyz, const float* __restri
   if (threadIdx.x == 255) s_pref[256] = base + incl;
   __syncthreads();
   const int total = s_pref[256];
-  // (d) pixel test t -> thread t mod 256
-  for (int t = (int)threadIdx.x; t < total; t += 256) {
-    int lo = 0, hi = n - 1;  // largest j with s_pref[j] <= t (faces with empty boxes share their successor's offset)
+  // (d) the CTA's concatenated pixel tests, an equal contiguous share per thread: one binary search for the face of the
+  // first test, then a linear walk (faces with empty boxes are stepped over)
+  const int chunk = (total + 255) >> 8;
+  int t = (int)threadIdx.x * chunk;
+  const int t_end = min(total, t + chunk);
+  if (t < t_end) {
+    int lo = 0, hi = n - 1;  // largest j with s_pref[j] <= t
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (s_pref[mid] <= t) lo = mid; else hi = mid - 1;
     }
-    const FlatFace& e = s_face[lo];
-    const int local = t - s_pref[lo];
-    zbuf_try(zbuf, e.f, e.inv, e.b, e.fn, e.x_lo + local % e.bw, e.y_lo + local / e.bw, is, near_, far_);
+    int j = lo;
+    for (; t < t_end; ++t) {
+      while (t >= s_pref[j + 1]) ++j;
+      const FlatFace& e = s_face[j];
+      const int local = t - s_pref[j];
+      zbuf_try(zbuf, e.f, e.inv, e.b, e.fn, e.x_lo + local % e.bw, e.y_lo + local / e.bw, is, near_, far_);
+    }
   }
 }
 
@@ -450,7 +458,7 @@ size_t zbuf_bytes(int B, int is) { return ((size_t)B * is * is * sizeof(unsigned
 template <bool PROJECT>
 int run_pass1(const float* faces_xyz, const float* cam, const float* verts, const int* fidx, int B, int V, int F,
               int is, float eye_z, float near_, float far_, void* workspace, float* faces_out, cudaStream_t st,
-              int* launches) {
+              int* launches, bool keys_clean = false) {
   // debug knob; a __constant__ symbol exists once per device, so it is set on every device that rasterises
   static const char* margin_env = getenv("JAF_RASTER_MARGIN");
   if (margin_env != nullptr) {
@@ -465,7 +473,7 @@ int run_pass1(const float* faces_xyz, const float* cam, const float* verts, cons
   }
   auto* zb = static_cast<unsigned long long*>(workspace);
   auto* hq = reinterpret_cast<HugeQueue*>(static_cast<char*>(workspace) + zbuf_bytes(B, is));
-  JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)B * is * is * 8, st));
+  if (!keys_clean) JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)B * is * is * 8, st));
   JAF_CUDA(cudaMemsetAsync(hq, 0, 64, st));
   if (F > 0) {
     static const bool flat = [] {  // JAF_RASTER_FLAT=0: the one-thread-per-face scatter (A/B runs)
@@ -497,12 +505,14 @@ namespace jaf {
 // Pass 1 of the rasteriser on projected poses (z-buffer keys only), for callers that resolve the keys themselves
 // (the pose-driven fused warp kernel).
 int raster_keys_from_poses(const float* cam, const float* verts, const int* fidx, int B, int V, int F, int is,
-                           float eye_z, float near_, float far_, void* workspace, cudaStream_t st, int* launches) {
+                           float eye_z, float near_, float far_, void* workspace, cudaStream_t st, int* launches,
+                           bool keys_clean) {
   if (!check_raster_args(B, F, is) || V <= 0) {
     set_error("raster_keys_from_poses: bad sizes");
     return JAF_ERR_INVALID;
   }
-  return run_pass1<true>(nullptr, cam, verts, fidx, B, V, F, is, eye_z, near_, far_, workspace, nullptr, st, launches);
+  return run_pass1<true>(nullptr, cam, verts, fidx, B, V, F, is, eye_z, near_, far_, workspace, nullptr, st, launches,
+                         keys_clean);
 }
 }  // namespace jaf
 

@@ -84,7 +84,8 @@ struct WFArgs {
   float* warped_rgb;
   // pose-driven flavour (jaf_warp_fuse_from_poses): the transfer flows are composed per tile from the target pose's
   // z-buffer keys and the poses, in shared memory, instead of being read from `grid`
-  const unsigned long long* zkeys;  // [B,S,S] (raster rows, i.e. not flipped)
+  unsigned long long* zkeys;        // [B,S,S] (raster rows, i.e. not flipped)
+  int leave_clean;                  // reset every consumed key to "empty" (the caller skips the next clear)
   const float* tgt_cam;             // [B,3]
   const float* tgt_verts;           // [B,V,3]
   const float* src_cam;             // [R,K,3]
@@ -500,10 +501,12 @@ k_warp_fuse_nhwc(const WFArgs a) {
       int fn = -1;
       if (x < (int)W && y < y_end) {
         const int yi = S - 1 - y;  // NR/rasterize.py:334-338: output row y is raster row S-1-y
-        const unsigned long long key = __ldg(a.zkeys + ((size_t)b * S + yi) * S + x);
+        unsigned long long* kp = a.zkeys + ((size_t)b * S + yi) * S + x;
+        const unsigned long long key = *kp;
         if (key != kEmptyKey) {
           fn = (int)(unsigned int)(key & 0xffffffffull);
           s_list[atomicAdd(&s_cnt, 1u)] = make_int2((int)p, fn);
+          if (a.leave_clean) *kp = kEmptyKey;  // only covered pixels (~12 %) need the write
         }
         if (a.fim_out != nullptr) a.fim_out[(size_t)b * HW + (unsigned)y * W + (unsigned)x] = fn;
       }
@@ -1787,7 +1790,8 @@ extern "C" int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPos
   cudaStream_t st = jaf::as_stream(p->stream);
   int launches = 0;
   const int st1 = jaf::raster_keys_from_poses(q->tgt_cam, q->tgt_verts, q->faces_idx, p->B, q->V, q->F, p->H, q->eye_z,
-                                              q->near_, q->far_, q->workspace, st, &launches);
+                                              q->near_, q->far_, q->workspace, st, &launches,
+                                              (q->flags & JAF_POSES_KEYS_CLEAN) != 0);
   if (st1 != JAF_OK) return st1;
 
   WFArgs a = {};
@@ -1797,7 +1801,8 @@ extern "C" int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPos
   a.rgb = fuse_rgb ? p->rgb : nullptr; a.out_rgb = fuse_rgb ? p->out_rgb : nullptr;
   a.feat = p->feat; a.out_feat = p->out_feat; a.ref_index = p->ref_index; a.logits = p->logits;
   a.tgt_mask = p->tgt_mask; a.fake = p->fake; a.conf = p->conf;
-  a.zkeys = static_cast<const unsigned long long*>(q->workspace);
+  a.zkeys = static_cast<unsigned long long*>(q->workspace);
+  a.leave_clean = (q->flags & JAF_POSES_LEAVE_CLEAN) != 0;
   a.tgt_cam = q->tgt_cam; a.tgt_verts = q->tgt_verts; a.src_cam = q->src_cam; a.src_verts = q->src_verts;
   a.fidx = q->faces_idx; a.V = q->V; a.eye_z = q->eye_z; a.near_ = q->near_; a.far_ = q->far_;
   a.fim_out = q->fim; a.T_out = q->T;

@@ -86,13 +86,20 @@ class _on:
         return False
 
 
-def _workspace(dev, nbytes):
-    """Grow-only scratch per device (z-buffer keys).  Stream-ordered use only."""
+_clean_keys: dict = {}  # workspace key -> number of leading z-buffer keys known to be empty (self-cleaning fused kernel)
+
+
+def _workspace(dev, nbytes, keep_clean: bool = False):
+    """Grow-only scratch per device (z-buffer keys).  Stream-ordered use only.  The buffer never leaves this module, so
+    the pose-driven kernel's "keys left empty" protocol (JAF_POSES_*) can be tracked here: every other user dirties it."""
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
         _workspaces[key] = buf
+        _clean_keys[key] = 0
+    if not keep_clean:
+        _clean_keys[key] = 0
     return buf
 
 
@@ -356,10 +363,19 @@ def warp_fuse_from_poses(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx
     pq.eye_z, pq.near_, pq.far_ = eye_z, near, far
     pq.T, pq.fim = _ptr(T), _ptr(fim)
     with _on(dev):
-        ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, S))
+        ws = _workspace(dev, _lib.lib().jaf_raster_workspace_bytes(B, S), keep_clean=True)
+        wkey = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+        # the kernel leaves every key it consumed empty: the next call on this (module-owned) workspace skips the clear.
+        # Not during CUDA-graph capture: a replayed graph must not depend on what ran between the replays.
+        capturing = torch.cuda.is_current_stream_capturing()
+        clean = (not capturing) and _clean_keys.get(wkey, 0) >= B * S * S
+        pq.flags = 0 if capturing else (2 | (1 if clean else 0))  # JAF_POSES_LEAVE_CLEAN | JAF_POSES_KEYS_CLEAN
+        _clean_keys[wkey] = 0
         pq.workspace = ws.data_ptr()
         q.stream = _stream()
         _lib.check(_lib.lib().jaf_warp_fuse_from_poses(C.byref(q), C.byref(pq)), "warp_fuse_from_poses")
+        if not capturing:
+            _clean_keys[wkey] = B * S * S
     return (out_rgb, out_feat, T, fim) if return_flow else (out_rgb, out_feat)
 
 

@@ -841,6 +841,43 @@ def test_frame_graph_replays_the_batch_1_sequence_bit_identically():
     assert all(torch.equal(a, b) for a, b in zip(e2, outs)) and not torch.equal(e2[0], eager[0])
 
 
+def test_warp_fuse_from_poses_self_cleaning_workspace():
+    """The module-owned raster workspace is left empty by the fused kernel and the next call skips the 8 B / pixel clear
+    (JAF_POSES_LEAVE_CLEAN / JAF_POSES_KEYS_CLEAN); any other user of the workspace dirties it.  Every call in any order
+    must equal the two-call path."""
+    K, C, S = 4, 64, 64
+    _, faces_idx = load_smpl_template()
+    f_idx = _cu(faces_idx)
+    rgb, feat = synth.reference_sets(4, K, C, S, S, seed=5, device=DEV)
+
+    def case(B, seed):
+        cam, verts = synth.smpl_poses(B * (K + 1), seed=seed, device=DEV)
+        return (cam[B:].reshape(B, K, 3).contiguous(), verts[B:].reshape(B, K, -1, 3).contiguous(), cam[:B].contiguous(),
+                verts[:B].contiguous())
+
+    def check(B, seed):
+        sc, sv, tc, tv = case(B, seed)
+        r1, f1 = ops.warp_fuse_from_poses(sc, sv, tc, tv, f_idx, S, rgb=rgb[:B].contiguous(), feat=feat[:B])
+        T, fim, _ = ops.cal_flow_multi(sc, sv, tc, tv, f_idx, S, return_wim=False)   # dirties the shared workspace
+        r2, f2 = ops.warp_fuse(T, rgb=rgb[:B].contiguous(), feat=feat[:B], fim=fim)
+        assert torch.equal(r1, r2) and torch.equal(f1, f2), (B, seed)
+
+    check(4, 1)
+    sc, sv, tc, tv = case(4, 2)
+    a1 = ops.warp_fuse_from_poses(sc, sv, tc, tv, f_idx, S, rgb=rgb, feat=feat)       # clears, leaves clean
+    sc3, sv3, tc3, tv3 = case(2, 3)
+    b1 = ops.warp_fuse_from_poses(sc3, sv3, tc3, tv3, f_idx, S, rgb=rgb[:2].contiguous(), feat=feat[:2])   # skips the clear
+    a2 = ops.warp_fuse_from_poses(sc, sv, tc, tv, f_idx, S, rgb=rgb, feat=feat)       # skips the clear (4 frames were clean)
+    assert torch.equal(a1[0], a2[0]) and torch.equal(a1[1], a2[1])
+    ops.render_fim_wim(tc, tv, f_idx, S)                                               # another user: keys are dirty now
+    a3 = ops.warp_fuse_from_poses(sc, sv, tc, tv, f_idx, S, rgb=rgb, feat=feat)       # must clear again
+    assert torch.equal(a1[0], a3[0]) and torch.equal(a1[1], a3[1])
+    T, fim, _ = ops.cal_flow_multi(sc3, sv3, tc3, tv3, f_idx, S, return_wim=False)
+    b2 = ops.warp_fuse(T, rgb=rgb[:2].contiguous(), feat=feat[:2], fim=fim)
+    assert torch.equal(b1[0], b2[0]) and torch.equal(b1[1], b2[1])
+    check(3, 4)
+
+
 def test_warp_fuse_from_poses_other_shapes_take_the_two_call_path():
     B, K, C, S = 2, 2, 32, 48   # C = 32: not served by the fused kernel
     _, faces_idx = load_smpl_template()
