@@ -484,14 +484,17 @@ k_warp_fuse_nhwc(const WFArgs a) {
   // =========================== phase 0 (POSES): flows of the tile from the poses ===========================
   extern __shared__ __align__(16) unsigned char wf_smem[];
   const unsigned tile_px = (unsigned)TW * (unsigned)a.rows_per_cta;
+  // dynamic shared memory of the SKIP flavours: [K flows per tile pixel (POSES only)] [coverage flag per pixel]
+  // [compacted list of covered pixels: (tile-local index, face)]
+  constexpr size_t kFlowBytes = POSES ? (size_t)KT * sizeof(float2) : 0;
   float2* __restrict__ s_T = reinterpret_cast<float2*>(wf_smem);                       // [KT][tile_px]
-  unsigned char* __restrict__ s_vis = wf_smem + (size_t)KT * tile_px * sizeof(float2);  // [tile_px]
+  unsigned char* __restrict__ s_vis = wf_smem + kFlowBytes * tile_px;                  // [tile_px]
+  int2* __restrict__ s_list = reinterpret_cast<int2*>(wf_smem + ((kFlowBytes * tile_px + tile_px + 15) & ~(size_t)15));
+  __shared__ unsigned s_cnt;
   if constexpr (POSES) {
     using namespace jaf_raster;
     const int S = a.H;  // the target raster IS the output frame (H == W == raster size, checked by the host)
-    // [p, face] of the covered pixels of the tile, compacted: the expensive part below runs on full warps
-    int2* __restrict__ s_list = reinterpret_cast<int2*>(wf_smem + (((size_t)KT * tile_px * sizeof(float2) + tile_px + 15) & ~(size_t)15));
-    __shared__ unsigned s_cnt;
+    // [p, face] of the covered pixels of the tile are compacted into s_list: the expensive part below runs on full warps
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     // ---- step 1: z-buffer keys -> coverage.  (fim is written here: it needs nothing else)
@@ -577,15 +580,164 @@ k_warp_fuse_nhwc(const WFArgs a) {
     // pixel-level visibility from a face-index map: the same whole-tile early-out (80 % of the tiles of a DanceVideo
     // frame hold no body pixel); the map's lines are read again, from L2, by the row loop of the other tiles
     if (b_fim != nullptr) {  // uniform
+      if (threadIdx.x == 0) s_cnt = 0;
+      __syncthreads();
       int any_vis = 0;
       for (unsigned p = threadIdx.x; p < tile_px; p += 256) {
         const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
-        if (x < (int)W && y < y_end) any_vis |= __ldg(b_fim + (unsigned)y * W + (unsigned)x) != -1;
+        int fn = -1;
+        if (x < (int)W && y < y_end) fn = __ldg(b_fim + (unsigned)y * W + (unsigned)x);
+        if (fn != -1) s_list[atomicAdd(&s_cnt, 1u)] = make_int2((int)p, fn);
+        s_vis[p] = fn != -1 ? 1 : 0;
+        any_vis |= fn != -1;
       }
       if (__syncthreads_or(any_vis) == 0) {
         fill_empty_tile<LPP, TW>(a, b, tx, y_begin, y_end, W, HW);
         return;
       }
+    }
+  }
+
+  // =========================== list-driven phases (pixel-level visibility) ===========================
+  // With pixel-level visibility (pose-driven, or a face-index map) the tile's covered pixels are known as a compacted list:
+  // the feature and RGB phases walk that list instead of the rows, so an uncovered pixel inside a partly covered tile costs
+  // one zero store instead of K x 4 weight-0 gathers and their FMAs (the body covers 40-50 % of the tiles it touches).
+  // Per pixel the operations and their order are those of the row loop below: identical results.
+  if constexpr (SKIP) {
+    if (POSES || b_fim != nullptr) {  // uniform
+      const unsigned cnt = s_cnt;
+      constexpr int SL = (LPP >= 2 * KT) ? 2 : 1;        // list entries a lane group prepares per step (spare lanes: the 2nd)
+      constexpr int PER_WARP = (32 / LPP) * SL;
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int g = lane / LPP, j = lane % LPP, gl = g * LPP;
+      const int kk = j % KT;
+      const int slot = (SL == 2) ? min(j / KT, 1) : 0;
+      const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + j * 16;
+      uint4* __restrict__ o_lane = reinterpret_cast<uint4*>(a.out_feat) + (size_t)b * HW * LPP + j;
+      const uint64_t keep = l2_policy_evict_last();
+#pragma unroll 1
+      for (unsigned base = (unsigned)warp * PER_WARP; base < cnt; base += 8u * PER_WARP) {  // warp-uniform
+        const unsigned i = base + (unsigned)(g * SL + slot);
+        const bool pin = i < cnt;
+        const unsigned p = pin ? (unsigned)s_list[i].x : 0u;
+        const unsigned pix = (unsigned)(y_begin + (int)(p / TW)) * W + (unsigned)(tx * TW) + p % TW;
+        float lg = 0.f, v = 1.f;
+        float2 gxy = make_float2(0.f, 0.f);
+        if (pin) {
+          if constexpr (POSES) gxy = s_T[(unsigned)kk * tile_px + p];
+          else gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + ((unsigned)kk * HW + pix)), keep);
+          if (b_logit) lg = ld_stream_keep_f32(b_logit + ((unsigned)kk * HW + pix), keep);
+          if (b_mask) v *= ld_stream_f32(b_mask + pix);  // fused*mask == sum_k (alpha_k vis_k mask) warped_k
+        }
+        const int kb = gl + slot * KT;
+        float m = lg, ssum;
+        if constexpr (KPOW2) {
+#pragma unroll
+          for (int sft = KT / 2; sft > 0; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, sft));
+        } else {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) m = fmaxf(m, __shfl_sync(FULL, lg, (kb + k) & 31));
+        }
+        const float e = expf(lg - m);
+        if constexpr (KPOW2) {
+          ssum = e;
+#pragma unroll
+          for (int sft = 1; sft < KT; sft <<= 1) ssum += __shfl_xor_sync(FULL, ssum, sft);
+        } else {
+          ssum = 0.f;
+#pragma unroll
+          for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, (kb + k) & 31);
+        }
+        const float aw = pin ? __fdividef(e, ssum) * v : 0.f;  // alpha_k * vis_k * mask
+        HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
+        t.nw *= aw;
+        t.ne *= aw;
+        t.sw *= aw;
+        t.se *= aw;
+        const unsigned off = (aw != 0.f) ? (unsigned)t.off : 0u;
+#pragma unroll
+        for (int rs = 0; rs < SL; ++rs) {
+          const unsigned i_rs = base + (unsigned)(g * SL + rs);
+          const unsigned pix_rs = __shfl_sync(FULL, pix, gl + rs * KT);
+          float2 acc[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            const int src = gl + rs * KT + k;
+            const unsigned o0 = __shfl_sync(FULL, off, src) + (unsigned)k * HWs;
+            const uint4* p0 = reinterpret_cast<const uint4*>(f_lane + (size_t)o0 * PIXB);
+            const uint4* p1 = reinterpret_cast<const uint4*>(f_lane + (size_t)(o0 + Ws) * PIXB);
+            uint4 q[4];
+            q[0] = ld_gather_u128(p0);
+            q[1] = ld_gather_u128(p0 + LPP);
+            q[2] = ld_gather_u128(p1);
+            q[3] = ld_gather_u128(p1 + LPP);
+            float wt[4];
+            wt[0] = __shfl_sync(FULL, t.nw, src);
+            wt[1] = __shfl_sync(FULL, t.ne, src);
+            wt[2] = __shfl_sync(FULL, t.sw, src);
+            wt[3] = __shfl_sync(FULL, t.se, src);
+#pragma unroll
+            for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+              const float2 w2 = make_float2(wt[tp], wt[tp]);
+              const uint32_t wd[4] = {q[tp].x, q[tp].y, q[tp].z, q[tp].w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
+            }
+          }
+          if (i_rs < cnt) {
+            uint4 o;
+            o.x = pack_bf16x2(acc[0].x, acc[0].y);
+            o.y = pack_bf16x2(acc[1].x, acc[1].y);
+            o.z = pack_bf16x2(acc[2].x, acc[2].y);
+            o.w = pack_bf16x2(acc[3].x, acc[3].y);
+            st_stream_u128(o_lane + (size_t)pix_rs * LPP, o);
+          }
+        }
+      }
+      // uncovered pixels of the tile: the empty feature vector
+      {
+        uint4* __restrict__ o_b = reinterpret_cast<uint4*>(a.out_feat) + (size_t)b * HW * LPP;
+        for (unsigned q = threadIdx.x; q < tile_px * LPP; q += 256) {
+          const unsigned p = q / LPP, l = q % LPP;
+          const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
+          if (x < (int)W && y < y_end && !s_vis[p])
+            st_stream_u128(o_b + ((size_t)y * W + (unsigned)x) * LPP + l, make_uint4(0u, 0u, 0u, 0u));
+        }
+      }
+      // RGB planes: covered pixels from the list, the others empty (or the blend with the empty frame)
+      if (a.rgb != nullptr && a.out_rgb != nullptr) {
+        const float* __restrict__ rgb_base = a.rgb + r * KT * 3 * (size_t)HWs;
+        const float* __restrict__ b_fake = (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr;
+        const float* __restrict__ b_conf = (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr;
+        float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
+        for (unsigned i = threadIdx.x; i < cnt; i += 256) {
+          const unsigned p = (unsigned)s_list[i].x;
+          const unsigned pix = (unsigned)(y_begin + (int)(p / TW)) * W + (unsigned)(tx * TW) + p % TW;
+          if constexpr (POSES)
+            rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, pix, HW, HWs, Ws, s_T,
+                                tile_px, p, 1);
+          else
+            rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, pix, HW, HWs, Ws);
+        }
+        for (unsigned p = threadIdx.x; p < tile_px; p += 256) {
+          const int x = tx * TW + (int)(p % TW), y = y_begin + (int)(p / TW);
+          if (x >= (int)W || y >= y_end || s_vis[p]) continue;
+          const unsigned pix = (unsigned)y * W + (unsigned)x;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float ov = 0.f;
+            if (b_mask) ov *= (a.mask_c == 3) ? __ldg(b_mask + ((unsigned)c * HW + pix)) : __ldg(b_mask + pix);
+            if (b_fake) {
+              const float wc = __ldg(b_conf + pix);
+              ov = __ldg(b_fake + ((unsigned)c * HW + pix)) * wc + ov * (1.0f - wc);  // src/flow_net.py:98
+            }
+            st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
+          }
+        }
+      }
+      return;
     }
   }
 
@@ -1549,17 +1701,20 @@ template <int LPP, int KV>
 bool launch_nhwc_kc(const WFArgs& a, int grid, cudaStream_t st) {
   if constexpr (KV <= LPP) {
     const bool skip = a.vis != nullptr || a.fim != nullptr;
+    // coverage flags + compacted list of covered pixels of a tile (the SKIP flavours; see the kernel's smem layout)
+    const size_t tile_px = (size_t)(8 * (32 / LPP)) * a.rows_per_cta;
+    const size_t skip_smem = ((tile_px + 15) & ~(size_t)15) + tile_px * sizeof(int2);
     if constexpr (LPP == 8 && KV == 4) {  // the headline shape carries the occupancy variants
       const int mb = wf_minb(skip);
       const int rows = wf_tune().rows;
 #define JAF_V(MB, R) if (mb == MB && rows == R) { \
         jaf::note_kernel("k_warp_fuse_nhwc<LPP=8,K=4,MINB=%d,SKIP=%d,ROWS=%d>", MB, (int)skip, R); \
-        if (skip) k_warp_fuse_nhwc<8, 4, MB, true, R><<<grid, 256, 0, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, R><<<grid, 256, 0, st>>>(a); return true; }
+        if (skip) k_warp_fuse_nhwc<8, 4, MB, true, R><<<grid, 256, skip_smem, st>>>(a); else k_warp_fuse_nhwc<8, 4, MB, false, R><<<grid, 256, 0, st>>>(a); return true; }
       JAF_V(4, 1) JAF_V(5, 1) JAF_V(6, 1) JAF_V(3, 2) JAF_V(4, 2) JAF_V(5, 2) JAF_V(6, 2)
 #undef JAF_V
     }
     jaf::note_kernel("k_warp_fuse_nhwc<LPP=%d,K=%d,MINB=6,SKIP=%d,ROWS=1>", LPP, KV, (int)skip);
-    if (skip) k_warp_fuse_nhwc<LPP, KV, 6, true><<<grid, 256, 0, st>>>(a);
+    if (skip) k_warp_fuse_nhwc<LPP, KV, 6, true><<<grid, 256, skip_smem, st>>>(a);
     else k_warp_fuse_nhwc<LPP, KV, 6, false><<<grid, 256, 0, st>>>(a);
     return true;
   } else {
