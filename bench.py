@@ -630,17 +630,29 @@ def run_aux(args):
         cam, verts = synth.smpl_poses(31, seed=3 + rank, device=dev)
         outs = [torch.empty(1, 3, 256, 256, device=dev) for _ in range(30)]
 
-        def sequence():
+        src_cam1, src_verts1 = cam[30:].reshape(1, 1, 3).contiguous(), verts[30:].reshape(1, 1, -1, 3).contiguous()
+
+        def sequence_two_calls():   # the reference's call structure: cal_flow, then warp + mask + blend
             for t in range(30):
                 flow, fim, _ = ops.cal_flow(cam[30:], verts[30:], cam[t:t + 1], verts[t:t + 1], f_idx, 256, return_maps=True)
                 ops.warp_fuse(flow[:, None], rgb=rgb, fim=fim, fake=fake, conf=conf, out_rgb=outs[t])
             return outs
+
+        def sequence():             # the pose-driven call: raster pass + one fused kernel per frame
+            for t in range(30):
+                ops.warp_fuse_from_poses(src_cam1, src_verts1, cam[t:t + 1], verts[t:t + 1], f_idx, 256, rgb=rgb, fake=fake,
+                                         conf=conf, out_rgb=outs[t])
+            return outs
+        two_call_out = [o.clone() for o in sequence_two_calls()]
+        ts_2, p2, _ = timed(sequence_two_calls, steps, 3)
+        g2 = ops.FrameGraph(sequence_two_calls)
+        ts_g2, pg2, _ = timed(g2.replay, steps * 3, 3)
         eager_out = [o.clone() for o in sequence()]
         ts_e, pe, _ = timed(sequence, steps, 3)
         seq_launches = last_timed_launches // steps
         gseq = ops.FrameGraph(sequence)
         ts_g, pg, _ = timed(gseq.replay, steps * 3, 3)
-        seq_ok = all(torch.equal(a, b) for a, b in zip(eager_out, outs))
+        seq_ok = all(torch.equal(a, b) for a, b in zip(eager_out, outs)) and all(torch.equal(a, b) for a, b in zip(eager_out, two_call_out))
         src_img, g1 = rgb[:, 0].contiguous(), grid[:, 0].contiguous()
 
         def torch_ref():
@@ -663,9 +675,12 @@ def run_aux(args):
                                     "sequence_30_frames_from_poses": {
                                         "us_per_frame_eager": round(pe[len(pe) // 2] * 1e3 / 30, 2),
                                         "us_per_frame_cuda_graph": round(pg[len(pg) // 2] * 1e3 / 30, 2),
+                                        "us_per_frame_two_calls_eager": round(p2[len(p2) // 2] * 1e3 / 30, 2),
+                                        "us_per_frame_two_calls_cuda_graph": round(pg2[len(pg2) // 2] * 1e3 / 30, 2),
                                         "kernels_per_frame": seq_launches // 30, "graph_matches_eager_bits": bool(seq_ok),
-                                        "note": "per frame: jaf_cal_flow (memset + scatter + huge + resolve/compose) + jaf_warp_fuse "
-                                                "(warp x visibility, confidence blend), batch 1, 256^2"}},
+                                        "note": "per frame, batch 1, 256^2: jaf_warp_fuse_from_poses (one clear + scatter + deferred "
+                                                "boxes + ONE fused resolve / compose / warp / visibility / blend kernel); two_calls = "
+                                                "jaf_cal_flow + jaf_warp_fuse (5 kernels); all variants bit-identical"}},
                      "gpu_launches": int(launches_per_call * steps * 10), "clocks": clocks})
         line["e2e"] = e2e_c1(ops, rgb, grid, mask, fake, conf, steps)
         if world == 1 and not args.no_cpu and rank == 0:

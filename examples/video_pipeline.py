@@ -23,6 +23,7 @@ from jafpro_b200.texture import assemble_atlas, gather_parts, mask_common_area_,
 
 dev = torch.device("cuda")
 torch.manual_seed(0)
+torch.set_grad_enabled(False)  # inference, like test/conv_pro_test.py:190 — the drop-ins are forward-only and say so
 FRAMES, K, S, C = 30, 4, 256, 64
 
 # ---- per video: pick K reference frames by view angle (src/data.py:504: compute_angle on every IUV map)

@@ -187,10 +187,11 @@ int jaf_warp_fuse(const JafWarpFuseParams* p);
  * src/nmr.py:263-278, + cal_bc_transform, :617-659) followed by the row-F operation above with the default visibility
  * "the target pixel is on the body" (fim != -1, the -2 sentinel of src/nmr.py:627).
  * `p` as for jaf_warp_fuse except: grid, vis and fim are ignored (they are what this call computes), H == W = the raster
- * size, feat/out_feat are required.  Source poses are indexed like the reference sets (r = ref_index[b] | b).
+ * size.  Source poses are indexed like the reference sets (r = ref_index[b] | b).  RGB-only calls (feat == NULL: the
+ * reference's own per-frame warp_image + mask + blend chain) are served as well.
  * T / fim (optional outputs) are bit-identical to jaf_cal_flow_multi's; out_rgb / out_feat are bit-identical to
  * jaf_cal_flow_multi + jaf_warp_fuse(fim).  Served shapes: jaf_warp_fuse_from_poses_supported() (C = 64 channels-last
- * bf16, K <= 8); others return JAF_ERR_UNSUPPORTED and take the two-call path.
+ * bf16 or C = 0 = RGB only, K <= 8); others return JAF_ERR_UNSUPPORTED and take the two-call path.
  * --------------------------------------------------------------------------------- */
 /* The z-buffer keys live in the caller's workspace.  A caller that OWNS the workspace between calls can save the
  * per-call clear (8 B per target pixel): JAF_POSES_LEAVE_CLEAN makes the fused kernel reset every key it consumed, and

@@ -32,7 +32,7 @@ struct HugeEntry {
   int b, fn, x_lo, y_lo, bw, npx, pad0, pad1;
 };
 struct HugeQueue {
-  unsigned int count;
+  unsigned int count;  // entries pushed MINUS ONE: the queue is reset by the same 0xFF memset that clears the z-buffer
   unsigned int pad[15];
   HugeEntry e[kHugeCap];
 };
@@ -131,7 +131,7 @@ k_raster_scatter(const float* __restrict__ faces_xyz, const float* __restrict__ 
   const int npx = (bw > 0 && bh > 0) ? bw * bh : 0;
   bool big = npx > kBigBox;
   if (npx > kHugeBox) {  // needle-like or degenerate face with a (near) full-image box: defer
-    const unsigned slot = atomicAdd(&huge->count, 1u);
+    const unsigned slot = atomicAdd(&huge->count, 1u) + 1u;  // the counter starts at 0xFFFFFFFF
     if (slot < (unsigned)kHugeCap) {
       HugeEntry en = {b, fn, bx.x_lo, bx.y_lo, bw, npx, 0, 0};
       huge->e[slot] = en;
@@ -224,7 +224,7 @@ k_raster_scatter_flat(const float* __restrict__ faces_xyz, const float* __restri
     const int bw = bx.x_hi - bx.x_lo + 1, bh = bx.y_hi - bx.y_lo + 1;
     npx = (bw > 0 && bh > 0) ? bw * bh : 0;
     if (npx > kHugeBox) {
-      const unsigned slot = atomicAdd(&huge->count, 1u);
+      const unsigned slot = atomicAdd(&huge->count, 1u) + 1u;  // the counter starts at 0xFFFFFFFF
       if (slot < (unsigned)kHugeCap) {
         HugeEntry en = {e.b, e.fn, bx.x_lo, bx.y_lo, bw, npx, 0, 0};
         huge->e[slot] = en;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256)
 k_raster_huge(const float* __restrict__ faces_xyz, const float* __restrict__ cam, const float* __restrict__ verts,
               const int* __restrict__ fidx, int V, int F, int is, float eye_z, float near_, float far_,
               unsigned long long* __restrict__ zbuf, const HugeQueue* __restrict__ huge, int first) {
-  const unsigned count = min(huge->count, (unsigned)kHugeCap);
+  const unsigned count = min(huge->count + 1u, (unsigned)kHugeCap);
   for (unsigned e = (unsigned)first + blockIdx.x; e < count; e += gridDim.x) {
   const HugeEntry en = huge->e[e];
   float f[9], inv[9], px[3], py[3];
@@ -473,8 +473,11 @@ int run_pass1(const float* faces_xyz, const float* cam, const float* verts, cons
   }
   auto* zb = static_cast<unsigned long long*>(workspace);
   auto* hq = reinterpret_cast<HugeQueue*>(static_cast<char*>(workspace) + zbuf_bytes(B, is));
-  if (!keys_clean) JAF_CUDA(cudaMemsetAsync(zb, 0xff, (size_t)B * is * is * 8, st));
-  JAF_CUDA(cudaMemsetAsync(hq, 0, 64, st));
+  // one clear for the z-buffer keys (all ones = empty) and the queue header behind them (counter = -1)
+  if (!keys_clean)
+    JAF_CUDA(cudaMemsetAsync(zb, 0xff, zbuf_bytes(B, is) + 64, st));
+  else
+    JAF_CUDA(cudaMemsetAsync(hq, 0xff, 64, st));
   if (F > 0) {
     static const bool flat = [] {  // JAF_RASTER_FLAT=0: the one-thread-per-face scatter (A/B runs)
       const char* e = getenv("JAF_RASTER_FLAT");

@@ -615,8 +615,9 @@ k_warp_fuse_nhwc(const WFArgs a) {
       const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + j * 16;
       uint4* __restrict__ o_lane = reinterpret_cast<uint4*>(a.out_feat) + (size_t)b * HW * LPP + j;
       const uint64_t keep = l2_policy_evict_last();
+      const bool have_feat = a.feat != nullptr && a.out_feat != nullptr;  // RGB-only calls skip the feature part (uniform)
 #pragma unroll 1
-      for (unsigned base = (unsigned)warp * PER_WARP; base < cnt; base += 8u * PER_WARP) {  // warp-uniform
+      for (unsigned base = (unsigned)warp * PER_WARP; have_feat && base < cnt; base += 8u * PER_WARP) {  // warp-uniform
         const unsigned i = base + (unsigned)(g * SL + slot);
         const bool pin = i < cnt;
         const unsigned p = pin ? (unsigned)s_list[i].x : 0u;
@@ -697,7 +698,7 @@ k_warp_fuse_nhwc(const WFArgs a) {
         }
       }
       // uncovered pixels of the tile: the empty feature vector
-      {
+      if (have_feat) {
         uint4* __restrict__ o_b = reinterpret_cast<uint4*>(a.out_feat) + (size_t)b * HW * LPP;
         for (unsigned q = threadIdx.x; q < tile_px * LPP; q += 256) {
           const unsigned p = q / LPP, l = q % LPP;
@@ -1671,8 +1672,10 @@ const WFTune& wf_tune() {
     WFTune v;
     v.minb_dense = wf_env("JAF_WF_MINB", 4);
     if (v.minb_dense < 3 || v.minb_dense > 6) v.minb_dense = 4;
-    v.minb_skip = wf_env("JAF_WF_MINB_SKIP", 5);
-    if (v.minb_skip < 4 || v.minb_skip > 6) v.minb_skip = 5;
+    // visibility-skipping flavours, list-driven phases (round 2): 4 CTAs/SM (64 registers, no spills) beat 5 (48 registers,
+    // spills in the list loop): SMPL flows 291.6 k vs 281.4 k frames/s, from poses 208.5 k vs 201.9 k
+    v.minb_skip = wf_env("JAF_WF_MINB_SKIP", 4);
+    if (v.minb_skip < 4 || v.minb_skip > 6) v.minb_skip = 4;
     v.rows = wf_env("JAF_WF_ROWS", 2);
     v.rows_per_cta = wf_env("JAF_WF_ROWS_PER_CTA", 0);
     v.wide = wf_env("JAF_WF_WIDE", 1);
@@ -1686,7 +1689,7 @@ const WFTune& wf_tune() {
     // measured on B200 (profiles/r02_bench_ab.jsonl): merged 93.8 k frames/s dense / 83.7 k hard, two-pass 94.8 k / 89.9 k:
     // the scalar RGB taps issued from the 4-lane groups cost more L1 wavefronts and issue slots than the second pass
     v.rgb_merge = wf_env("JAF_WF_RGB_MERGE", 0);
-    v.minb_poses = wf_env("JAF_WF_MINB_POSES", 5) == 4 ? 4 : 5;
+    v.minb_poses = wf_env("JAF_WF_MINB_POSES", 4) == 5 ? 5 : 4;
     // measured (profiles/r02_bench_ab.jsonl, 512^2 K=8): rounds of four 9.6 k frames/s (0.525) vs two references per lane
     // 11.1 k (0.605): the second round's sample positions serialise behind the first round's reduction, which costs more
     // than the fourth resident CTA brings
@@ -1899,14 +1902,16 @@ namespace {
 
 // The pose-driven flavour exists for the headline layout: channels-last bf16 features with C = 64, K <= 8.
 bool poses_supported(int C, int K, int feat_layout, int feat_dtype) {
-  return C == 64 && K >= 1 && K <= 8 && feat_layout == JAF_LAYOUT_NHWC && feat_dtype == JAF_DTYPE_BF16;
+  if (K < 1 || K > 8) return false;
+  if (C == 0) return true;  // RGB planes only (the reference's per-frame warp_image call, test/conv_pro_test.py:255-278)
+  return C == 64 && feat_layout == JAF_LAYOUT_NHWC && feat_dtype == JAF_DTYPE_BF16;
 }
 
 template <int KV>
 void launch_poses_k(const WFArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
   constexpr int R = KV <= 4 ? 2 : 1;
   // JAF_WF_MINB_POSES: 5 CTAs/SM (48 registers, the row loop spills a few loop invariants) or 4 (64, no spills)
-  const int mb = (KV <= 4 && wf_tune().minb_poses == 5) ? 5 : 4;
+  const int mb = (KV <= 4 && wf_tune().minb_poses == 5) ? 5 : 4;  // default 4 (wf_tune)
   jaf::note_kernel("k_warp_fuse_nhwc<LPP=8,K=%d,MINB=%d,SKIP=1,ROWS=%d,POSES=1>", KV, mb, R);
   if constexpr (KV <= 4) {
     if (mb == 5) {
@@ -1929,14 +1934,15 @@ extern "C" int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPos
               "bad sizes (the output frame is the target raster: H == W)");
   JAF_REQUIRE(q->tgt_cam && q->tgt_verts && q->src_cam && q->src_verts && q->faces_idx && q->workspace, "null pose input");
   JAF_REQUIRE(q->V > 0 && q->F >= 0, "bad mesh sizes");
-  JAF_REQUIRE(p->feat && p->out_feat, "features are required");
+  const bool want_feat = p->feat && p->out_feat && p->C > 0;
+  JAF_REQUIRE(want_feat || (p->rgb && p->out_rgb), "nothing to do: need rgb+out_rgb and/or feat+out_feat");
   JAF_REQUIRE(!p->tgt_mask || p->mask_c == 1 || p->mask_c == 3, "mask_c must be 1 or 3");
   JAF_REQUIRE((long)p->Hs * p->Ws < (1L << 29) && (long)p->H * p->W < (1L << 29), "image too large");
   JAF_REQUIRE(!p->warped_rgb, "per-reference warps are not available in the pose-driven flavour");
   JAF_REQUIRE(!q->T || (reinterpret_cast<uintptr_t>(q->T) & 7u) == 0, "T must be 8-byte aligned");
-  JAF_REQUIRE((reinterpret_cast<uintptr_t>(p->feat) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p->out_feat) & 15u) == 0,
+  JAF_REQUIRE(!want_feat || ((reinterpret_cast<uintptr_t>(p->feat) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p->out_feat) & 15u) == 0),
               "features must be 16-byte aligned");
-  if (!poses_supported(p->C, p->K, p->feat_layout, p->feat_dtype)) {
+  if (!poses_supported(want_feat ? p->C : 0, p->K, p->feat_layout, p->feat_dtype)) {
     jaf::set_error("jaf_warp_fuse_from_poses: this build fuses C = 64 channels-last bf16 features with K <= 8; use "
                    "jaf_cal_flow_multi + jaf_warp_fuse for other shapes");
     return JAF_ERR_UNSUPPORTED;
@@ -1954,7 +1960,8 @@ extern "C" int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPos
   a.align_corners = p->align_corners; a.mask_c = p->tgt_mask ? p->mask_c : 1;
   const bool fuse_rgb = p->rgb && p->out_rgb;
   a.rgb = fuse_rgb ? p->rgb : nullptr; a.out_rgb = fuse_rgb ? p->out_rgb : nullptr;
-  a.feat = p->feat; a.out_feat = p->out_feat; a.ref_index = p->ref_index; a.logits = p->logits;
+  a.feat = want_feat ? p->feat : nullptr; a.out_feat = want_feat ? p->out_feat : nullptr;
+  a.ref_index = p->ref_index; a.logits = p->logits;
   a.tgt_mask = p->tgt_mask; a.fake = p->fake; a.conf = p->conf;
   a.zkeys = static_cast<unsigned long long*>(q->workspace);
   a.leave_clean = (q->flags & JAF_POSES_LEAVE_CLEAN) != 0;
@@ -1963,7 +1970,9 @@ extern "C" int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPos
   a.fim_out = q->fim; a.T_out = q->T;
   const int tw = 32;  // 8-lane groups: 4 pixel columns per warp, 8 warps
   a.tiles_x = (a.W + tw - 1) / tw;
-  const int rows_dflt = wf_tune().rows_per_cta > 0 ? wf_tune().rows_per_cta : 16;
+  // 32 x 32 tiles for K <= 4 (212 k vs 208 k frames/s at 32 x 16); K = 5..8 keeps 16 rows (the K flows of a tile must fit
+  // the 48 KB of default dynamic shared memory)
+  const int rows_dflt = wf_tune().rows_per_cta > 0 ? wf_tune().rows_per_cta : (a.K <= 4 ? 32 : 16);
   a.rows_per_cta = a.H < rows_dflt ? a.H : rows_dflt;
   a.tiles_y = (a.H + a.rows_per_cta - 1) / a.rows_per_cta;
   const long grid = (long)a.tiles_x * a.tiles_y * a.B;

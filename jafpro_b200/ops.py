@@ -313,11 +313,15 @@ def warp_fuse_from_poses(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx
     R, K = sv.shape[:2]
     S = int(image_size)
     dev = tv.device
-    if feat is None:
-        raise RuntimeError("warp_fuse_from_poses needs feat (use cal_flow_multi + warp_fuse for RGB-only calls)")
-    layout, dt, Cc, Hs, Ws = _feat_layout(feat)
-    if feat.shape[0] != R or feat.shape[1] != K:
-        raise RuntimeError("feat must be [R, K, C, Hs, Ws] with the R, K of the source poses")
+    if feat is None and rgb is None:
+        raise RuntimeError("warp_fuse_from_poses needs rgb and/or feat")
+    if feat is not None:
+        layout, dt, Cc, Hs, Ws = _feat_layout(feat)
+        if feat.shape[0] != R or feat.shape[1] != K:
+            raise RuntimeError("feat must be [R, K, C, Hs, Ws] with the R, K of the source poses")
+    else:  # RGB planes only
+        layout, dt, Cc = 1, 1, 0
+        Hs, Ws = rgb.shape[-2:]
     if ref_index is None and R != B:
         raise RuntimeError("without ref_index the source poses / reference sets need one entry per target frame")
     if not _lib.lib().jaf_warp_fuse_from_poses_supported(Cc, K, layout, dt):
@@ -338,9 +342,10 @@ def warp_fuse_from_poses(src_cam, src_vertices, tgt_cam, tgt_vertices, faces_idx
         if out_rgb is None:
             out_rgb = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
         q.rgb, q.out_rgb = rgb.data_ptr(), _check(out_rgb, "out_rgb", torch.float32).data_ptr()
-    if out_feat is None:
-        out_feat = torch.empty((B, S, S, Cc), dtype=feat.dtype, device=dev).permute(0, 3, 1, 2)
-    q.feat, q.out_feat = feat.data_ptr(), out_feat.data_ptr()
+    if feat is not None:
+        if out_feat is None:
+            out_feat = torch.empty((B, S, S, Cc), dtype=feat.dtype, device=dev).permute(0, 3, 1, 2)
+        q.feat, q.out_feat = feat.data_ptr(), out_feat.data_ptr()
     keep = []
     for name, t, dtype, shape in (("logits", logits, torch.float32, (B, K, S, S)), ("fake", fake, torch.float32, (B, 3, S, S)),
                                   ("conf", conf, torch.float32, (B, 1, S, S)), ("ref_index", ref_index, torch.int32, (B,))):

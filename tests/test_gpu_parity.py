@@ -841,6 +841,29 @@ def test_frame_graph_replays_the_batch_1_sequence_bit_identically():
     assert all(torch.equal(a, b) for a, b in zip(e2, outs)) and not torch.equal(e2[0], eager[0])
 
 
+@pytest.mark.parametrize("K", [1, 3])
+def test_warp_fuse_from_poses_rgb_only(K):
+    """The reference's per-frame chain at its own shapes (cal_flow -> warp_image -> mask -> confidence blend,
+    test/conv_pro_test.py:255-278; no feature tensor) through the pose-driven call: raster pass + ONE fused kernel."""
+    B, S = 2, 64
+    _, faces_idx = load_smpl_template()
+    f_idx = _cu(faces_idx)
+    cam, verts = synth.smpl_poses(B * (K + 1), seed=60 + K, device=DEV)
+    tc, tv = cam[:B].contiguous(), verts[:B].contiguous()
+    sc, sv = cam[B:].reshape(B, K, 3).contiguous(), verts[B:].reshape(B, K, -1, 3).contiguous()
+    rgb = torch.randn(B, K, 3, S, S, device=DEV)
+    logits = torch.randn(B, K, S, S, device=DEV)
+    fake, conf = torch.randn(B, 3, S, S, device=DEV), torch.rand(B, 1, S, S, device=DEV)
+    n0 = _lib.launch_count()
+    r1, f1 = ops.warp_fuse_from_poses(sc, sv, tc, tv, f_idx, S, rgb=rgb, logits=logits, fake=fake, conf=conf)
+    assert f1 is None and _lib.launch_count() - n0 == 3
+    T, fim, _ = ops.cal_flow_multi(sc, sv, tc, tv, f_idx, S, return_wim=False)
+    r2, _ = ops.warp_fuse(T, rgb=rgb, logits=logits, fim=fim, fake=fake, conf=conf)
+    assert float((r1 - r2).abs().max()) <= 1e-6      # (the RGB-only kernel of the two-call path divides the softmax once)
+    o = oracle.warp_fuse(_np(T), rgb=_np(rgb), logits=_np(logits), fim=_np(fim), fake=_np(fake), conf=_np(conf))
+    assert float(np.abs(_np(r1) - o["out_rgb"]).max()) <= 2e-6
+
+
 def test_warp_fuse_from_poses_self_cleaning_workspace():
     """The module-owned raster workspace is left empty by the fused kernel and the next call skips the 8 B / pixel clear
     (JAF_POSES_LEAVE_CLEAN / JAF_POSES_KEYS_CLEAN); any other user of the workspace dirties it.  Every call in any order
