@@ -235,9 +235,9 @@ def make_inputs(wl, rank, device, flow="dense"):
 
 
 def cpu_frames_per_pass(S, K, C):
-    """Frames of one CPU pass: one 30-frame video when its fp32 working set stays under ~2.5 GB."""
+    """Frames of one CPU pass: one 30-frame video when its fp32 working set stays under ~3 GB (256^2, K=4, C=64: 2.7 GB)."""
     per_frame = K * S * S * 4 * (3 + C + 3) + S * S * 4 * (3 + C)
-    return max(1, min(30, int(2.5e9 // max(1, per_frame))))
+    return max(1, min(30, int(3.0e9 // max(1, per_frame))))
 
 
 class CpuWarpFuse:

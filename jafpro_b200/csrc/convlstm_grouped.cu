@@ -36,6 +36,8 @@ using namespace jaf::tc;
 constexpr int kThreads = 1024;  // warp 0: weight stream + MMA issue; the other warps: staging + epilogue
 constexpr int kThreadsHalf = 512;  // two CTAs per SM (64 registers per thread either way)
 constexpr int kHalfSmem = 112 * 1024;
+constexpr int kThreadsQuarter = 256;  // four CTAs per SM: more staging / MMA / epilogue phases of different tiles overlap
+constexpr int kQuarterSmem = 55 * 1024;
 constexpr int kRing = 3;        // weight stages in flight
 constexpr int kMaxSmem = 232448 - 1024;
 
@@ -456,7 +458,7 @@ int jaf_convlstm_gpack_weight(const float* weight, int G, int Cin, int Ch, void*
 
 // Launch plan of one grouped step (shared by the launcher and jaf_convlstm_grouped_supported): fills `a`, the launch
 // shape and the dynamic shared memory.  Returns JAF_OK, or JAF_ERR_UNSUPPORTED when the cell does not fit the SM.
-static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_count, GArgs& a, bool& half, size_t& smem,
+static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_count, GArgs& a, int& threads, size_t& smem,
                         long& grid) {
   a.G = G; a.B = B; a.Cin = Cin; a.Ch = Ch; a.H = H; a.W = W;
   a.xs = (long)Cin * H * W;
@@ -515,19 +517,30 @@ static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_coun
       if ((long)m * a.Ns <= col_cap && sm <= smem_cap && m <= tiles_total) MT = m;
     }
   };
-  int ks_full, mt_full, ks_half, mt_half;
+  int ks_full, mt_full, ks_half, mt_half, ks_q, mt_q;
   plan(kMaxSmem, 512, 28 * 1024, ks_full, mt_full);
   plan(kHalfSmem, 256, 10 * 1024, ks_half, mt_half);
+  plan(kQuarterSmem, 128, 6 * 1024, ks_q, mt_q);
   if (mt_full < 1) {
     jaf::set_error("jaf_convlstm_step_grouped: cell does not fit shared memory (Cin=%d Ch=%d W=%d); use "
                    "jaf_convlstm_step_f32", Cin, Ch, W);
     return JAF_ERR_UNSUPPORTED;
   }
-  half = mt_half >= 1 && (long)G * CS * jaf::ceil_div(tiles_total, mt_half) > sm_count;
+  bool half = mt_half >= 1 && (long)G * CS * jaf::ceil_div(tiles_total, mt_half) > sm_count;
   if (forced_mode == 1) half = false;
   if (forced_mode == 2 && mt_half >= 1) half = true;
-  int MT = half ? mt_half : mt_full;
-  a.KS = half ? ks_half : ks_full;
+  // quarter shape: JAF_CG_MODE=3 forces it; JAF_CG_MODE=0 (auto) takes it when it fits and the grid is at least two
+  // waves of it (measured on the reference pyramid: profiles/r02_convlstm_grouped.jsonl)
+  bool quarter = mt_q >= 1 && forced_mode == 3;
+  static const int auto_quarter = [] {
+    const char* e = getenv("JAF_CG_AUTO_QUARTER");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced_mode == 0 && auto_quarter && mt_q >= 1 && (long)G * CS * jaf::ceil_div(tiles_total, mt_q) > 8L * sm_count) quarter = true;
+  if (quarter) half = true;  // shares the "not one CTA per SM" handling below
+  int MT = quarter ? mt_q : (half ? mt_half : mt_full);
+  a.KS = quarter ? ks_q : (half ? ks_half : ks_full);
+  threads = quarter ? kThreadsQuarter : (half ? kThreadsHalf : kThreads);
   a.nstages = a.S / a.KS;
   a.stage_bytes = (uint32_t)a.KS * 64u * (uint32_t)a.Ns;
   // keep at least one CTA per SM
@@ -558,10 +571,10 @@ int jaf_convlstm_grouped_supported(int G, int B, int Cin, int Ch, int H, int W) 
   int sms = jaf::sm_count(jaf::current_device());
   if (sms <= 0) sms = 148;  // no device yet: plan for a B200
   GArgs a;
-  bool half;
+  int threads;
   size_t smem;
   long grid;
-  return plan_grouped(G, B, Cin, Ch, H, W, sms, a, half, smem, grid) == JAF_OK ? 1 : 0;
+  return plan_grouped(G, B, Cin, Ch, H, W, sms, a, threads, smem, grid) == JAF_OK ? 1 : 0;
 }
 
 int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, const void* wpack, const float* bias,
@@ -581,12 +594,12 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
   GArgs a;
   a.x = x; a.h = h; a.c = c; a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
   a.h_out = h_out; a.c_out = c_out;
-  bool half;
+  int threads;
   size_t smem;
   long grid;
-  const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, half, smem, grid);
+  const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, threads, smem, grid);
   if (st != JAF_OK) return st;
-  k_convlstm_grouped<<<(unsigned)grid, half ? kThreadsHalf : kThreads, smem, jaf::as_stream(stream)>>>(a);
+  k_convlstm_grouped<<<(unsigned)grid, threads, smem, jaf::as_stream(stream)>>>(a);
   return jaf::finish_launch("k_convlstm_grouped");
 }
 
@@ -608,10 +621,10 @@ int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const flo
   }
   GArgs a;
   a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
-  bool half;
+  int threads;
   size_t smem;
   long grid;
-  const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, half, smem, grid);
+  const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, threads, smem, grid);
   if (st != JAF_OK) return st;
   const long HW = (long)H * W;
   // the recurrence of src/convLSTM.py:131-134 in one call: step t reads x[:, :, t] and h[:, :, t-1] straight from the
@@ -627,7 +640,7 @@ int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const flo
     a.h_out = h_seq + (long)t * Ch * HW;
     a.hos = (long)T * Ch * HW;
     a.c_out = cbuf[t & 1];
-    k_convlstm_grouped<<<(unsigned)grid, half ? kThreadsHalf : kThreads, smem, jaf::as_stream(stream)>>>(a);
+    k_convlstm_grouped<<<(unsigned)grid, threads, smem, jaf::as_stream(stream)>>>(a);
   }
   return jaf::finish_launch("k_convlstm_grouped (sequence)", T);
 }

@@ -1972,7 +1972,9 @@ extern "C" int jaf_warp_fuse_from_poses(const JafWarpFuseParams* p, const JafPos
   a.tiles_x = (a.W + tw - 1) / tw;
   // 32 x 32 tiles for K <= 4 (212 k vs 208 k frames/s at 32 x 16); K = 5..8 keeps 16 rows (the K flows of a tile must fit
   // the 48 KB of default dynamic shared memory)
-  const int rows_dflt = wf_tune().rows_per_cta > 0 ? wf_tune().rows_per_cta : (a.K <= 4 ? 32 : 16);
+  int rows_dflt = wf_tune().rows_per_cta > 0 ? wf_tune().rows_per_cta : (a.K <= 4 ? 32 : 16);
+  // small batches (the reference's per-frame loop runs batch 1): keep at least one wave of CTAs on the GPU
+  if (wf_tune().rows_per_cta <= 0 && (long)a.tiles_x * ((a.H + rows_dflt - 1) / rows_dflt) * a.B < 148L * 4) rows_dflt = 8;
   a.rows_per_cta = a.H < rows_dflt ? a.H : rows_dflt;
   a.tiles_y = (a.H + a.rows_per_cta - 1) / a.rows_per_cta;
   const long grid = (long)a.tiles_x * a.tiles_y * a.B;

@@ -232,3 +232,25 @@ def test_reference_frame_selection_rule():
     big = np.arange(40, dtype=np.float64)
     assert list(select_reference_frames(big, 1)[1]) == [0] and list(select_reference_frames(-big, 1)[1]) == [0]
     assert list(select_reference_frames(big, 4)[1])[0] == 30     # np.clip(frames, 0, 30), src/data.py:527
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU arm): one JSON line with the contract keys and the SAME `config` as our arm
+    would print for that workload (the driver compares them).  Run on the small latency workload."""
+    import json
+    import types
+    import bench
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1_latency",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    args = types.SimpleNamespace(workload="c1_latency", flow="dense")
+    assert line["config"] == bench.config_for(args, 1)
+    # and the headline workload's config is built by the same function for both arms
+    a2 = types.SimpleNamespace(workload="dancevideo_256_k4_c64", flow="dense")
+    cfg = bench.config_for(a2, 1)
+    assert cfg["frames_per_step_per_gpu"] == 240 and cfg["K"] == 4 and cfg["C"] == 64 and "knobs" in cfg
