@@ -434,6 +434,275 @@ k_gpack_weight(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, int
   *reinterpret_cast<__nv_bfloat16*>(stepb + 32 * (size_t)N + off) = lo;
 }
 
+
+// =====================================================================================
+// Operand-swapped flavour for the narrow cells (4*Ch <= 128: the 12- and 24-channel levels of the reference pyramid,
+// which hold 85 % of its pixels).  In k_convlstm_grouped the pixels are the M side (128 rows) and the gate rows the N
+// side: an MMA costs 128 cycles whatever N is (tools/probes/umma_probe.cu), so with N = 48 / 96 the tensor pipe does
+// 19 / 38 % of its work per issued MMA and the level is bound by the issue rate (ncu: tensor pipe 16-20 % active).
+// Here the WEIGHTS are the A operand (M = 128 rows = 4 gates x 32 channel slots, zero rows for missing channels) and 256
+// PIXELS the B operand (N = 256): the same 128 cycles now cover 256 pixels instead of 128.  Both operands keep the
+// K-major no-swizzle layout, so the staged pixel window and the packed weight image are used as they are — the roles
+// swap in the descriptors only.  The accumulator comes out transposed (TMEM lane = gate row, column = pixel): lane
+// quarter q holds gate q (i, f, o, g) of channel `lane`, so four warps (one per quarter) apply bias + activation to
+// their gate, exchange the results through shared memory (the staging buffer, free once the MMAs are done) and then
+// combine c' = f*c + i*g, h' = o*tanh(c') with thread = pixel (coalesced NCHW accesses).
+// =====================================================================================
+constexpr int kThreadsT = 512;       // warp 0: weights + MMA issue; warps 1..15 stage; warps 4..15 = three epilogue sets
+constexpr int kTileT = 256;          // pixels (flattened padded positions) per CTA = N of the MMA
+constexpr int kRowsT = 128;          // A rows: gate * 32 + channel slot
+constexpr int kStepBytesT = 2 * 2 * kRowsT * 16;  // one k-step of packed weights: [hi | lo][2 chunks][128 rows][16 B]
+constexpr int kXPitch = 33;          // floats per (gate, channel) row of the exchange buffer (32 pixels + 1: no bank conflicts)
+constexpr int kXSetFloats = 4 * 32 * kXPitch;
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreadsT, 2)
+k_convlstm_grouped_t(const GArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* sP = smem;                               // pixels: [hi | lo] x [Ctp/8 chunks][R rows][16 B]; later the exchange buffers
+  const uint32_t pix_bytes = max(2u * a.a_half, (uint32_t)(3 * kXSetFloats * 4));
+  uint8_t* sW = smem + ((pix_bytes + 127u) & ~127u);  // weight ring: kRing x KS k-steps
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kRing * a.stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kRing;
+  uint64_t* aready_bar = bars + 2 * kRing;
+  uint64_t* tfull_bar = bars + 2 * kRing + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRing + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x % a.tiles_per_group;
+  const int g = blockIdx.x / a.tiles_per_group;
+  const long p_end = a.Q - a.Wp - 1;                       // one past the last output position
+  const long p0 = (long)a.Wp + 1 + (long)t * kTileT;       // first output position of this CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(aready_bar, blockDim.x - 32);
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+
+  if (warp == 0) {
+    // ===================== weight stream + MMA issue =====================
+    const bool leader = lane == 0;
+    const uint8_t* wg = a.wpack + (size_t)g * a.S * kStepBytesT;
+    const uint32_t stage_bytes = a.stage_bytes;
+    const int nstages = a.nstages, KS = a.KS;
+    auto load_stage = [&](int st, int slot) {
+      mbar_expect_tx(&full_bar[slot], stage_bytes);
+      bulk_g2s(sW + (size_t)slot * stage_bytes, wg + (size_t)st * stage_bytes, stage_bytes, &full_bar[slot]);
+    };
+    const int pre = min(kRing, nstages);
+    if (leader) {
+      for (int st = 0; st < pre; ++st) load_stage(st, st);
+    }
+    const uint32_t R = (uint32_t)a.R, Wp = (uint32_t)a.Wp;
+    const int spt = a.Ctp / 16;
+    // A = weights: 128 rows, the two 8-element K chunks 128 rows apart; B = pixels: chunks R rows apart
+    const uint64_t wd0 = desc_noswz(smem_u32(sW), kRowsT * 16u), pd0 = desc_noswz(smem_u32(sP), R * 16u);
+    const uint32_t w_top = (uint32_t)(wd0 >> 32), p_top = (uint32_t)(pd0 >> 32);
+    const uint32_t w0 = (uint32_t)wd0, p_hi0 = (uint32_t)pd0, p_lo_delta = a.a_half >> 4;
+    const uint32_t stage_u = stage_bytes >> 4;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileT >> 3) << 17) | ((uint32_t)(kRowsT >> 4) << 24);
+    mbar_wait(aready_bar, 0);
+    tc_fence_after();
+    int kc = 0, kx = 0, ky = 0;
+    uint32_t accf = 0;
+    for (int st = 0; st < nstages; ++st) {
+      const int slot = st % kRing;
+      mbar_wait(&full_bar[slot], (uint32_t)(st / kRing) & 1u);
+      tc_fence_after();
+      uint32_t wh = w0 + (uint32_t)slot * stage_u;
+      for (int j = 0; j < KS; ++j, wh += (uint32_t)(kStepBytesT >> 4)) {
+        const uint32_t ph = p_hi0 + (uint32_t)(kc * 2) * R + (uint32_t)ky * Wp + (uint32_t)kx;
+        // w_hi*x_hi + w_hi*x_lo + w_lo*x_hi   (lo half of a k-step: 2 chunks x 128 rows = 256 descriptor units further)
+        if (elect_one()) umma_split3(tmem_base, wh, wh + 2u * kRowsT, w_top, ph, ph + p_lo_delta, p_top, idesc, accf);
+        accf = 1u;
+        if (++kc == spt) {
+          kc = 0;
+          if (++kx == 3) {
+            kx = 0;
+            ++ky;
+          }
+        }
+      }
+      if (leader) umma_commit(&empty_bar[slot]);
+      if (st >= 1 && st - 1 + kRing < nstages) {
+        const int ps = (st - 1) % kRing;
+        mbar_wait(&empty_bar[ps], (uint32_t)((st - 1) / kRing) & 1u);
+        if (leader) load_stage(st - 1 + kRing, ps);
+      }
+    }
+    if (leader) umma_commit(tfull_bar);
+  } else {
+    // ===================== stage the pixel rows (15 warps): identical to k_convlstm_grouped =====================
+    const size_t HW = (size_t)a.H * a.W;
+    {
+      const int wid = threadIdx.x - 32;
+      const long q0 = p0 - a.Wp - 1;
+      const int npairs = a.Ctp / 16;
+      const int items = a.R * npairs;
+      const int nworkers = (int)blockDim.x - 32;
+      for (int it = wid; it < items; it += nworkers) {
+        const int cp = it / a.R, i = it - cp * a.R;
+        const long q = q0 + i;
+        bool inside = q < a.Q;
+        size_t pix = 0;
+        int b = 0;
+        if (inside) {
+          const int u = (int)(q / a.HpWp);
+          const int rem = (int)(q - (long)u * a.HpWp);
+          const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
+          b = u / a.nb;
+          const int x = (u - b * a.nb) * a.Wb + xp - 1;
+          inside = x >= 0 && x < a.W && yp >= 1 && yp <= a.H;
+          pix = (size_t)(yp - 1) * a.W + (size_t)x;
+        }
+        const float* xb = a.x + ((size_t)g * a.B + b) * (size_t)a.xs + pix;
+        const float* hb = a.h + ((size_t)g * a.B + b) * (size_t)a.hs + pix;
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int ch = cp * 16 + e;
+          float val = 0.f;
+          if (inside && ch < a.Ct) val = ch < a.Cin ? __ldg(xb + (size_t)ch * HW) : __ldg(hb + (size_t)(ch - a.Cin) * HW);
+          v[e] = val;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint4 hi, lo;
+          split2(v[8 * u + 0], v[8 * u + 1], hi.x, lo.x);
+          split2(v[8 * u + 2], v[8 * u + 3], hi.y, lo.y);
+          split2(v[8 * u + 4], v[8 * u + 5], hi.z, lo.z);
+          split2(v[8 * u + 6], v[8 * u + 7], hi.w, lo.w);
+          uint8_t* dst = sP + ((size_t)(cp * 2 + u) * a.R + i) * 16;
+          *reinterpret_cast<uint4*>(dst) = hi;
+          *reinterpret_cast<uint4*>(dst + a.a_half) = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(aready_bar);
+    }
+    // ===================== epilogue: three sets of four warps (one warp per gate / TMEM lane quarter) =====================
+    if (warp >= 4) {
+      const int q = warp & 3, set = (warp - 4) >> 2;    // gate of this warp (i, f, o, g), which 32-pixel chunks
+      float* X = reinterpret_cast<float*>(sP) + (size_t)set * kXSetFloats;  // [gate][channel slot][kXPitch]
+      const int Ch = a.Ch;
+      float bias = 0.f;
+      if (a.bias != nullptr && lane < Ch) bias = __ldg(a.bias + (size_t)g * 4 * Ch + q * Ch + lane);  // rows gate*Ch + ch (:46)
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      for (int chunk = set; chunk < kTileT / 32; chunk += 3) {
+        if (p0 + (long)chunk * 32 >= p_end) break;  // uniform over the set
+        // (1) this warp's gate of channel `lane`, 32 pixels: bias + activation -> exchange buffer
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), v);
+        tmem_ld_wait();
+        if (lane < Ch) {
+          float* xr = X + ((size_t)q * 32 + lane) * kXPitch;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xr[j] = (q < 3) ? sigmoid_f(v[j] + bias) : tanh_f(v[j] + bias);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+        // (2) combine, thread = pixel (lane), channels q, q + 4, ... : c' = f*c + i*g, h' = o*tanh(c')
+        const long p = p0 + (long)chunk * 32 + lane;
+        bool ok = p < p_end;
+        size_t base = 0, hbase = 0;
+        if (ok) {
+          const int un = (int)(p / a.HpWp);
+          const int rem = (int)(p - (long)un * a.HpWp);
+          const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
+          const int b = un / a.nb;
+          const int x = (un - b * a.nb) * a.Wb + xp - 1;
+          ok = xp >= 1 && xp <= a.Wb && x < a.W && yp >= 1 && yp <= a.H;
+          base = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)x;
+          hbase = ((size_t)g * a.B + b) * (size_t)a.hos + (size_t)(yp - 1) * a.W + (size_t)x;
+        }
+        if (ok) {
+          for (int ch = q; ch < Ch; ch += 4) {
+            const float ig = X[((size_t)0 * 32 + ch) * kXPitch + lane], fg = X[((size_t)1 * 32 + ch) * kXPitch + lane];
+            const float og = X[((size_t)2 * 32 + ch) * kXPitch + lane], g_ = X[((size_t)3 * 32 + ch) * kXPitch + lane];
+            const float cn = fg * __ldg(a.c + base + (size_t)ch * HW) + ig * g_;  // src/convLSTM.py:53
+            a.c_out[base + (size_t)ch * HW] = cn;
+            a.h_out[hbase + (size_t)ch * HW] = og * tanh_f(cn);                    // :54
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");  // the buffer is rewritten by the next chunk
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+// weight [G][4Ch][Ct][3][3] f32 -> per cell, per k-step (tap, 16 channels): [hi | lo] x [2 chunks][128 rows][8 bf16],
+// row = gate * 32 + channel (zero rows where channel >= Ch)
+__global__ void __launch_bounds__(256)
+k_gpack_weight_t(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, int Ch, int Ct, int Ctp) {
+  const int spt = Ctp / 16, S = 9 * spt;
+  const size_t total = (size_t)G * S * 2 * kRowsT * 8;  // one thread per (g, step, chunk, row, e)
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int e = (int)(i % 8);
+  size_t r = i / 8;
+  const int row = (int)(r % kRowsT);
+  r /= kRowsT;
+  const int cc = (int)(r % 2);
+  r /= 2;
+  const int step = (int)(r % S);
+  const int g = (int)(r / S);
+  const int tap = step / spt, kc = step % spt;
+  const int ch_in = kc * 16 + cc * 8 + e;
+  const int gate = row / 32, ch = row % 32;
+  float v = 0.f;
+  if (ch < Ch && ch_in < Ct) v = w[(((size_t)g * 4 * Ch + (size_t)gate * Ch + ch) * Ct + ch_in) * 9 + tap];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  uint8_t* stepb = wp + ((size_t)g * S + step) * kStepBytesT;
+  const size_t off = (size_t)cc * 16 * kRowsT + (size_t)row * 16 + (size_t)e * 2;
+  *reinterpret_cast<__nv_bfloat16*>(stepb + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(stepb + 32 * (size_t)kRowsT + off) = lo;
+}
+
+// Cells served by the operand-swapped kernel (the packed-weight format follows this rule, so it must not change
+// between packing and stepping: the environment is read once per process).
+bool grouped_swapped(int Ch) {
+  static const bool enabled = [] {
+    const char* e = getenv("JAF_CG_SWAP");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return enabled && Ch <= 32;
+}
+
 bool grouped_shape_ok(int Cin, int Ch) { return Cin > 0 && Ch > 0 && Ch % 4 == 0 && 4 * Ch <= 512 && ((4 * Ch <= 256) || (2 * Ch) % 16 == 0); }
 
 }  // namespace
@@ -443,6 +712,7 @@ extern "C" {
 size_t jaf_convlstm_gpack_bytes(int G, int Cin, int Ch) {
   if (G <= 0 || !grouped_shape_ok(Cin, Ch)) return 0;
   const int Ctp = (Cin + Ch + 15) / 16 * 16;
+  if (grouped_swapped(Ch)) return (size_t)G * 9 * (Ctp / 16) * kStepBytesT;
   return (size_t)G * 9 * (Ctp / 16) * 64 * (4 * Ch);
 }
 
@@ -450,6 +720,12 @@ int jaf_convlstm_gpack_weight(const float* weight, int G, int Cin, int Ch, void*
   JAF_REQUIRE(weight && wpack, "null pointer");
   JAF_REQUIRE(G > 0 && grouped_shape_ok(Cin, Ch), "Ch must be a multiple of 4 and at most 128");
   const int Ct = Cin + Ch, Ctp = (Ct + 15) / 16 * 16, N = 4 * Ch;
+  if (grouped_swapped(Ch)) {
+    const size_t total_t = (size_t)G * 9 * (Ctp / 16) * 2 * kRowsT * 8;
+    k_gpack_weight_t<<<jaf::ceil_div((long)total_t, 256), 256, 0, jaf::as_stream(stream)>>>(weight, static_cast<uint8_t*>(wpack),
+                                                                                         G, Ch, Ct, Ctp);
+    return jaf::finish_launch("k_gpack_weight_t");
+  }
   const size_t total = (size_t)G * 9 * (Ctp / 16) * 2 * N * 8;
   k_gpack_weight<<<jaf::ceil_div((long)total, 256), 256, 0, jaf::as_stream(stream)>>>(
       weight, static_cast<uint8_t*>(wpack), G, N, Ct, Ctp);
@@ -566,6 +842,48 @@ static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_coun
   return JAF_OK;
 }
 
+// Launch plan of the operand-swapped kernel: the geometry of plan_grouped with 256-pixel tiles, one accumulator tile
+// per CTA and two CTAs per SM.
+static int plan_grouped_t(int G, int B, int Cin, int Ch, int H, int W, GArgs& a, size_t& smem, long& grid) {
+  a.G = G; a.B = B; a.Cin = Cin; a.Ch = Ch; a.H = H; a.W = W;
+  a.xs = (long)Cin * H * W;
+  a.hs = a.hos = (long)Ch * H * W;
+  static const int band_target = [] {
+    const char* e = getenv("JAF_CG_BAND");
+    const int v = e ? atoi(e) : 25;
+    return v >= 8 ? v : 25;
+  }();
+  a.nb = (W + band_target / 2) / band_target;
+  if (a.nb < 1) a.nb = 1;
+  a.Wb = (W + a.nb - 1) / a.nb;
+  a.Wp = a.Wb + 2;
+  a.HpWp = (H + 2) * a.Wp;
+  a.Q = (long)B * a.nb * a.HpWp;
+  a.Ct = Cin + Ch;
+  a.Ctp = (a.Ct + 15) / 16 * 16;
+  a.N = 4 * Ch;
+  a.S = 9 * (a.Ctp / 16);
+  a.CS = 1; a.Chs = Ch; a.Ns = a.N; a.nsplit = 1; a.Nsub = a.N;
+  a.MT = kTileT / 128;
+  a.R = kTileT + 2 * a.Wp + 2;
+  a.a_half = (uint32_t)(a.Ctp / 8) * (uint32_t)a.R * 16u;
+  a.KS = 1;
+  a.nstages = a.S;
+  a.stage_bytes = (uint32_t)a.KS * kStepBytesT;
+  a.tmem_cols = 256;
+  a.idesc = 0;
+  const long out_rows = a.Q - 2L * a.Wp - 2;
+  a.tiles_per_group = jaf::ceil_div(out_rows, kTileT);
+  const size_t pix = ((size_t)(2u * a.a_half > (uint32_t)(3 * kXSetFloats * 4) ? 2u * a.a_half : (uint32_t)(3 * kXSetFloats * 4)) + 127) & ~(size_t)127;
+  smem = pix + (size_t)kRing * a.stage_bytes + 256 + 128;
+  grid = (long)G * a.tiles_per_group;
+  if (smem > (size_t)kHalfSmem || (uint32_t)a.R * 16u >= (1u << 18) || grid >= (1L << 31)) {
+    jaf::set_error("jaf_convlstm_step_grouped: cell does not fit the operand-swapped plan (Cin=%d Ch=%d W=%d)", Cin, Ch, W);
+    return JAF_ERR_UNSUPPORTED;
+  }
+  return JAF_OK;
+}
+
 int jaf_convlstm_grouped_supported(int G, int B, int Cin, int Ch, int H, int W) {
   if (G <= 0 || B <= 0 || H <= 0 || W <= 0 || !grouped_shape_ok(Cin, Ch)) return 0;
   int sms = jaf::sm_count(jaf::current_device());
@@ -574,6 +892,7 @@ int jaf_convlstm_grouped_supported(int G, int B, int Cin, int Ch, int H, int W) 
   int threads;
   size_t smem;
   long grid;
+  if (grouped_swapped(Ch)) return plan_grouped_t(G, B, Cin, Ch, H, W, a, smem, grid) == JAF_OK ? 1 : 0;
   return plan_grouped(G, B, Cin, Ch, H, W, sms, a, threads, smem, grid) == JAF_OK ? 1 : 0;
 }
 
@@ -597,6 +916,17 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
   int threads;
   size_t smem;
   long grid;
+  if (grouped_swapped(Ch)) {
+    static jaf::PerDeviceOnce attr_once_t;
+    if (!attr_once_t.done(dev)) {
+      JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kHalfSmem));
+      attr_once_t.mark(dev);
+    }
+    const int stt = plan_grouped_t(G, B, Cin, Ch, H, W, a, smem, grid);
+    if (stt != JAF_OK) return stt;
+    k_convlstm_grouped_t<<<(unsigned)grid, kThreadsT, smem, jaf::as_stream(stream)>>>(a);
+    return jaf::finish_launch("k_convlstm_grouped_t");
+  }
   const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, threads, smem, grid);
   if (st != JAF_OK) return st;
   k_convlstm_grouped<<<(unsigned)grid, threads, smem, jaf::as_stream(stream)>>>(a);
@@ -621,10 +951,19 @@ int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const flo
   }
   GArgs a;
   a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
-  int threads;
+  int threads = kThreadsT;
   size_t smem;
   long grid;
-  const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, threads, smem, grid);
+  const bool swapped = grouped_swapped(Ch);
+  if (swapped) {
+    static jaf::PerDeviceOnce attr_once_t;
+    if (!attr_once_t.done(dev)) {
+      JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kHalfSmem));
+      attr_once_t.mark(dev);
+    }
+  }
+  const int st = swapped ? plan_grouped_t(G, B, Cin, Ch, H, W, a, smem, grid)
+                         : plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, threads, smem, grid);
   if (st != JAF_OK) return st;
   const long HW = (long)H * W;
   // the recurrence of src/convLSTM.py:131-134 in one call: step t reads x[:, :, t] and h[:, :, t-1] straight from the
@@ -640,7 +979,8 @@ int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const flo
     a.h_out = h_seq + (long)t * Ch * HW;
     a.hos = (long)T * Ch * HW;
     a.c_out = cbuf[t & 1];
-    k_convlstm_grouped<<<(unsigned)grid, threads, smem, jaf::as_stream(stream)>>>(a);
+    if (swapped) k_convlstm_grouped_t<<<(unsigned)grid, kThreadsT, smem, jaf::as_stream(stream)>>>(a);
+    else k_convlstm_grouped<<<(unsigned)grid, threads, smem, jaf::as_stream(stream)>>>(a);
   }
   return jaf::finish_launch("k_convlstm_grouped (sequence)", T);
 }
