@@ -448,12 +448,12 @@ k_gpack_weight(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, int
 // their gate, exchange the results through shared memory (the staging buffer, free once the MMAs are done) and then
 // combine c' = f*c + i*g, h' = o*tanh(c') with thread = pixel (coalesced NCHW accesses).
 // =====================================================================================
-constexpr int kThreadsT = 512;       // warp 0: weights + MMA issue; warps 1..15 stage; warps 4..15 = three epilogue sets
+constexpr int kThreadsT = 512;       // warp 0: weights + MMA issue; warps 1..15 stage; all 16 warps = four epilogue sets
 constexpr int kTileT = 256;          // pixels (flattened padded positions) per CTA = N of the MMA
 constexpr int kRowsT = 128;          // A rows: gate * 32 + channel slot
 constexpr int kStepBytesT = 2 * 2 * kRowsT * 16;  // one k-step of packed weights: [hi | lo][2 chunks][128 rows][16 B]
 constexpr int kXPitch = 33;          // floats per (gate, channel) row of the exchange buffer (32 pixels + 1: no bank conflicts)
-constexpr int kXSetFloats = 4 * 32 * kXPitch;
+constexpr int kXSetFloats = 4 * 32 * kXPitch;  // upper bound of one set's exchange buffer ([4 gates][Ch <= 32][kXPitch])
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -471,10 +471,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 
 __global__ void __launch_bounds__(kThreadsT, 2)
 k_convlstm_grouped_t(const GArgs a) {
+  PROF_STAMP(t_start);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   uint8_t* sP = smem;                               // pixels: [hi | lo] x [Ctp/8 chunks][R rows][16 B]; later the exchange buffers
-  const uint32_t pix_bytes = max(2u * a.a_half, (uint32_t)(3 * kXSetFloats * 4));
+  const uint32_t pix_bytes = max(2u * a.a_half, (uint32_t)(4 * kXSetFloats * 4));
   uint8_t* sW = smem + ((pix_bytes + 127u) & ~127u);  // weight ring: kRing x KS k-steps
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kRing * a.stage_bytes);
   uint64_t* full_bar = bars;
@@ -531,6 +532,7 @@ k_convlstm_grouped_t(const GArgs a) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileT >> 3) << 17) | ((uint32_t)(kRowsT >> 4) << 24);
     mbar_wait(aready_bar, 0);
     tc_fence_after();
+    PROF_STAMP(t_aready);
     int kc = 0, kx = 0, ky = 0;
     uint32_t accf = 0;
     for (int st = 0; st < nstages; ++st) {
@@ -559,6 +561,14 @@ k_convlstm_grouped_t(const GArgs a) {
       }
     }
     if (leader) umma_commit(tfull_bar);
+#ifdef JAF_GROUPED_PROFILE
+    PROF_STAMP(t_issued);
+    mbar_wait(tfull_bar, 0);
+    PROF_STAMP(t_done);
+    if ((blockIdx.x == 0 || blockIdx.x == 1000) && leader)
+      printf("cta %d (swapped): R=%d nstages=%d | staged at %llu ns, mma issued +%llu, mma done +%llu\n", blockIdx.x, a.R,
+             a.nstages, t_aready - t_start, t_issued - t_aready, t_done - t_aready);
+#endif
   } else {
     // ===================== stage the pixel rows (15 warps): identical to k_convlstm_grouped =====================
     const size_t HW = (size_t)a.H * a.W;
@@ -608,54 +618,76 @@ k_convlstm_grouped_t(const GArgs a) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(aready_bar);
     }
-    // ===================== epilogue: three sets of four warps (one warp per gate / TMEM lane quarter) =====================
-    if (warp >= 4) {
-      const int q = warp & 3, set = (warp - 4) >> 2;    // gate of this warp (i, f, o, g), which 32-pixel chunks
-      float* X = reinterpret_cast<float*>(sP) + (size_t)set * kXSetFloats;  // [gate][channel slot][kXPitch]
-      const int Ch = a.Ch;
-      float bias = 0.f;
-      if (a.bias != nullptr && lane < Ch) bias = __ldg(a.bias + (size_t)g * 4 * Ch + q * Ch + lane);  // rows gate*Ch + ch (:46)
-      mbar_wait(tfull_bar, 0);
-      tc_fence_after();
-      for (int chunk = set; chunk < kTileT / 32; chunk += 3) {
-        if (p0 + (long)chunk * 32 >= p_end) break;  // uniform over the set
-        // (1) this warp's gate of channel `lane`, 32 pixels: bias + activation -> exchange buffer
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), v);
-        tmem_ld_wait();
-        if (lane < Ch) {
-          float* xr = X + ((size_t)q * 32 + lane) * kXPitch;
+  }
+  // ===================== epilogue: four sets of four warps (one warp per gate / TMEM lane quarter) =====================
+  // All 16 warps take part (the MMA warp joins once its last commit is out).  Per 32-pixel chunk: (0) the combine
+  // stage's cell-state loads are issued first (their addresses do not depend on the accumulator), (1) each warp applies
+  // bias + activation to its gate of channel `lane` and writes the exchange buffer, (2) thread = pixel combines
+  // c' = f*c + i*g, h' = o*tanh(c') for channels q, q + 4, ...
+  {
+    const size_t HW = (size_t)a.H * a.W;
+    const int q = warp & 3, set = warp >> 2;
+    const int Ch = a.Ch;
+    float* X = reinterpret_cast<float*>(sP) + (size_t)set * (4 * Ch * kXPitch);  // [gate][channel][kXPitch]
+    float bias = 0.f;
+    if (a.bias != nullptr && lane < Ch) bias = __ldg(a.bias + (size_t)g * 4 * Ch + q * Ch + lane);  // rows gate*Ch + ch (:46)
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    for (int chunk = set; chunk < kTileT / 32; chunk += 4) {
+      if (p0 + (long)chunk * 32 >= p_end) break;  // uniform over the set
+      // (0) where this thread's pixel lives + its previous cell state (channels q, q+4, ... : at most 8 per thread)
+      const long p = p0 + (long)chunk * 32 + lane;
+      bool ok = p < p_end;
+      size_t base = 0, hbase = 0;
+      if (ok) {
+        const int un = (int)(p / a.HpWp);
+        const int rem = (int)(p - (long)un * a.HpWp);
+        const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
+        const int b = un / a.nb;
+        const int x = (un - b * a.nb) * a.Wb + xp - 1;
+        ok = xp >= 1 && xp <= a.Wb && x < a.W && yp >= 1 && yp <= a.H;
+        base = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)x;
+        hbase = ((size_t)g * a.B + b) * (size_t)a.hos + (size_t)(yp - 1) * a.W + (size_t)x;
+      }
+      float cprev[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) xr[j] = (q < 3) ? sigmoid_f(v[j] + bias) : tanh_f(v[j] + bias);
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
-        // (2) combine, thread = pixel (lane), channels q, q + 4, ... : c' = f*c + i*g, h' = o*tanh(c')
-        const long p = p0 + (long)chunk * 32 + lane;
-        bool ok = p < p_end;
-        size_t base = 0, hbase = 0;
-        if (ok) {
-          const int un = (int)(p / a.HpWp);
-          const int rem = (int)(p - (long)un * a.HpWp);
-          const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
-          const int b = un / a.nb;
-          const int x = (un - b * a.nb) * a.Wb + xp - 1;
-          ok = xp >= 1 && xp <= a.Wb && x < a.W && yp >= 1 && yp <= a.H;
-          base = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)x;
-          hbase = ((size_t)g * a.B + b) * (size_t)a.hos + (size_t)(yp - 1) * a.W + (size_t)x;
-        }
-        if (ok) {
-          for (int ch = q; ch < Ch; ch += 4) {
-            const float ig = X[((size_t)0 * 32 + ch) * kXPitch + lane], fg = X[((size_t)1 * 32 + ch) * kXPitch + lane];
-            const float og = X[((size_t)2 * 32 + ch) * kXPitch + lane], g_ = X[((size_t)3 * 32 + ch) * kXPitch + lane];
-            const float cn = fg * __ldg(a.c + base + (size_t)ch * HW) + ig * g_;  // src/convLSTM.py:53
+      for (int u = 0; u < 8; ++u) {
+        const int ch = q + 4 * u;
+        cprev[u] = (ok && ch < Ch) ? __ldg(a.c + base + (size_t)ch * HW) : 0.f;
+      }
+      // (1) this warp's gate of channel `lane`, 32 pixels: bias + activation -> exchange buffer
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), v);
+      tmem_ld_wait();
+      if (lane < Ch) {
+        float* xr = X + ((size_t)q * Ch + lane) * kXPitch;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xr[j] = (q < 3) ? sigmoid_f(v[j] + bias) : tanh_f(v[j] + bias);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+      // (2) combine, thread = pixel
+      if (ok) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int ch = q + 4 * u;
+          if (ch < Ch) {
+            const float ig = X[((size_t)0 * Ch + ch) * kXPitch + lane], fg = X[((size_t)1 * Ch + ch) * kXPitch + lane];
+            const float og = X[((size_t)2 * Ch + ch) * kXPitch + lane], g_ = X[((size_t)3 * Ch + ch) * kXPitch + lane];
+            const float cn = fg * cprev[u] + ig * g_;                  // src/convLSTM.py:53
             a.c_out[base + (size_t)ch * HW] = cn;
-            a.h_out[hbase + (size_t)ch * HW] = og * tanh_f(cn);                    // :54
+            a.h_out[hbase + (size_t)ch * HW] = og * tanh_f(cn);         // :54
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");  // the buffer is rewritten by the next chunk
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");  // the buffer is rewritten by the next chunk
     }
   }
+#ifdef JAF_GROUPED_PROFILE
+  if ((threadIdx.x == 128 || threadIdx.x == 32) && (blockIdx.x == 0 || blockIdx.x == 1000)) {
+    PROF_STAMP(t_end);
+    printf("cta %d (swapped): warp %d finished at %llu ns after start\n", blockIdx.x, warp, t_end - t_start);
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -695,12 +727,17 @@ k_gpack_weight_t(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, i
 
 // Cells served by the operand-swapped kernel (the packed-weight format follows this rule, so it must not change
 // between packing and stepping: the environment is read once per process).
+// Measured on the reference pyramid (24 cells, B = 1; profiles/r02_convlstm_grouped.jsonl): 24 channels @100^2 0.133 ms
+// swapped vs 0.164 ms, @50^2 0.041 vs 0.048; 12 channels @200^2 0.368 vs 0.280 (only 12 of the 32 lanes of each epilogue
+// warp hold a channel, and the per-CTA timers put 10 of 26 us in the exchange epilogue) -> swapped for 16 < Ch <= 32.
+// JAF_CG_SWAP: 0 never, 1 (default) by the rule above, 2 every cell with Ch <= 32.
 bool grouped_swapped(int Ch) {
-  static const bool enabled = [] {
+  static const int mode = [] {
     const char* e = getenv("JAF_CG_SWAP");
-    return e == nullptr || atoi(e) != 0;
+    return e == nullptr ? 1 : atoi(e);
   }();
-  return enabled && Ch <= 32;
+  if (mode == 0 || Ch > 32) return false;
+  return mode == 2 || Ch > 16;
 }
 
 bool grouped_shape_ok(int Cin, int Ch) { return Cin > 0 && Ch > 0 && Ch % 4 == 0 && 4 * Ch <= 512 && ((4 * Ch <= 256) || (2 * Ch) % 16 == 0); }
@@ -874,7 +911,7 @@ static int plan_grouped_t(int G, int B, int Cin, int Ch, int H, int W, GArgs& a,
   a.idesc = 0;
   const long out_rows = a.Q - 2L * a.Wp - 2;
   a.tiles_per_group = jaf::ceil_div(out_rows, kTileT);
-  const size_t pix = ((size_t)(2u * a.a_half > (uint32_t)(3 * kXSetFloats * 4) ? 2u * a.a_half : (uint32_t)(3 * kXSetFloats * 4)) + 127) & ~(size_t)127;
+  const size_t pix = ((size_t)(2u * a.a_half > (uint32_t)(4 * kXSetFloats * 4) ? 2u * a.a_half : (uint32_t)(4 * kXSetFloats * 4)) + 127) & ~(size_t)127;
   smem = pix + (size_t)kRing * a.stage_bytes + 256 + 128;
   grid = (long)G * a.tiles_per_group;
   if (smem > (size_t)kHalfSmem || (uint32_t)a.R * 16u >= (1u << 18) || grid >= (1L << 31)) {
