@@ -41,6 +41,10 @@ constexpr int kQuarterSmem = 55 * 1024;
 constexpr int kRing = 3;        // weight stages in flight
 constexpr int kMaxSmem = 232448 - 1024;
 
+struct FastDiv {
+  uint32_t d, m;
+};
+
 struct GArgs {
   const float* x;
   const float* h;
@@ -61,6 +65,9 @@ struct GArgs {
   int MT, R;         // accumulator tiles per CTA, staged rows
   int S, KS, nstages;
   int tiles_per_group;
+  FastDiv d_hpwp, d_wp, d_nb;  // persistent kernel: position -> (image, band, row, column) without divisions
+  int ring;          // persistent kernel: weight k-steps in flight
+  long ntiles;       // persistent kernel: G * tiles_per_group
   uint32_t idesc, a_half, stage_bytes, tmem_cols;
 };
 
@@ -141,8 +148,18 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 #define PROF_STAMP(var) const unsigned long long var = gtime()
+#define PROF_DECL(var) unsigned long long var = 0
+#define PROF_ACC(acc, ...)                  \
+  {                                         \
+    const unsigned long long t0_ = gtime(); \
+    __VA_ARGS__;                            \
+    acc += gtime() - t0_;                   \
+  }
 #else
 #define PROF_STAMP(var)
+#define PROF_DECL(var)
+#define PROF_ACC(acc, ...) \
+  { __VA_ARGS__; }
 #endif
 
 // Warp 0: weight stream + MMA issue (one thread).  Warps 1..31: activation staging, then the gate epilogue
@@ -585,8 +602,8 @@ k_convlstm_grouped_t(const GArgs a) {
         size_t pix = 0;
         int b = 0;
         if (inside) {
-          const int u = (int)(q / a.HpWp);
-          const int rem = (int)(q - (long)u * a.HpWp);
+          const int u = (int)((uint32_t)q / (uint32_t)a.HpWp);  // Q < 2^31 (checked by the planner)
+          const int rem = (int)((uint32_t)q - (uint32_t)u * (uint32_t)a.HpWp);
           const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
           b = u / a.nb;
           const int x = (u - b * a.nb) * a.Wb + xp - 1;
@@ -640,8 +657,8 @@ k_convlstm_grouped_t(const GArgs a) {
       bool ok = p < p_end;
       size_t base = 0, hbase = 0;
       if (ok) {
-        const int un = (int)(p / a.HpWp);
-        const int rem = (int)(p - (long)un * a.HpWp);
+        const int un = (int)((uint32_t)p / (uint32_t)a.HpWp);
+        const int rem = (int)((uint32_t)p - (uint32_t)un * (uint32_t)a.HpWp);
         const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
         const int b = un / a.nb;
         const int x = (un - b * a.nb) * a.Wb + xp - 1;
@@ -661,8 +678,13 @@ k_convlstm_grouped_t(const GArgs a) {
       tmem_ld_wait();
       if (lane < Ch) {
         float* xr = X + ((size_t)q * Ch + lane) * kXPitch;
+        if (q < 3) {  // hoisted: with the select inside the loop ptxas emits a branch per element (no ILP across the 32)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) xr[j] = (q < 3) ? sigmoid_f(v[j] + bias) : tanh_f(v[j] + bias);
+          for (int j = 0; j < 32; ++j) xr[j] = sigmoid_f(v[j] + bias);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xr[j] = tanh_f(v[j] + bias);
+        }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
       // (2) combine, thread = pixel
@@ -693,6 +715,346 @@ k_convlstm_grouped_t(const GArgs a) {
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+// n / d for n < 2^32 with m = min(floor(2^32 / d), 2^32 - 1): umulhi gives the quotient or one less
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f, uint32_t& rem) {
+  uint32_t q = __umulhi(n, f.m);
+  rem = n - q * f.d;
+  if (rem >= f.d) {
+    ++q;
+    rem -= f.d;
+  }
+  return q;
+}
+
+constexpr int kThreadsP = 768;
+constexpr int kStagerWarp0 = 2, kStagerWarps = 10, kEpiWarp0 = 12, kEpiSets = 3;
+constexpr int kMaxRingP = 16;
+
+// Gate epilogue of the persistent kernel, NU = Ch / 4 channels per thread.  Per 32-pixel chunk of the accumulator:
+// (0) thread = pixel: where the pixel lives + its previous cell state (loads in flight during the next two stages);
+// (1) warp q owns TMEM lane quarter q = gate q of channel `lane`: it dumps the RAW accumulator row (32 pixels) into the
+//     set's exchange buffer — no arithmetic here, because only Ch of the 32 lanes hold a channel;
+// (2) thread = pixel, channels q, q + 4, ...: bias + the five activations + c' = f*c + i*g, h' = o*tanh(c') on full warps,
+//     the NU channels as independent instruction streams (NU is a template parameter: no per-channel branches).
+template <int NU>
+__device__ __forceinline__ void epilogue_role_p(const GArgs& a, float* sX, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
+                                                long first, int n_here, long p_end) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t HW = (size_t)a.H * a.W;
+  const int q = warp & 3, set = (warp - kEpiWarp0) >> 2;
+  constexpr int Ch = 4 * NU;
+  constexpr int xset_floats = 4 * Ch * kXPitch + 4 * Ch;  // [gate][channel][kXPitch] + bias [gate][channel]
+  float* X = sX + (size_t)set * xset_floats;
+  float* sbias = X + 4 * Ch * kXPitch;
+  int g_bias = -1;
+  PROF_DECL(w_f);
+  PROF_DECL(w_pre);
+  PROF_DECL(w_dump);
+  PROF_DECL(w_comb);
+  PROF_STAMP(t_begin);
+  for (int i = 0; i < n_here; ++i) {
+    const int buf = i & 1;
+    const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+    const long tile = first + i;
+    const int g = (int)(tile / a.tiles_per_group);
+    const long p0 = (long)a.Wp + 1 + (tile - (long)g * a.tiles_per_group) * kTileT;
+    if (g != g_bias) {  // set-uniform; the previous tile's last barrier has passed, the next one orders these writes
+      g_bias = g;
+      const int t4 = (warp & 3) * 32 + lane;
+      if (t4 < 4 * Ch) sbias[t4] = a.bias != nullptr ? __ldg(a.bias + (size_t)g * 4 * Ch + t4) : 0.f;  // rows gate*Ch + ch (:46)
+    }
+    bool waited = false;
+    for (int chunk = set; chunk < kTileT / 32; chunk += kEpiSets) {
+      if (p0 + (long)chunk * 32 >= p_end) break;  // uniform over the set
+      PROF_STAMP(t0);
+      const long p = p0 + (long)chunk * 32 + lane;
+      bool ok = p < p_end;
+      const float* cp = a.c;
+      float* cop = a.c_out;
+      float* hop = a.h_out;
+      if (ok) {
+        uint32_t rem, xp, ub;
+        const uint32_t un = fdiv((uint32_t)p, a.d_hpwp, rem);
+        const uint32_t yp = fdiv(rem, a.d_wp, xp);
+        const uint32_t b = fdiv(un, a.d_nb, ub);
+        const int x = (int)ub * a.Wb + (int)xp - 1;
+        ok = xp >= 1 && (int)xp <= a.Wb && x < a.W && yp >= 1 && (int)yp <= a.H;
+        const size_t pix = (size_t)(yp - 1) * a.W + (size_t)x + (size_t)q * HW;
+        const size_t base = ((size_t)g * a.B + b) * Ch * HW + pix;
+        cp += base;
+        cop += base;
+        hop += ((size_t)g * a.B + b) * (size_t)a.hos + pix;
+      }
+      float cprev[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) cprev[u] = ok ? __ldg(cp + (size_t)(4 * u) * HW) : 0.f;
+      PROF_STAMP(t1);
+      if (!waited) {
+        mbar_wait(&tfull[buf], ph);
+        tc_fence_after();
+        waited = true;
+      }
+      PROF_STAMP(t2);
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kTileT + chunk * 32), v);
+      tmem_ld_wait();
+      if (lane < Ch) {
+        float* xr = X + ((size_t)q * Ch + lane) * kXPitch;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xr[j] = v[j];
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+      PROF_STAMP(t3);
+      if (ok) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int ch = q + 4 * u;
+          const float* xc = X + ch * kXPitch + lane;
+          const float ig = sigmoid_f(xc[0 * Ch * kXPitch] + sbias[ch]), fg = sigmoid_f(xc[1 * Ch * kXPitch] + sbias[Ch + ch]);
+          const float og = sigmoid_f(xc[2 * Ch * kXPitch] + sbias[2 * Ch + ch]), g_ = tanh_f(xc[3 * Ch * kXPitch] + sbias[3 * Ch + ch]);
+          const float cn = fg * cprev[u] + ig * g_;       // src/convLSTM.py:53
+          cop[(size_t)(4 * u) * HW] = cn;
+          hop[(size_t)(4 * u) * HW] = og * tanh_f(cn);     // :54
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");  // the buffer is rewritten by the next chunk
+#ifdef JAF_GROUPED_PROFILE
+      {
+        const unsigned long long t4 = gtime();
+        w_pre += t1 - t0;
+        w_f += t2 - t1;
+        w_dump += t3 - t2;
+        w_comb += t4 - t3;
+      }
+#endif
+    }
+    if (!waited) mbar_wait(&tfull[buf], ph);  // a set without a chunk in this (short, last) tile still tracks the phase
+    tc_fence_before();
+    mbar_arrive(&tempty[buf]);
+  }
+#ifdef JAF_GROUPED_PROFILE
+  if (lane == 0 && set == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+    printf("cta %d epilogue warp %d: total %llu ns | pre %llu, wait tfull %llu, dump+barrier %llu, combine+barrier %llu\n", blockIdx.x,
+           warp, gtime() - t_begin, w_pre, w_f, w_dump, w_comb);
+#endif
+}
+
+// =====================================================================================
+// Persistent, warp-specialised flavour of the operand-swapped kernel (round-2 verdict item 5).  The per-CTA timers of
+// k_convlstm_grouped_t put a 256-pixel tile at ~6 us of staging + ~8.5 us of MMAs (bound by the 3-slot weight ring:
+// each refill waits for an L2 round trip) + ~10 us of epilogue, run one after the other with only two CTAs per SM to
+// overlap them: the tensor pipe is 28 % active.  Here ONE CTA per SM walks a contiguous run of tiles and the three
+// phases of consecutive tiles overlap:
+//   warp 0        MMA issue: waits for the staged pixels of tile i and a free accumulator, issues the 3*S MMAs
+//   warp 1        weight stream: cp.async.bulk of one k-step (8 KB) per slot through a deep ring (8..16 slots), running
+//                 ahead across tile boundaries
+//   warps 2..11   stage the pixel window of tile i+1 (fp32 NCHW -> hi/lo bf16) into the other of two buffers
+//   warps 12..23  gate epilogue of tile i-1 from the other of two 256-column TMEM accumulators (3 sets of 4 warps)
+// Same arithmetic, same order of accumulation per output as k_convlstm_grouped_t: bit-identical results.
+// =====================================================================================
+__global__ void __launch_bounds__(kThreadsP, 1)
+k_convlstm_grouped_p(const GArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const uint32_t pbuf_bytes = (2u * a.a_half + 127u) & ~127u;
+  uint8_t* sP = smem;                                    // 2 x pixels: [hi | lo] x [Ctp/8 chunks][R rows][16 B]
+  float* sX = reinterpret_cast<float*>(smem + 2 * pbuf_bytes);  // kEpiSets x [4 gates][Ch][kXPitch]
+  const uint32_t xset_floats = 4u * (uint32_t)a.Ch * kXPitch + 4u * (uint32_t)a.Ch;  // + the cell's bias
+  uint8_t* sW = smem + 2 * pbuf_bytes + ((kEpiSets * xset_floats * 4u + 127u) & ~127u);  // ring x one k-step
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)a.ring * kStepBytesT);
+  uint64_t* wfull = bars;                     // [ring] bulk copy -> MMA
+  uint64_t* wempty = bars + kMaxRingP;        // [ring] MMA -> bulk copy
+  uint64_t* pfull = bars + 2 * kMaxRingP;     // [2] stagers -> MMA
+  uint64_t* pempty = pfull + 2;               // [2] MMA -> stagers
+  uint64_t* tfull = pfull + 4;                // [2] MMA -> epilogue
+  uint64_t* tempty = pfull + 6;               // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long first = (long)blockIdx.x * a.ntiles / gridDim.x;
+  const int n_here = (int)((long)(blockIdx.x + 1) * a.ntiles / gridDim.x - first);
+  const long p_end = a.Q - a.Wp - 1;  // one past the last output position of a cell
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.ring; ++s) {
+      mbar_init(&wfull[s], 1);
+      mbar_init(&wempty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&pfull[s], kStagerWarps * 32);
+      mbar_init(&pempty[s], 1);
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], kEpiSets * 4 * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+
+  if (warp == 0) {
+    // ===================== MMA issue =====================
+    const bool leader = lane == 0;
+    const uint32_t R = (uint32_t)a.R, Wp = (uint32_t)a.Wp;
+    const int spt = a.Ctp / 16, S = a.S, ring = a.ring;
+    const uint64_t wd0 = desc_noswz(smem_u32(sW), kRowsT * 16u), pd0 = desc_noswz(smem_u32(sP), R * 16u);
+    const uint32_t w_top = (uint32_t)(wd0 >> 32), p_top = (uint32_t)(pd0 >> 32);
+    const uint32_t w0 = (uint32_t)wd0, p_hi0 = (uint32_t)pd0, p_lo_delta = a.a_half >> 4;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileT >> 3) << 17) | ((uint32_t)(kRowsT >> 4) << 24);
+    int slot = 0;
+    uint32_t wph = 0;
+    PROF_DECL(w_t);
+    PROF_DECL(w_p);
+    PROF_DECL(w_w);
+    PROF_STAMP(t_begin);
+    for (int i = 0; i < n_here; ++i) {
+      const int buf = i & 1;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      PROF_ACC(w_t, mbar_wait(&tempty[buf], ph ^ 1u));
+      PROF_ACC(w_p, mbar_wait(&pfull[buf], ph));
+      tc_fence_after();
+      const uint32_t tm = tmem_base + (uint32_t)buf * kTileT;
+      const uint32_t pb = p_hi0 + (uint32_t)buf * (pbuf_bytes >> 4);
+      int kc = 0, kx = 0, ky = 0;
+      uint32_t accf = 0;
+      for (int ks = 0; ks < S; ++ks) {
+        PROF_ACC(w_w, mbar_wait(&wfull[slot], wph));
+        tc_fence_after();
+        const uint32_t wh = w0 + (uint32_t)slot * (uint32_t)(kStepBytesT >> 4);
+        const uint32_t ph_ = pb + (uint32_t)(kc * 2) * R + (uint32_t)ky * Wp + (uint32_t)kx;
+        if (elect_one()) umma_split3(tm, wh, wh + 2u * kRowsT, w_top, ph_, ph_ + p_lo_delta, p_top, idesc, accf);
+        if (leader) umma_commit(&wempty[slot]);
+        accf = 1u;
+        if (++slot == ring) {
+          slot = 0;
+          wph ^= 1u;
+        }
+        if (++kc == spt) {
+          kc = 0;
+          if (++kx == 3) {
+            kx = 0;
+            ++ky;
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(&pempty[buf]);
+        umma_commit(&tfull[buf]);
+      }
+    }
+#ifdef JAF_GROUPED_PROFILE
+    if (leader && (blockIdx.x == 0 || blockIdx.x == 77))
+      printf("cta %d mma: %d tiles, total %llu ns | wait tempty %llu, pfull %llu, wfull %llu\n", blockIdx.x, n_here,
+             gtime() - t_begin, w_t, w_p, w_w);
+#endif
+  } else if (warp == 1) {
+    // ===================== weight stream =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t wph = 0;
+      for (int i = 0; i < n_here; ++i) {
+        const int g = (int)((first + i) / a.tiles_per_group);
+        const uint8_t* wg = a.wpack + (size_t)g * a.S * kStepBytesT;
+        for (int ks = 0; ks < a.S; ++ks) {
+          mbar_wait(&wempty[slot], wph ^ 1u);
+          mbar_expect_tx(&wfull[slot], kStepBytesT);
+          bulk_g2s(sW + (size_t)slot * kStepBytesT, wg + (size_t)ks * kStepBytesT, kStepBytesT, &wfull[slot]);
+          if (++slot == a.ring) {
+            slot = 0;
+            wph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp < kEpiWarp0) {
+    // ===================== stage the pixel rows: thread = row, every channel of the row in flight at once =====================
+    const size_t HW = (size_t)a.H * a.W;
+    const int wid = threadIdx.x - kStagerWarp0 * 32;
+    PROF_DECL(w_e);
+    PROF_STAMP(t_begin);
+    for (int i = 0; i < n_here; ++i) {
+      const int buf = i & 1;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const long tile = first + i;
+      const int g = (int)(tile / a.tiles_per_group);
+      const long p0 = (long)a.Wp + 1 + (tile - (long)g * a.tiles_per_group) * kTileT;
+      const long q0 = p0 - a.Wp - 1;
+      uint8_t* dstb = sP + (size_t)buf * pbuf_bytes;
+      PROF_ACC(w_e, mbar_wait(&pempty[buf], ph ^ 1u));
+      for (int r = wid; r < a.R; r += kStagerWarps * 32) {
+        const long q = q0 + r;
+        bool inside = q < a.Q;
+        size_t pix = 0;
+        uint32_t b = 0;
+        if (inside) {
+          uint32_t rem, xp, ub;
+          const uint32_t u = fdiv((uint32_t)q, a.d_hpwp, rem);  // (image, band)
+          const uint32_t yp = fdiv(rem, a.d_wp, xp);
+          b = fdiv(u, a.d_nb, ub);
+          const int x = (int)ub * a.Wb + (int)xp - 1;  // a band's halo columns are its neighbours' pixels
+          inside = x >= 0 && x < a.W && yp >= 1 && (int)yp <= a.H;
+          pix = (size_t)(yp - 1) * a.W + (size_t)x;
+        }
+        const float* xb = a.x + ((size_t)g * a.B + b) * (size_t)a.xs + pix;
+        const float* hb = a.h + ((size_t)g * a.B + b) * (size_t)a.hs + pix;
+        for (int c0 = 0; c0 < a.Ctp; c0 += 32) {  // batches of 32 channels: all their loads are issued before the first use
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int ch = c0 + e;
+            float val = 0.f;
+            if (inside && ch < a.Ct) val = ch < a.Cin ? __ldg(xb + (size_t)ch * HW) : __ldg(hb + (size_t)(ch - a.Cin) * HW);
+            v[e] = val;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c0 + 8 * u < a.Ctp) {
+              uint4 hi, lo;
+              split2(v[8 * u + 0], v[8 * u + 1], hi.x, lo.x);
+              split2(v[8 * u + 2], v[8 * u + 3], hi.y, lo.y);
+              split2(v[8 * u + 4], v[8 * u + 5], hi.z, lo.z);
+              split2(v[8 * u + 6], v[8 * u + 7], hi.w, lo.w);
+              uint8_t* dst = dstb + ((size_t)(c0 / 8 + u) * a.R + r) * 16;
+              *reinterpret_cast<uint4*>(dst) = hi;
+              *reinterpret_cast<uint4*>(dst + a.a_half) = lo;
+            }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&pfull[buf]);
+    }
+#ifdef JAF_GROUPED_PROFILE
+    if (wid == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+      printf("cta %d stager: total %llu ns | wait pempty %llu\n", blockIdx.x, gtime() - t_begin, w_e);
+#endif
+  } else {
+    // ===================== epilogue: sets of four warps (one warp per gate / TMEM lane quarter) =====================
+    const int nu = a.Ch >> 2;
+    switch (nu) {
+      case 1: epilogue_role_p<1>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
+      case 2: epilogue_role_p<2>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
+      case 3: epilogue_role_p<3>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
+      case 4: epilogue_role_p<4>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
+      case 5: epilogue_role_p<5>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
+      case 6: epilogue_role_p<6>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
+      case 7: epilogue_role_p<7>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
+      default: epilogue_role_p<8>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -730,11 +1092,12 @@ k_gpack_weight_t(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, i
 // Measured on the reference pyramid (24 cells, B = 1; profiles/r02_convlstm_grouped.jsonl): 24 channels @100^2 0.133 ms
 // swapped vs 0.164 ms, @50^2 0.041 vs 0.048; 12 channels @200^2 0.368 vs 0.280 (only 12 of the 32 lanes of each epilogue
 // warp hold a channel, and the per-CTA timers put 10 of 26 us in the exchange epilogue) -> swapped for 16 < Ch <= 32.
-// JAF_CG_SWAP: 0 never, 1 (default) by the rule above, 2 every cell with Ch <= 32.
+// With the persistent kernel (k_convlstm_grouped_p) the 12-channel level is faster swapped as well (0.19 vs 0.28 ms).
+// JAF_CG_SWAP: 0 never, 1 only 16 < Ch <= 32, 2 (default) every cell with Ch <= 32.
 bool grouped_swapped(int Ch) {
   static const int mode = [] {
     const char* e = getenv("JAF_CG_SWAP");
-    return e == nullptr ? 1 : atoi(e);
+    return e == nullptr ? 2 : atoi(e);
   }();
   if (mode == 0 || Ch > 32) return false;
   return mode == 2 || Ch > 16;
@@ -881,7 +1244,8 @@ static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_coun
 
 // Launch plan of the operand-swapped kernel: the geometry of plan_grouped with 256-pixel tiles, one accumulator tile
 // per CTA and two CTAs per SM.
-static int plan_grouped_t(int G, int B, int Cin, int Ch, int H, int W, GArgs& a, size_t& smem, long& grid) {
+static int plan_grouped_t(int G, int B, int Cin, int Ch, int H, int W, int sm_count, GArgs& a, size_t& smem, long& grid,
+                          bool& persistent) {
   a.G = G; a.B = B; a.Cin = Cin; a.Ch = Ch; a.H = H; a.W = W;
   a.xs = (long)Cin * H * W;
   a.hs = a.hos = (long)Ch * H * W;
@@ -914,6 +1278,41 @@ static int plan_grouped_t(int G, int B, int Cin, int Ch, int H, int W, GArgs& a,
   const size_t pix = ((size_t)(2u * a.a_half > (uint32_t)(4 * kXSetFloats * 4) ? 2u * a.a_half : (uint32_t)(4 * kXSetFloats * 4)) + 127) & ~(size_t)127;
   smem = pix + (size_t)kRing * a.stage_bytes + 256 + 128;
   grid = (long)G * a.tiles_per_group;
+  a.ntiles = grid;
+  // persistent flavour: two pixel buffers + the exchange buffers of the three epilogue sets + a weight ring of >= 4 k-steps
+  static const int persist_mode = [] {
+    const char* e = getenv("JAF_CG_PERSIST");
+    return e ? atoi(e) : 1;
+  }();
+  persistent = false;
+  if (a.Q >= (1L << 31)) {
+    jaf::set_error("jaf_convlstm_step_grouped: batch too large for 32-bit positions");
+    return JAF_ERR_UNSUPPORTED;
+  }
+  if (persist_mode != 0 && (uint32_t)a.R * 16u < (1u << 18) && grid < (1L << 31)) {
+    const size_t pbuf = ((size_t)2 * a.a_half + 127) & ~(size_t)127;
+    const size_t xb = ((size_t)kEpiSets * (4 * Ch * kXPitch + 4 * Ch) * 4 + 127) & ~(size_t)127;
+    auto mk = [](int d) {
+      FastDiv f;
+      f.d = (uint32_t)d;
+      const uint64_t m = (1ull << 32) / (uint64_t)d;
+      f.m = m > 0xffffffffull ? 0xffffffffu : (uint32_t)m;
+      return f;
+    };
+    a.d_hpwp = mk(a.HpWp);
+    a.d_wp = mk(a.Wp);
+    a.d_nb = mk(a.nb);
+    const size_t fixed = 2 * pbuf + xb + (2 * kMaxRingP + 9) * 8 + 128;
+    if (fixed + 4 * (size_t)kStepBytesT <= (size_t)kMaxSmem) {
+      size_t ring = ((size_t)kMaxSmem - fixed) / kStepBytesT;
+      if (ring > (size_t)kMaxRingP) ring = kMaxRingP;
+      a.ring = (int)ring;
+      persistent = true;
+      smem = fixed + ring * kStepBytesT;
+      grid = a.ntiles < sm_count ? a.ntiles : sm_count;
+      return JAF_OK;
+    }
+  }
   if (smem > (size_t)kHalfSmem || (uint32_t)a.R * 16u >= (1u << 18) || grid >= (1L << 31)) {
     jaf::set_error("jaf_convlstm_step_grouped: cell does not fit the operand-swapped plan (Cin=%d Ch=%d W=%d)", Cin, Ch, W);
     return JAF_ERR_UNSUPPORTED;
@@ -929,7 +1328,8 @@ int jaf_convlstm_grouped_supported(int G, int B, int Cin, int Ch, int H, int W) 
   int threads;
   size_t smem;
   long grid;
-  if (grouped_swapped(Ch)) return plan_grouped_t(G, B, Cin, Ch, H, W, a, smem, grid) == JAF_OK ? 1 : 0;
+  bool persistent;
+  if (grouped_swapped(Ch)) return plan_grouped_t(G, B, Cin, Ch, H, W, sms, a, smem, grid, persistent) == JAF_OK ? 1 : 0;
   return plan_grouped(G, B, Cin, Ch, H, W, sms, a, threads, smem, grid) == JAF_OK ? 1 : 0;
 }
 
@@ -957,10 +1357,16 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
     static jaf::PerDeviceOnce attr_once_t;
     if (!attr_once_t.done(dev)) {
       JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kHalfSmem));
+      JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_p, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
       attr_once_t.mark(dev);
     }
-    const int stt = plan_grouped_t(G, B, Cin, Ch, H, W, a, smem, grid);
+    bool persistent;
+    const int stt = plan_grouped_t(G, B, Cin, Ch, H, W, sm_count, a, smem, grid, persistent);
     if (stt != JAF_OK) return stt;
+    if (persistent) {
+      k_convlstm_grouped_p<<<(unsigned)grid, kThreadsP, smem, jaf::as_stream(stream)>>>(a);
+      return jaf::finish_launch("k_convlstm_grouped_p");
+    }
     k_convlstm_grouped_t<<<(unsigned)grid, kThreadsT, smem, jaf::as_stream(stream)>>>(a);
     return jaf::finish_launch("k_convlstm_grouped_t");
   }
@@ -996,10 +1402,12 @@ int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const flo
     static jaf::PerDeviceOnce attr_once_t;
     if (!attr_once_t.done(dev)) {
       JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kHalfSmem));
+      JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_p, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
       attr_once_t.mark(dev);
     }
   }
-  const int st = swapped ? plan_grouped_t(G, B, Cin, Ch, H, W, a, smem, grid)
+  bool persistent = false;
+  const int st = swapped ? plan_grouped_t(G, B, Cin, Ch, H, W, sm_count, a, smem, grid, persistent)
                          : plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, threads, smem, grid);
   if (st != JAF_OK) return st;
   const long HW = (long)H * W;
@@ -1016,7 +1424,8 @@ int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const flo
     a.h_out = h_seq + (long)t * Ch * HW;
     a.hos = (long)T * Ch * HW;
     a.c_out = cbuf[t & 1];
-    if (swapped) k_convlstm_grouped_t<<<(unsigned)grid, kThreadsT, smem, jaf::as_stream(stream)>>>(a);
+    if (swapped && persistent) k_convlstm_grouped_p<<<(unsigned)grid, kThreadsP, smem, jaf::as_stream(stream)>>>(a);
+    else if (swapped) k_convlstm_grouped_t<<<(unsigned)grid, kThreadsT, smem, jaf::as_stream(stream)>>>(a);
     else k_convlstm_grouped<<<(unsigned)grid, threads, smem, jaf::as_stream(stream)>>>(a);
   }
   return jaf::finish_launch("k_convlstm_grouped (sequence)", T);
