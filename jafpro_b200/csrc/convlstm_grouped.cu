@@ -66,6 +66,7 @@ struct GArgs {
   int S, KS, nstages;
   int tiles_per_group;
   FastDiv d_hpwp, d_wp, d_nb;  // persistent kernel: position -> (image, band, row, column) without divisions
+  int C8, U;         // persistent kernel: 8-channel chunks of the staged window, K units (9 * C8)
   int ring;          // persistent kernel: weight k-steps in flight
   long ntiles;       // persistent kernel: G * tiles_per_group
   uint32_t idesc, a_half, stage_bytes, tmem_cols;
@@ -453,24 +454,44 @@ k_gpack_weight(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, int
 
 
 // =====================================================================================
-// Operand-swapped flavour for the narrow cells (4*Ch <= 128: the 12- and 24-channel levels of the reference pyramid,
-// which hold 85 % of its pixels).  In k_convlstm_grouped the pixels are the M side (128 rows) and the gate rows the N
-// side: an MMA costs 128 cycles whatever N is (tools/probes/umma_probe.cu), so with N = 48 / 96 the tensor pipe does
-// 19 / 38 % of its work per issued MMA and the level is bound by the issue rate (ncu: tensor pipe 16-20 % active).
-// Here the WEIGHTS are the A operand (M = 128 rows = 4 gates x 32 channel slots, zero rows for missing channels) and 256
-// PIXELS the B operand (N = 256): the same 128 cycles now cover 256 pixels instead of 128.  Both operands keep the
-// K-major no-swizzle layout, so the staged pixel window and the packed weight image are used as they are — the roles
-// swap in the descriptors only.  The accumulator comes out transposed (TMEM lane = gate row, column = pixel): lane
-// quarter q holds gate q (i, f, o, g) of channel `lane`, so four warps (one per quarter) apply bias + activation to
-// their gate, exchange the results through shared memory (the staging buffer, free once the MMAs are done) and then
-// combine c' = f*c + i*g, h' = o*tanh(c') with thread = pixel (coalesced NCHW accesses).
+// Operand-swapped, persistent, warp-specialised flavour for the narrow cells (Ch <= 32, Cin + Ch <= 48: the 12- and
+// 24-channel levels of the reference pyramid, which hold 85 % of its pixels).
+//
+// Why swapped.  In k_convlstm_grouped the pixels are the M side (128 rows) and the gate rows the N side: an MMA costs
+// 128 cycles whatever N is (tools/probes/umma_probe.cu), so with N = 48 / 96 the tensor pipe does 19 / 38 % of its work
+// per issued MMA (ncu: tensor pipe 16-20 % active).  Here the WEIGHTS are the A operand (M = 128, of which the 4*Ch rows
+// `gate*Ch + channel` — the reference's own row order, :46 — are real) and 256 PIXELS the B operand (N = 256): the same
+// 128 cycles cover 256 pixels.  Both operands keep the K-major no-swizzle layout, so the staged pixel window serves all
+// nine taps exactly as before.
+//
+// K is flattened over (8-channel chunk, tap): a k-step is two "units" of 8 channels, each with its own tap shift — the
+// two K chunks of a no-swizzle descriptor may lie anywhere (LBO), so unit (chunk c, tap t) is simply the address
+// c*R + shift(t).  Units are ordered chunk-major, which keeps LBO positive.  24 input channels x 9 taps are 27 units =
+// 14 k-steps instead of 18 with 16-channel k-steps (Ctp = 32), and the staged window holds 3 chunks instead of 4.
+//
+// Weight rows are packed densely: one k-step is [hi | lo][2 units][4*Ch rows][16 B] = 256*Ch bytes (3 KB at Ch = 12
+// instead of 8 KB for 128 padded rows).  The M = 128 descriptor reads on into whatever follows the 4*Ch rows; those
+// accumulator rows (TMEM lanes >= 4*Ch) are never read.
+//
+// Why persistent.  A 256-pixel tile costs ~3 us of staging, ~3-5 us of MMAs and ~4 us of gate epilogue; run one after
+// the other by two CTAs per SM (the first swapped kernel) the tensor pipe was 28 % active.  ONE CTA per SM now walks a
+// contiguous run of tiles and the phases of consecutive tiles overlap:
+//   warp 0        MMA issue: waits for the staged pixels of tile i and a free accumulator, issues the 3*S MMAs
+//   warp 1        weight stream: one cp.async.bulk per k-step through a deep ring, running ahead across tile boundaries
+//   warps 2..11   stage the pixel window of tile i+1 (thread = row, every channel in flight; fp32 NCHW -> hi/lo bf16)
+//   warps 12..27  gate epilogue of tile i-1 from the other of two 256-column TMEM accumulators: four sets of four warps.
+//                 Warp q of a set may read TMEM lane quarter q only, and a lane holds ONE gate row for 32 pixels, so the
+//                 set transposes through shared memory: each warp dumps its RAW rows, then thread = pixel applies bias,
+//                 the five activations and c' = f*c + i*g, h' = o*tanh(c') for channels q, q+4, ... on full warps with
+//                 coalesced NCHW accesses.  The previous cell state of the NEXT chunk is loaded one chunk ahead.
 // =====================================================================================
-constexpr int kThreadsT = 512;       // warp 0: weights + MMA issue; warps 1..15 stage; all 16 warps = four epilogue sets
-constexpr int kTileT = 256;          // pixels (flattened padded positions) per CTA = N of the MMA
-constexpr int kRowsT = 128;          // A rows: gate * 32 + channel slot
-constexpr int kStepBytesT = 2 * 2 * kRowsT * 16;  // one k-step of packed weights: [hi | lo][2 chunks][128 rows][16 B]
-constexpr int kXPitch = 33;          // floats per (gate, channel) row of the exchange buffer (32 pixels + 1: no bank conflicts)
-constexpr int kXSetFloats = 4 * 32 * kXPitch;  // upper bound of one set's exchange buffer ([4 gates][Ch <= 32][kXPitch])
+constexpr int kTileT = 256;          // pixels (flattened padded positions) per tile = N of the MMA
+constexpr int kXPitch = 33;          // floats per gate row of the exchange buffer (32 pixels + 1: no bank conflicts)
+constexpr int kThreadsP = 896;
+constexpr int kStagerWarp0 = 2, kStagerWarps = 10, kEpiWarp0 = 12, kEpiSets = 4;
+constexpr int kChunksPerSet = kTileT / 32 / kEpiSets;  // 2
+constexpr int kMaxRingP = 24;
+constexpr int kRingPad = 2048;       // the M = 128 descriptor of the last ring slot reads up to 128 rows x 16 B past a unit
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -486,238 +507,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(kThreadsT, 2)
-k_convlstm_grouped_t(const GArgs a) {
-  PROF_STAMP(t_start);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  uint8_t* sP = smem;                               // pixels: [hi | lo] x [Ctp/8 chunks][R rows][16 B]; later the exchange buffers
-  const uint32_t pix_bytes = max(2u * a.a_half, (uint32_t)(4 * kXSetFloats * 4));
-  uint8_t* sW = smem + ((pix_bytes + 127u) & ~127u);  // weight ring: kRing x KS k-steps
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kRing * a.stage_bytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kRing;
-  uint64_t* aready_bar = bars + 2 * kRing;
-  uint64_t* tfull_bar = bars + 2 * kRing + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRing + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x % a.tiles_per_group;
-  const int g = blockIdx.x / a.tiles_per_group;
-  const long p_end = a.Q - a.Wp - 1;                       // one past the last output position
-  const long p0 = (long)a.Wp + 1 + (long)t * kTileT;       // first output position of this CTA
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kRing; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(aready_bar, blockDim.x - 32);
-    mbar_init(tfull_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
-
-  if (warp == 0) {
-    // ===================== weight stream + MMA issue =====================
-    const bool leader = lane == 0;
-    const uint8_t* wg = a.wpack + (size_t)g * a.S * kStepBytesT;
-    const uint32_t stage_bytes = a.stage_bytes;
-    const int nstages = a.nstages, KS = a.KS;
-    auto load_stage = [&](int st, int slot) {
-      mbar_expect_tx(&full_bar[slot], stage_bytes);
-      bulk_g2s(sW + (size_t)slot * stage_bytes, wg + (size_t)st * stage_bytes, stage_bytes, &full_bar[slot]);
-    };
-    const int pre = min(kRing, nstages);
-    if (leader) {
-      for (int st = 0; st < pre; ++st) load_stage(st, st);
-    }
-    const uint32_t R = (uint32_t)a.R, Wp = (uint32_t)a.Wp;
-    const int spt = a.Ctp / 16;
-    // A = weights: 128 rows, the two 8-element K chunks 128 rows apart; B = pixels: chunks R rows apart
-    const uint64_t wd0 = desc_noswz(smem_u32(sW), kRowsT * 16u), pd0 = desc_noswz(smem_u32(sP), R * 16u);
-    const uint32_t w_top = (uint32_t)(wd0 >> 32), p_top = (uint32_t)(pd0 >> 32);
-    const uint32_t w0 = (uint32_t)wd0, p_hi0 = (uint32_t)pd0, p_lo_delta = a.a_half >> 4;
-    const uint32_t stage_u = stage_bytes >> 4;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileT >> 3) << 17) | ((uint32_t)(kRowsT >> 4) << 24);
-    mbar_wait(aready_bar, 0);
-    tc_fence_after();
-    PROF_STAMP(t_aready);
-    int kc = 0, kx = 0, ky = 0;
-    uint32_t accf = 0;
-    for (int st = 0; st < nstages; ++st) {
-      const int slot = st % kRing;
-      mbar_wait(&full_bar[slot], (uint32_t)(st / kRing) & 1u);
-      tc_fence_after();
-      uint32_t wh = w0 + (uint32_t)slot * stage_u;
-      for (int j = 0; j < KS; ++j, wh += (uint32_t)(kStepBytesT >> 4)) {
-        const uint32_t ph = p_hi0 + (uint32_t)(kc * 2) * R + (uint32_t)ky * Wp + (uint32_t)kx;
-        // w_hi*x_hi + w_hi*x_lo + w_lo*x_hi   (lo half of a k-step: 2 chunks x 128 rows = 256 descriptor units further)
-        if (elect_one()) umma_split3(tmem_base, wh, wh + 2u * kRowsT, w_top, ph, ph + p_lo_delta, p_top, idesc, accf);
-        accf = 1u;
-        if (++kc == spt) {
-          kc = 0;
-          if (++kx == 3) {
-            kx = 0;
-            ++ky;
-          }
-        }
-      }
-      if (leader) umma_commit(&empty_bar[slot]);
-      if (st >= 1 && st - 1 + kRing < nstages) {
-        const int ps = (st - 1) % kRing;
-        mbar_wait(&empty_bar[ps], (uint32_t)((st - 1) / kRing) & 1u);
-        if (leader) load_stage(st - 1 + kRing, ps);
-      }
-    }
-    if (leader) umma_commit(tfull_bar);
-#ifdef JAF_GROUPED_PROFILE
-    PROF_STAMP(t_issued);
-    mbar_wait(tfull_bar, 0);
-    PROF_STAMP(t_done);
-    if ((blockIdx.x == 0 || blockIdx.x == 1000) && leader)
-      printf("cta %d (swapped): R=%d nstages=%d | staged at %llu ns, mma issued +%llu, mma done +%llu\n", blockIdx.x, a.R,
-             a.nstages, t_aready - t_start, t_issued - t_aready, t_done - t_aready);
-#endif
-  } else {
-    // ===================== stage the pixel rows (15 warps): identical to k_convlstm_grouped =====================
-    const size_t HW = (size_t)a.H * a.W;
-    {
-      const int wid = threadIdx.x - 32;
-      const long q0 = p0 - a.Wp - 1;
-      const int npairs = a.Ctp / 16;
-      const int items = a.R * npairs;
-      const int nworkers = (int)blockDim.x - 32;
-      for (int it = wid; it < items; it += nworkers) {
-        const int cp = it / a.R, i = it - cp * a.R;
-        const long q = q0 + i;
-        bool inside = q < a.Q;
-        size_t pix = 0;
-        int b = 0;
-        if (inside) {
-          const int u = (int)((uint32_t)q / (uint32_t)a.HpWp);  // Q < 2^31 (checked by the planner)
-          const int rem = (int)((uint32_t)q - (uint32_t)u * (uint32_t)a.HpWp);
-          const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
-          b = u / a.nb;
-          const int x = (u - b * a.nb) * a.Wb + xp - 1;
-          inside = x >= 0 && x < a.W && yp >= 1 && yp <= a.H;
-          pix = (size_t)(yp - 1) * a.W + (size_t)x;
-        }
-        const float* xb = a.x + ((size_t)g * a.B + b) * (size_t)a.xs + pix;
-        const float* hb = a.h + ((size_t)g * a.B + b) * (size_t)a.hs + pix;
-        float v[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int ch = cp * 16 + e;
-          float val = 0.f;
-          if (inside && ch < a.Ct) val = ch < a.Cin ? __ldg(xb + (size_t)ch * HW) : __ldg(hb + (size_t)(ch - a.Cin) * HW);
-          v[e] = val;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          uint4 hi, lo;
-          split2(v[8 * u + 0], v[8 * u + 1], hi.x, lo.x);
-          split2(v[8 * u + 2], v[8 * u + 3], hi.y, lo.y);
-          split2(v[8 * u + 4], v[8 * u + 5], hi.z, lo.z);
-          split2(v[8 * u + 6], v[8 * u + 7], hi.w, lo.w);
-          uint8_t* dst = sP + ((size_t)(cp * 2 + u) * a.R + i) * 16;
-          *reinterpret_cast<uint4*>(dst) = hi;
-          *reinterpret_cast<uint4*>(dst + a.a_half) = lo;
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(aready_bar);
-    }
-  }
-  // ===================== epilogue: four sets of four warps (one warp per gate / TMEM lane quarter) =====================
-  // All 16 warps take part (the MMA warp joins once its last commit is out).  Per 32-pixel chunk: (0) the combine
-  // stage's cell-state loads are issued first (their addresses do not depend on the accumulator), (1) each warp applies
-  // bias + activation to its gate of channel `lane` and writes the exchange buffer, (2) thread = pixel combines
-  // c' = f*c + i*g, h' = o*tanh(c') for channels q, q + 4, ...
-  {
-    const size_t HW = (size_t)a.H * a.W;
-    const int q = warp & 3, set = warp >> 2;
-    const int Ch = a.Ch;
-    float* X = reinterpret_cast<float*>(sP) + (size_t)set * (4 * Ch * kXPitch);  // [gate][channel][kXPitch]
-    float bias = 0.f;
-    if (a.bias != nullptr && lane < Ch) bias = __ldg(a.bias + (size_t)g * 4 * Ch + q * Ch + lane);  // rows gate*Ch + ch (:46)
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
-    for (int chunk = set; chunk < kTileT / 32; chunk += 4) {
-      if (p0 + (long)chunk * 32 >= p_end) break;  // uniform over the set
-      // (0) where this thread's pixel lives + its previous cell state (channels q, q+4, ... : at most 8 per thread)
-      const long p = p0 + (long)chunk * 32 + lane;
-      bool ok = p < p_end;
-      size_t base = 0, hbase = 0;
-      if (ok) {
-        const int un = (int)((uint32_t)p / (uint32_t)a.HpWp);
-        const int rem = (int)((uint32_t)p - (uint32_t)un * (uint32_t)a.HpWp);
-        const int yp = rem / a.Wp, xp = rem - yp * a.Wp;
-        const int b = un / a.nb;
-        const int x = (un - b * a.nb) * a.Wb + xp - 1;
-        ok = xp >= 1 && xp <= a.Wb && x < a.W && yp >= 1 && yp <= a.H;
-        base = ((size_t)g * a.B + b) * a.Ch * HW + (size_t)(yp - 1) * a.W + (size_t)x;
-        hbase = ((size_t)g * a.B + b) * (size_t)a.hos + (size_t)(yp - 1) * a.W + (size_t)x;
-      }
-      float cprev[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int ch = q + 4 * u;
-        cprev[u] = (ok && ch < Ch) ? __ldg(a.c + base + (size_t)ch * HW) : 0.f;
-      }
-      // (1) this warp's gate of channel `lane`, 32 pixels: bias + activation -> exchange buffer
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), v);
-      tmem_ld_wait();
-      if (lane < Ch) {
-        float* xr = X + ((size_t)q * Ch + lane) * kXPitch;
-        if (q < 3) {  // hoisted: with the select inside the loop ptxas emits a branch per element (no ILP across the 32)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) xr[j] = sigmoid_f(v[j] + bias);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) xr[j] = tanh_f(v[j] + bias);
-        }
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
-      // (2) combine, thread = pixel
-      if (ok) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int ch = q + 4 * u;
-          if (ch < Ch) {
-            const float ig = X[((size_t)0 * Ch + ch) * kXPitch + lane], fg = X[((size_t)1 * Ch + ch) * kXPitch + lane];
-            const float og = X[((size_t)2 * Ch + ch) * kXPitch + lane], g_ = X[((size_t)3 * Ch + ch) * kXPitch + lane];
-            const float cn = fg * cprev[u] + ig * g_;                  // src/convLSTM.py:53
-            a.c_out[base + (size_t)ch * HW] = cn;
-            a.h_out[hbase + (size_t)ch * HW] = og * tanh_f(cn);         // :54
-          }
-        }
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");  // the buffer is rewritten by the next chunk
-    }
-  }
-#ifdef JAF_GROUPED_PROFILE
-  if ((threadIdx.x == 128 || threadIdx.x == 32) && (blockIdx.x == 0 || blockIdx.x == 1000)) {
-    PROF_STAMP(t_end);
-    printf("cta %d (swapped): warp %d finished at %llu ns after start\n", blockIdx.x, warp, t_end - t_start);
-  }
-#endif
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
-  }
-}
-
 // n / d for n < 2^32 with m = min(floor(2^32 / d), 2^32 - 1): umulhi gives the quotient or one less
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f, uint32_t& rem) {
   uint32_t q = __umulhi(n, f.m);
@@ -729,142 +518,136 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f, uint32_t& rem) {
   return q;
 }
 
-constexpr int kThreadsP = 768;
-constexpr int kStagerWarp0 = 2, kStagerWarps = 10, kEpiWarp0 = 12, kEpiSets = 3;
-constexpr int kMaxRingP = 16;
-
-// Gate epilogue of the persistent kernel, NU = Ch / 4 channels per thread.  Per 32-pixel chunk of the accumulator:
-// (0) thread = pixel: where the pixel lives + its previous cell state (loads in flight during the next two stages);
-// (1) warp q owns TMEM lane quarter q = gate q of channel `lane`: it dumps the RAW accumulator row (32 pixels) into the
-//     set's exchange buffer — no arithmetic here, because only Ch of the 32 lanes hold a channel;
-// (2) thread = pixel, channels q, q + 4, ...: bias + the five activations + c' = f*c + i*g, h' = o*tanh(c') on full warps,
-//     the NU channels as independent instruction streams (NU is a template parameter: no per-channel branches).
+// Gate epilogue role of the persistent kernel, NU = Ch / 4 channels per thread (a template parameter, so that the NU
+// channels of the pixel stage are independent instruction streams without per-channel branches).
 template <int NU>
 __device__ __forceinline__ void epilogue_role_p(const GArgs& a, float* sX, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
                                                 long first, int n_here, long p_end) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t HW = (size_t)a.H * a.W;
   const int q = warp & 3, set = (warp - kEpiWarp0) >> 2;
-  constexpr int Ch = 4 * NU;
-  constexpr int xset_floats = 4 * Ch * kXPitch + 4 * Ch;  // [gate][channel][kXPitch] + bias [gate][channel]
+  constexpr int Ch = 4 * NU, rows = 4 * Ch;
+  constexpr int xset_floats = rows * kXPitch + rows;  // raw gate rows [gate*Ch + channel][kXPitch] + the cell's bias
   float* X = sX + (size_t)set * xset_floats;
-  float* sbias = X + 4 * Ch * kXPitch;
-  int g_bias = -1;
+  float* sbias = X + rows * kXPitch;
+  const int my_rows = rows - 32 * q;  // rows of this warp's TMEM lane quarter that exist (<= 0: nothing to dump)
+  const int nit = kChunksPerSet * n_here;
   PROF_DECL(w_f);
-  PROF_DECL(w_pre);
-  PROF_DECL(w_dump);
-  PROF_DECL(w_comb);
   PROF_STAMP(t_begin);
-  for (int i = 0; i < n_here; ++i) {
+
+  // where the pixel of (iteration, lane) lives + its previous cell state, one iteration ahead of their use
+  bool ok_c = false, ok_n = false;
+  float* cop_c = a.c_out;
+  float* hop_c = a.h_out;
+  float* cop_n = a.c_out;
+  float* hop_n = a.h_out;
+  float c_c[NU], c_n[NU];
+  int g_c = 0, g_n = 0;
+  bool act_c = false, act_n = false;
+  auto prep = [&](int it) {
+    const long tile = first + it / kChunksPerSet;
+    const int chunk = set + kEpiSets * (it % kChunksPerSet);
+    g_n = (int)(tile / a.tiles_per_group);
+    const long p0 = (long)a.Wp + 1 + (tile - (long)g_n * a.tiles_per_group) * kTileT + (long)chunk * 32;
+    act_n = p0 < p_end;  // uniform over the set
+#ifdef JAF_PROBE_SKIP_EPI
+    act_n = false;
+#endif
+    const long p = p0 + lane;
+    ok_n = p < p_end;
+    const float* cp = a.c;
+    cop_n = a.c_out;
+    hop_n = a.h_out;
+    if (ok_n) {
+      uint32_t rem, xp, ub;
+      const uint32_t un = fdiv((uint32_t)p, a.d_hpwp, rem);
+      const uint32_t yp = fdiv(rem, a.d_wp, xp);
+      const uint32_t b = fdiv(un, a.d_nb, ub);
+      const int x = (int)ub * a.Wb + (int)xp - 1;
+      ok_n = xp >= 1 && (int)xp <= a.Wb && x < a.W && yp >= 1 && (int)yp <= a.H;
+      const size_t pix = (size_t)(yp - 1) * a.W + (size_t)x + (size_t)q * HW;
+      const size_t base = ((size_t)g_n * a.B + b) * Ch * HW + pix;
+      cp += base;
+      cop_n += base;
+      hop_n += ((size_t)g_n * a.B + b) * (size_t)a.hos + pix;
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) c_n[u] = ok_n ? __ldg(cp + (size_t)(4 * u) * HW) : 0.f;
+  };
+  auto shift = [&]() {
+    ok_c = ok_n; act_c = act_n; g_c = g_n; cop_c = cop_n; hop_c = hop_n;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) c_c[u] = c_n[u];
+  };
+  if (nit > 0) prep(0);
+  int g_bias = -1;
+  for (int it = 0; it < nit; ++it) {
+    shift();
+    const int i = it / kChunksPerSet, part = it % kChunksPerSet;
     const int buf = i & 1;
     const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-    const long tile = first + i;
-    const int g = (int)(tile / a.tiles_per_group);
-    const long p0 = (long)a.Wp + 1 + (tile - (long)g * a.tiles_per_group) * kTileT;
-    if (g != g_bias) {  // set-uniform; the previous tile's last barrier has passed, the next one orders these writes
-      g_bias = g;
-      const int t4 = (warp & 3) * 32 + lane;
-      if (t4 < 4 * Ch) sbias[t4] = a.bias != nullptr ? __ldg(a.bias + (size_t)g * 4 * Ch + t4) : 0.f;  // rows gate*Ch + ch (:46)
+    const int chunk = set + kEpiSets * part;
+    if (part == 0) {
+      if (g_c != g_bias) {  // set-uniform; the last barrier of the previous chunk has passed, the next one orders the writes
+        g_bias = g_c;
+        const int t4 = q * 32 + lane;
+        if (t4 < rows) sbias[t4] = a.bias != nullptr ? __ldg(a.bias + (size_t)g_c * rows + t4) : 0.f;
+      }
+      PROF_ACC(w_f, mbar_wait(&tfull[buf], ph));
+      tc_fence_after();
     }
-    bool waited = false;
-    for (int chunk = set; chunk < kTileT / 32; chunk += kEpiSets) {
-      if (p0 + (long)chunk * 32 >= p_end) break;  // uniform over the set
-      PROF_STAMP(t0);
-      const long p = p0 + (long)chunk * 32 + lane;
-      bool ok = p < p_end;
-      const float* cp = a.c;
-      float* cop = a.c_out;
-      float* hop = a.h_out;
-      if (ok) {
-        uint32_t rem, xp, ub;
-        const uint32_t un = fdiv((uint32_t)p, a.d_hpwp, rem);
-        const uint32_t yp = fdiv(rem, a.d_wp, xp);
-        const uint32_t b = fdiv(un, a.d_nb, ub);
-        const int x = (int)ub * a.Wb + (int)xp - 1;
-        ok = xp >= 1 && (int)xp <= a.Wb && x < a.W && yp >= 1 && (int)yp <= a.H;
-        const size_t pix = (size_t)(yp - 1) * a.W + (size_t)x + (size_t)q * HW;
-        const size_t base = ((size_t)g * a.B + b) * Ch * HW + pix;
-        cp += base;
-        cop += base;
-        hop += ((size_t)g * a.B + b) * (size_t)a.hos + pix;
-      }
-      float cprev[NU];
-#pragma unroll
-      for (int u = 0; u < NU; ++u) cprev[u] = ok ? __ldg(cp + (size_t)(4 * u) * HW) : 0.f;
-      PROF_STAMP(t1);
-      if (!waited) {
-        mbar_wait(&tfull[buf], ph);
-        tc_fence_after();
-        waited = true;
-      }
-      PROF_STAMP(t2);
+    // (1) dump this warp's raw gate rows of the chunk (TMEM lane = row gate*Ch + channel, column = pixel)
+    if (act_c && my_rows > 0) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kTileT + chunk * 32), v);
       tmem_ld_wait();
-      if (lane < Ch) {
-        float* xr = X + ((size_t)q * Ch + lane) * kXPitch;
+      if (lane < my_rows) {
+        float* xr = X + (size_t)(q * 32 + lane) * kXPitch;
 #pragma unroll
         for (int j = 0; j < 32; ++j) xr[j] = v[j];
       }
+    }
+    if (part == kChunksPerSet - 1) {  // this warp has read everything it needs from the accumulator: free it early
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+    // (0') next chunk's addresses and cell-state loads: in flight during the pixel stage below
+    if (it + 1 < nit) prep(it + 1);
+    if (act_c) {
       asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
-      PROF_STAMP(t3);
-      if (ok) {
+      // (2) thread = pixel, channels q, q + 4, ...
+      if (ok_c) {
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
           const int ch = q + 4 * u;
           const float* xc = X + ch * kXPitch + lane;
           const float ig = sigmoid_f(xc[0 * Ch * kXPitch] + sbias[ch]), fg = sigmoid_f(xc[1 * Ch * kXPitch] + sbias[Ch + ch]);
           const float og = sigmoid_f(xc[2 * Ch * kXPitch] + sbias[2 * Ch + ch]), g_ = tanh_f(xc[3 * Ch * kXPitch] + sbias[3 * Ch + ch]);
-          const float cn = fg * cprev[u] + ig * g_;       // src/convLSTM.py:53
-          cop[(size_t)(4 * u) * HW] = cn;
-          hop[(size_t)(4 * u) * HW] = og * tanh_f(cn);     // :54
+          const float cn = fg * c_c[u] + ig * g_;        // src/convLSTM.py:53
+          cop_c[(size_t)(4 * u) * HW] = cn;
+          hop_c[(size_t)(4 * u) * HW] = og * tanh_f(cn);  // :54
         }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");  // the buffer is rewritten by the next chunk
-#ifdef JAF_GROUPED_PROFILE
-      {
-        const unsigned long long t4 = gtime();
-        w_pre += t1 - t0;
-        w_f += t2 - t1;
-        w_dump += t3 - t2;
-        w_comb += t4 - t3;
-      }
-#endif
     }
-    if (!waited) mbar_wait(&tfull[buf], ph);  // a set without a chunk in this (short, last) tile still tracks the phase
-    tc_fence_before();
-    mbar_arrive(&tempty[buf]);
   }
 #ifdef JAF_GROUPED_PROFILE
   if (lane == 0 && set == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-    printf("cta %d epilogue warp %d: total %llu ns | pre %llu, wait tfull %llu, dump+barrier %llu, combine+barrier %llu\n", blockIdx.x,
-           warp, gtime() - t_begin, w_pre, w_f, w_dump, w_comb);
+    printf("cta %d epilogue warp %d: total %llu ns | wait tfull %llu\n", blockIdx.x, warp, gtime() - t_begin, w_f);
 #endif
 }
 
-// =====================================================================================
-// Persistent, warp-specialised flavour of the operand-swapped kernel (round-2 verdict item 5).  The per-CTA timers of
-// k_convlstm_grouped_t put a 256-pixel tile at ~6 us of staging + ~8.5 us of MMAs (bound by the 3-slot weight ring:
-// each refill waits for an L2 round trip) + ~10 us of epilogue, run one after the other with only two CTAs per SM to
-// overlap them: the tensor pipe is 28 % active.  Here ONE CTA per SM walks a contiguous run of tiles and the three
-// phases of consecutive tiles overlap:
-//   warp 0        MMA issue: waits for the staged pixels of tile i and a free accumulator, issues the 3*S MMAs
-//   warp 1        weight stream: cp.async.bulk of one k-step (8 KB) per slot through a deep ring (8..16 slots), running
-//                 ahead across tile boundaries
-//   warps 2..11   stage the pixel window of tile i+1 (fp32 NCHW -> hi/lo bf16) into the other of two buffers
-//   warps 12..23  gate epilogue of tile i-1 from the other of two 256-column TMEM accumulators (3 sets of 4 warps)
-// Same arithmetic, same order of accumulation per output as k_convlstm_grouped_t: bit-identical results.
-// =====================================================================================
 __global__ void __launch_bounds__(kThreadsP, 1)
 k_convlstm_grouped_p(const GArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const uint32_t pbuf_bytes = (2u * a.a_half + 127u) & ~127u;
-  uint8_t* sP = smem;                                    // 2 x pixels: [hi | lo] x [Ctp/8 chunks][R rows][16 B]
-  float* sX = reinterpret_cast<float*>(smem + 2 * pbuf_bytes);  // kEpiSets x [4 gates][Ch][kXPitch]
-  const uint32_t xset_floats = 4u * (uint32_t)a.Ch * kXPitch + 4u * (uint32_t)a.Ch;  // + the cell's bias
-  uint8_t* sW = smem + 2 * pbuf_bytes + ((kEpiSets * xset_floats * 4u + 127u) & ~127u);  // ring x one k-step
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)a.ring * kStepBytesT);
+  uint8_t* sP = smem;                                    // 2 x pixels: [hi | lo] x [C8 chunks][R rows][16 B]
+  float* sX = reinterpret_cast<float*>(smem + 2 * pbuf_bytes);  // kEpiSets x ([4*Ch rows][kXPitch] + bias)
+  const uint32_t xset_floats = 4u * (uint32_t)a.Ch * (kXPitch + 1);
+  uint8_t* sW = smem + 2 * pbuf_bytes + ((kEpiSets * xset_floats * 4u + 127u) & ~127u);  // ring x one k-step (+ kRingPad)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)a.ring * a.stage_bytes + kRingPad);
   uint64_t* wfull = bars;                     // [ring] bulk copy -> MMA
   uint64_t* wempty = bars + kMaxRingP;        // [ring] MMA -> bulk copy
   uint64_t* pfull = bars + 2 * kMaxRingP;     // [2] stagers -> MMA
@@ -884,10 +667,10 @@ k_convlstm_grouped_p(const GArgs a) {
       mbar_init(&wempty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&pfull[s], kStagerWarps * 32);
+      mbar_init(&pfull[s], kStagerWarps);
       mbar_init(&pempty[s], 1);
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], kEpiSets * 4 * 32);
+      mbar_init(&tempty[s], kEpiSets * 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -903,12 +686,14 @@ k_convlstm_grouped_p(const GArgs a) {
   if (warp == 0) {
     // ===================== MMA issue =====================
     const bool leader = lane == 0;
-    const uint32_t R = (uint32_t)a.R, Wp = (uint32_t)a.Wp;
-    const int spt = a.Ctp / 16, S = a.S, ring = a.ring;
-    const uint64_t wd0 = desc_noswz(smem_u32(sW), kRowsT * 16u), pd0 = desc_noswz(smem_u32(sP), R * 16u);
+    const uint32_t R = (uint32_t)a.R, Wp = (uint32_t)a.Wp, rows = 4u * (uint32_t)a.Ch;
+    const int S = a.S, ring = a.ring, U = a.U;
+    // A = weights: 128 rows of which `rows` are packed, the two units of a k-step `rows` rows apart; B = pixels
+    const uint64_t wd0 = desc_noswz(smem_u32(sW), rows * 16u), pd0 = desc_noswz(smem_u32(sP), 0);
     const uint32_t w_top = (uint32_t)(wd0 >> 32), p_top = (uint32_t)(pd0 >> 32);
-    const uint32_t w0 = (uint32_t)wd0, p_hi0 = (uint32_t)pd0, p_lo_delta = a.a_half >> 4;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileT >> 3) << 17) | ((uint32_t)(kRowsT >> 4) << 24);
+    const uint32_t w0 = (uint32_t)wd0, p0u = (uint32_t)pd0, p_lo_delta = a.a_half >> 4;
+    const uint32_t stage_u = a.stage_bytes >> 4;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int slot = 0;
     uint32_t wph = 0;
     PROF_DECL(w_t);
@@ -922,27 +707,30 @@ k_convlstm_grouped_p(const GArgs a) {
       PROF_ACC(w_p, mbar_wait(&pfull[buf], ph));
       tc_fence_after();
       const uint32_t tm = tmem_base + (uint32_t)buf * kTileT;
-      const uint32_t pb = p_hi0 + (uint32_t)buf * (pbuf_bytes >> 4);
-      int kc = 0, kx = 0, ky = 0;
+      const uint32_t pb = p0u + (uint32_t)buf * (pbuf_bytes >> 4);
+      // unit = (8-channel chunk c8, tap (ky, kx)) at c8*R + ky*Wp + kx rows; chunk-major order
+      uint32_t ubase = 0, kx = 0, ky = 0;
+      int u = 0;
       uint32_t accf = 0;
       for (int ks = 0; ks < S; ++ks) {
+        const uint32_t ad0 = ubase + ky * Wp + kx;
+        if (++kx == 3) { kx = 0; if (++ky == 3) { ky = 0; ubase += R; } }
+        uint32_t ad1 = ad0;  // odd unit count: the last k-step's second unit has zero weights and re-reads the first
+        if (++u < U) {
+          ad1 = ubase + ky * Wp + kx;
+          if (++kx == 3) { kx = 0; if (++ky == 3) { ky = 0; ubase += R; } }
+          ++u;
+        }
         PROF_ACC(w_w, mbar_wait(&wfull[slot], wph));
         tc_fence_after();
-        const uint32_t wh = w0 + (uint32_t)slot * (uint32_t)(kStepBytesT >> 4);
-        const uint32_t ph_ = pb + (uint32_t)(kc * 2) * R + (uint32_t)ky * Wp + (uint32_t)kx;
-        if (elect_one()) umma_split3(tm, wh, wh + 2u * kRowsT, w_top, ph_, ph_ + p_lo_delta, p_top, idesc, accf);
+        const uint32_t wh = w0 + (uint32_t)slot * stage_u;
+        const uint32_t phd = (pb + ad0) | ((ad1 - ad0) << 16);
+        if (elect_one()) umma_split3(tm, wh, wh + 2u * rows, w_top, phd, phd + p_lo_delta, p_top, idesc, accf);
         if (leader) umma_commit(&wempty[slot]);
         accf = 1u;
         if (++slot == ring) {
           slot = 0;
           wph ^= 1u;
-        }
-        if (++kc == spt) {
-          kc = 0;
-          if (++kx == 3) {
-            kx = 0;
-            ++ky;
-          }
         }
       }
       if (leader) {
@@ -962,11 +750,11 @@ k_convlstm_grouped_p(const GArgs a) {
       uint32_t wph = 0;
       for (int i = 0; i < n_here; ++i) {
         const int g = (int)((first + i) / a.tiles_per_group);
-        const uint8_t* wg = a.wpack + (size_t)g * a.S * kStepBytesT;
+        const uint8_t* wg = a.wpack + (size_t)g * a.S * a.stage_bytes;
         for (int ks = 0; ks < a.S; ++ks) {
           mbar_wait(&wempty[slot], wph ^ 1u);
-          mbar_expect_tx(&wfull[slot], kStepBytesT);
-          bulk_g2s(sW + (size_t)slot * kStepBytesT, wg + (size_t)ks * kStepBytesT, kStepBytesT, &wfull[slot]);
+          mbar_expect_tx(&wfull[slot], a.stage_bytes);
+          bulk_g2s(sW + (size_t)slot * a.stage_bytes, wg + (size_t)ks * a.stage_bytes, a.stage_bytes, &wfull[slot]);
           if (++slot == a.ring) {
             slot = 0;
             wph ^= 1u;
@@ -978,6 +766,7 @@ k_convlstm_grouped_p(const GArgs a) {
     // ===================== stage the pixel rows: thread = row, every channel of the row in flight at once =====================
     const size_t HW = (size_t)a.H * a.W;
     const int wid = threadIdx.x - kStagerWarp0 * 32;
+    const int C8 = a.C8;
     PROF_DECL(w_e);
     PROF_STAMP(t_begin);
     for (int i = 0; i < n_here; ++i) {
@@ -989,7 +778,11 @@ k_convlstm_grouped_p(const GArgs a) {
       const long q0 = p0 - a.Wp - 1;
       uint8_t* dstb = sP + (size_t)buf * pbuf_bytes;
       PROF_ACC(w_e, mbar_wait(&pempty[buf], ph ^ 1u));
+#ifdef JAF_PROBE_SKIP_STAGE
+      for (int r = wid + (1 << 30); r < a.R; r += kStagerWarps * 32) {
+#else
       for (int r = wid; r < a.R; r += kStagerWarps * 32) {
+#endif
         const long q = q0 + r;
         bool inside = q < a.Q;
         size_t pix = 0;
@@ -1001,28 +794,36 @@ k_convlstm_grouped_p(const GArgs a) {
           b = fdiv(u, a.d_nb, ub);
           const int x = (int)ub * a.Wb + (int)xp - 1;  // a band's halo columns are its neighbours' pixels
           inside = x >= 0 && x < a.W && yp >= 1 && (int)yp <= a.H;
-          pix = (size_t)(yp - 1) * a.W + (size_t)x;
+          pix = inside ? (size_t)(yp - 1) * a.W + (size_t)x : 0;
+          if (!inside) b = 0;
         }
+        // padding rows read pixel 0 of image 0 (a valid address) and are zeroed below: the loads stay unconditional
         const float* xb = a.x + ((size_t)g * a.B + b) * (size_t)a.xs + pix;
-        const float* hb = a.h + ((size_t)g * a.B + b) * (size_t)a.hs + pix;
-        for (int c0 = 0; c0 < a.Ctp; c0 += 32) {  // batches of 32 channels: all their loads are issued before the first use
+        const float* hb = a.h + ((size_t)g * a.B + b) * (size_t)a.hs + pix - (size_t)a.Cin * HW;
+        for (int c0 = 0; c0 < C8; c0 += 4) {  // batches of 4 chunks = 32 channels: all their loads are issued before the first use
           float v[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int ch = c0 + e;
-            float val = 0.f;
-            if (inside && ch < a.Ct) val = ch < a.Cin ? __ldg(xb + (size_t)ch * HW) : __ldg(hb + (size_t)(ch - a.Cin) * HW);
-            v[e] = val;
+          for (int u = 0; u < 4; ++u) {
+            if (c0 + u < C8) {  // uniform
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int ch = min((c0 + u) * 8 + e, a.Ct - 1);  // a partial last chunk re-reads the last channel (zeroed below)
+                v[8 * u + e] = __ldg((ch < a.Cin ? xb : hb) + (size_t)ch * HW);
+              }
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (c0 + 8 * u < a.Ctp) {
+            if (c0 + u < C8) {
+              float w[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w[e] = (inside && (c0 + u) * 8 + e < a.Ct) ? v[8 * u + e] : 0.f;
               uint4 hi, lo;
-              split2(v[8 * u + 0], v[8 * u + 1], hi.x, lo.x);
-              split2(v[8 * u + 2], v[8 * u + 3], hi.y, lo.y);
-              split2(v[8 * u + 4], v[8 * u + 5], hi.z, lo.z);
-              split2(v[8 * u + 6], v[8 * u + 7], hi.w, lo.w);
-              uint8_t* dst = dstb + ((size_t)(c0 / 8 + u) * a.R + r) * 16;
+              split2(w[0], w[1], hi.x, lo.x);
+              split2(w[2], w[3], hi.y, lo.y);
+              split2(w[4], w[5], hi.z, lo.z);
+              split2(w[6], w[7], hi.w, lo.w);
+              uint8_t* dst = dstb + ((size_t)(c0 + u) * a.R + r) * 16;
               *reinterpret_cast<uint4*>(dst) = hi;
               *reinterpret_cast<uint4*>(dst + a.a_half) = lo;
             }
@@ -1030,16 +831,16 @@ k_convlstm_grouped_p(const GArgs a) {
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&pfull[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pfull[buf]);
     }
 #ifdef JAF_GROUPED_PROFILE
     if (wid == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
       printf("cta %d stager: total %llu ns | wait pempty %llu\n", blockIdx.x, gtime() - t_begin, w_e);
 #endif
   } else {
-    // ===================== epilogue: sets of four warps (one warp per gate / TMEM lane quarter) =====================
-    const int nu = a.Ch >> 2;
-    switch (nu) {
+    // ===================== epilogue: four sets of four warps =====================
+    switch (a.Ch >> 2) {
       case 1: epilogue_role_p<1>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
       case 2: epilogue_role_p<2>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
       case 3: epilogue_role_p<3>(a, sX, tfull, tempty, tmem_base, first, n_here, p_end); break;
@@ -1058,49 +859,51 @@ k_convlstm_grouped_p(const GArgs a) {
   }
 }
 
-// weight [G][4Ch][Ct][3][3] f32 -> per cell, per k-step (tap, 16 channels): [hi | lo] x [2 chunks][128 rows][8 bf16],
-// row = gate * 32 + channel (zero rows where channel >= Ch)
+// weight [G][4Ch][Ct][3][3] f32 -> per cell, per k-step j (units 2j, 2j+1; unit u = 8-channel chunk u/9, tap u%9):
+// [hi | lo] x [2 units][4*Ch rows][8 bf16], rows in the reference's order gate*Ch + channel; zero where the unit or the
+// input channel does not exist
 __global__ void __launch_bounds__(256)
-k_gpack_weight_t(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, int Ch, int Ct, int Ctp) {
-  const int spt = Ctp / 16, S = 9 * spt;
-  const size_t total = (size_t)G * S * 2 * kRowsT * 8;  // one thread per (g, step, chunk, row, e)
+k_gpack_weight_p(const float* __restrict__ w, uint8_t* __restrict__ wp, int G, int Ch, int Ct, int U, int S) {
+  const int rows = 4 * Ch;
+  const size_t total = (size_t)G * S * 2 * rows * 8;  // one thread per (g, k-step, unit slot, row, e)
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int e = (int)(i % 8);
   size_t r = i / 8;
-  const int row = (int)(r % kRowsT);
-  r /= kRowsT;
-  const int cc = (int)(r % 2);
+  const int row = (int)(r % rows);
+  r /= rows;
+  const int us = (int)(r % 2);
   r /= 2;
   const int step = (int)(r % S);
   const int g = (int)(r / S);
-  const int tap = step / spt, kc = step % spt;
-  const int ch_in = kc * 16 + cc * 8 + e;
-  const int gate = row / 32, ch = row % 32;
+  const int u = 2 * step + us;
+  const int c8 = u / 9, tap = u % 9;
+  const int ch_in = c8 * 8 + e;
   float v = 0.f;
-  if (ch < Ch && ch_in < Ct) v = w[(((size_t)g * 4 * Ch + (size_t)gate * Ch + ch) * Ct + ch_in) * 9 + tap];
+  if (u < U && ch_in < Ct) v = w[(((size_t)g * rows + row) * Ct + ch_in) * 9 + tap];
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-  uint8_t* stepb = wp + ((size_t)g * S + step) * kStepBytesT;
-  const size_t off = (size_t)cc * 16 * kRowsT + (size_t)row * 16 + (size_t)e * 2;
+  uint8_t* stepb = wp + ((size_t)g * S + step) * (64 * (size_t)rows);
+  const size_t off = (size_t)us * 16 * rows + (size_t)row * 16 + (size_t)e * 2;
   *reinterpret_cast<__nv_bfloat16*>(stepb + off) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(stepb + 32 * (size_t)kRowsT + off) = lo;
+  *reinterpret_cast<__nv_bfloat16*>(stepb + 32 * (size_t)rows + off) = lo;
 }
 
-// Cells served by the operand-swapped kernel (the packed-weight format follows this rule, so it must not change
-// between packing and stepping: the environment is read once per process).
-// Measured on the reference pyramid (24 cells, B = 1; profiles/r02_convlstm_grouped.jsonl): 24 channels @100^2 0.133 ms
-// swapped vs 0.164 ms, @50^2 0.041 vs 0.048; 12 channels @200^2 0.368 vs 0.280 (only 12 of the 32 lanes of each epilogue
-// warp hold a channel, and the per-CTA timers put 10 of 26 us in the exchange epilogue) -> swapped for 16 < Ch <= 32.
-// With the persistent kernel (k_convlstm_grouped_p) the 12-channel level is faster swapped as well (0.19 vs 0.28 ms).
-// JAF_CG_SWAP: 0 never, 1 only 16 < Ch <= 32, 2 (default) every cell with Ch <= 32.
-bool grouped_swapped(int Ch) {
+// Cells served by the operand-swapped persistent kernel (the packed-weight format follows this rule, so it must not
+// change between packing and stepping: the environment is read once per process).  Ch <= 32 keeps the 4*Ch gate rows
+// within one M = 128 tile; two pixel buffers + the exchange buffers + a weight ring of >= 4 k-steps must fit 227 KB for
+// every map size (the band width is capped, see plan_grouped_p): Cin + Ch <= 48 at Ch <= 24, <= 40 at Ch = 32.  Measured on the reference pyramid (24 cells,
+// B = 1; profiles/r02_convlstm_grouped.jsonl).  JAF_CG_SWAP=0 sends every cell to k_convlstm_grouped (A/B runs).
+bool grouped_swapped(int Cin, int Ch) {
   static const int mode = [] {
     const char* e = getenv("JAF_CG_SWAP");
-    return e == nullptr ? 2 : atoi(e);
+    return e == nullptr ? 1 : atoi(e);
   }();
   if (mode == 0 || Ch > 32) return false;
-  return mode == 2 || Ch > 16;
+  // worst case over map sizes: bands are at most 37 columns wide (plan_grouped_p), i.e. R <= 256 + 2 * 39 + 2 rows
+  const size_t pbuf = ((size_t)2 * ((Cin + Ch + 7) / 8) * 336 * 16 + 127) & ~(size_t)127;
+  const size_t xb = ((size_t)kEpiSets * 4 * Ch * (kXPitch + 1) * 4 + 127) & ~(size_t)127;
+  return 2 * pbuf + xb + kRingPad + (2 * kMaxRingP + 9) * 8 + 128 + 4 * (size_t)64 * 4 * Ch <= (size_t)kMaxSmem;
 }
 
 bool grouped_shape_ok(int Cin, int Ch) { return Cin > 0 && Ch > 0 && Ch % 4 == 0 && 4 * Ch <= 512 && ((4 * Ch <= 256) || (2 * Ch) % 16 == 0); }
@@ -1109,10 +912,14 @@ bool grouped_shape_ok(int Cin, int Ch) { return Cin > 0 && Ch > 0 && Ch % 4 == 0
 
 extern "C" {
 
+// k-steps of the swapped format: two 8-channel units per step, 9 taps per 8-channel chunk
+static inline int swapped_units(int Cin, int Ch) { return 9 * ((Cin + Ch + 7) / 8); }
+static inline int swapped_steps(int Cin, int Ch) { return (swapped_units(Cin, Ch) + 1) / 2; }
+
 size_t jaf_convlstm_gpack_bytes(int G, int Cin, int Ch) {
   if (G <= 0 || !grouped_shape_ok(Cin, Ch)) return 0;
+  if (grouped_swapped(Cin, Ch)) return (size_t)G * swapped_steps(Cin, Ch) * 64 * (4 * Ch);
   const int Ctp = (Cin + Ch + 15) / 16 * 16;
-  if (grouped_swapped(Ch)) return (size_t)G * 9 * (Ctp / 16) * kStepBytesT;
   return (size_t)G * 9 * (Ctp / 16) * 64 * (4 * Ch);
 }
 
@@ -1120,11 +927,12 @@ int jaf_convlstm_gpack_weight(const float* weight, int G, int Cin, int Ch, void*
   JAF_REQUIRE(weight && wpack, "null pointer");
   JAF_REQUIRE(G > 0 && grouped_shape_ok(Cin, Ch), "Ch must be a multiple of 4 and at most 128");
   const int Ct = Cin + Ch, Ctp = (Ct + 15) / 16 * 16, N = 4 * Ch;
-  if (grouped_swapped(Ch)) {
-    const size_t total_t = (size_t)G * 9 * (Ctp / 16) * 2 * kRowsT * 8;
-    k_gpack_weight_t<<<jaf::ceil_div((long)total_t, 256), 256, 0, jaf::as_stream(stream)>>>(weight, static_cast<uint8_t*>(wpack),
-                                                                                         G, Ch, Ct, Ctp);
-    return jaf::finish_launch("k_gpack_weight_t");
+  if (grouped_swapped(Cin, Ch)) {
+    const int U = swapped_units(Cin, Ch), S = swapped_steps(Cin, Ch);
+    const size_t total_p = (size_t)G * S * 2 * N * 8;
+    k_gpack_weight_p<<<jaf::ceil_div((long)total_p, 256), 256, 0, jaf::as_stream(stream)>>>(weight, static_cast<uint8_t*>(wpack),
+                                                                                         G, Ch, Ct, U, S);
+    return jaf::finish_launch("k_gpack_weight_p");
   }
   const size_t total = (size_t)G * 9 * (Ctp / 16) * 2 * N * 8;
   k_gpack_weight<<<jaf::ceil_div((long)total, 256), 256, 0, jaf::as_stream(stream)>>>(
@@ -1242,17 +1050,16 @@ static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_coun
   return JAF_OK;
 }
 
-// Launch plan of the operand-swapped kernel: the geometry of plan_grouped with 256-pixel tiles, one accumulator tile
-// per CTA and two CTAs per SM.
-static int plan_grouped_t(int G, int B, int Cin, int Ch, int H, int W, int sm_count, GArgs& a, size_t& smem, long& grid,
-                          bool& persistent) {
+// Launch plan of the operand-swapped persistent kernel: the geometry of plan_grouped (bands of <= 25 columns) with
+// 256-pixel tiles, one CTA per SM walking a contiguous run of tiles.
+static int plan_grouped_p(int G, int B, int Cin, int Ch, int H, int W, int sm_count, GArgs& a, size_t& smem, long& grid) {
   a.G = G; a.B = B; a.Cin = Cin; a.Ch = Ch; a.H = H; a.W = W;
   a.xs = (long)Cin * H * W;
   a.hs = a.hos = (long)Ch * H * W;
   static const int band_target = [] {
     const char* e = getenv("JAF_CG_BAND");
     const int v = e ? atoi(e) : 25;
-    return v >= 8 ? v : 25;
+    return (v >= 8 && v <= 25) ? v : 25;  // capped: the shared-memory budget of grouped_swapped() assumes it
   }();
   a.nb = (W + band_target / 2) / band_target;
   if (a.nb < 1) a.nb = 1;
@@ -1261,62 +1068,47 @@ static int plan_grouped_t(int G, int B, int Cin, int Ch, int H, int W, int sm_co
   a.HpWp = (H + 2) * a.Wp;
   a.Q = (long)B * a.nb * a.HpWp;
   a.Ct = Cin + Ch;
-  a.Ctp = (a.Ct + 15) / 16 * 16;
+  a.C8 = (a.Ct + 7) / 8;
+  a.Ctp = a.C8 * 8;
+  a.U = 9 * a.C8;
+  a.S = (a.U + 1) / 2;
   a.N = 4 * Ch;
-  a.S = 9 * (a.Ctp / 16);
   a.CS = 1; a.Chs = Ch; a.Ns = a.N; a.nsplit = 1; a.Nsub = a.N;
   a.MT = kTileT / 128;
   a.R = kTileT + 2 * a.Wp + 2;
-  a.a_half = (uint32_t)(a.Ctp / 8) * (uint32_t)a.R * 16u;
+  a.a_half = (uint32_t)a.C8 * (uint32_t)a.R * 16u;
   a.KS = 1;
   a.nstages = a.S;
-  a.stage_bytes = (uint32_t)a.KS * kStepBytesT;
-  a.tmem_cols = 256;
+  a.stage_bytes = 64u * (uint32_t)a.N;
+  a.tmem_cols = 512;
   a.idesc = 0;
   const long out_rows = a.Q - 2L * a.Wp - 2;
   a.tiles_per_group = jaf::ceil_div(out_rows, kTileT);
-  const size_t pix = ((size_t)(2u * a.a_half > (uint32_t)(4 * kXSetFloats * 4) ? 2u * a.a_half : (uint32_t)(4 * kXSetFloats * 4)) + 127) & ~(size_t)127;
-  smem = pix + (size_t)kRing * a.stage_bytes + 256 + 128;
-  grid = (long)G * a.tiles_per_group;
-  a.ntiles = grid;
-  // persistent flavour: two pixel buffers + the exchange buffers of the three epilogue sets + a weight ring of >= 4 k-steps
-  static const int persist_mode = [] {
-    const char* e = getenv("JAF_CG_PERSIST");
-    return e ? atoi(e) : 1;
-  }();
-  persistent = false;
-  if (a.Q >= (1L << 31)) {
-    jaf::set_error("jaf_convlstm_step_grouped: batch too large for 32-bit positions");
+  a.ntiles = (long)G * a.tiles_per_group;
+  auto mk = [](int d) {
+    FastDiv f;
+    f.d = (uint32_t)d;
+    const uint64_t m = (1ull << 32) / (uint64_t)d;
+    f.m = m > 0xffffffffull ? 0xffffffffu : (uint32_t)m;
+    return f;
+  };
+  a.d_hpwp = mk(a.HpWp);
+  a.d_wp = mk(a.Wp);
+  a.d_nb = mk(a.nb);
+  const size_t pbuf = ((size_t)2 * a.a_half + 127) & ~(size_t)127;
+  const size_t xb = ((size_t)kEpiSets * 4 * Ch * (kXPitch + 1) * 4 + 127) & ~(size_t)127;
+  const size_t fixed = 2 * pbuf + xb + kRingPad + (2 * kMaxRingP + 9) * 8 + 128;
+  if (a.Q >= (1L << 31) || a.ntiles >= (1L << 31) || (size_t)2 * pbuf >= ((size_t)1 << 18) ||
+      fixed + 4 * (size_t)a.stage_bytes > (size_t)kMaxSmem) {
+    jaf::set_error("jaf_convlstm_step_grouped: cell does not fit the operand-swapped plan (Cin=%d Ch=%d H=%d W=%d B=%d)", Cin, Ch,
+                   H, W, B);
     return JAF_ERR_UNSUPPORTED;
   }
-  if (persist_mode != 0 && (uint32_t)a.R * 16u < (1u << 18) && grid < (1L << 31)) {
-    const size_t pbuf = ((size_t)2 * a.a_half + 127) & ~(size_t)127;
-    const size_t xb = ((size_t)kEpiSets * (4 * Ch * kXPitch + 4 * Ch) * 4 + 127) & ~(size_t)127;
-    auto mk = [](int d) {
-      FastDiv f;
-      f.d = (uint32_t)d;
-      const uint64_t m = (1ull << 32) / (uint64_t)d;
-      f.m = m > 0xffffffffull ? 0xffffffffu : (uint32_t)m;
-      return f;
-    };
-    a.d_hpwp = mk(a.HpWp);
-    a.d_wp = mk(a.Wp);
-    a.d_nb = mk(a.nb);
-    const size_t fixed = 2 * pbuf + xb + (2 * kMaxRingP + 9) * 8 + 128;
-    if (fixed + 4 * (size_t)kStepBytesT <= (size_t)kMaxSmem) {
-      size_t ring = ((size_t)kMaxSmem - fixed) / kStepBytesT;
-      if (ring > (size_t)kMaxRingP) ring = kMaxRingP;
-      a.ring = (int)ring;
-      persistent = true;
-      smem = fixed + ring * kStepBytesT;
-      grid = a.ntiles < sm_count ? a.ntiles : sm_count;
-      return JAF_OK;
-    }
-  }
-  if (smem > (size_t)kHalfSmem || (uint32_t)a.R * 16u >= (1u << 18) || grid >= (1L << 31)) {
-    jaf::set_error("jaf_convlstm_step_grouped: cell does not fit the operand-swapped plan (Cin=%d Ch=%d W=%d)", Cin, Ch, W);
-    return JAF_ERR_UNSUPPORTED;
-  }
+  size_t ring = ((size_t)kMaxSmem - fixed) / a.stage_bytes;
+  if (ring > (size_t)kMaxRingP) ring = kMaxRingP;
+  a.ring = (int)ring;
+  smem = fixed + ring * a.stage_bytes;
+  grid = a.ntiles < sm_count ? a.ntiles : sm_count;
   return JAF_OK;
 }
 
@@ -1328,8 +1120,7 @@ int jaf_convlstm_grouped_supported(int G, int B, int Cin, int Ch, int H, int W) 
   int threads;
   size_t smem;
   long grid;
-  bool persistent;
-  if (grouped_swapped(Ch)) return plan_grouped_t(G, B, Cin, Ch, H, W, sms, a, smem, grid, persistent) == JAF_OK ? 1 : 0;
+  if (grouped_swapped(Cin, Ch)) return plan_grouped_p(G, B, Cin, Ch, H, W, sms, a, smem, grid) == JAF_OK ? 1 : 0;
   return plan_grouped(G, B, Cin, Ch, H, W, sms, a, threads, smem, grid) == JAF_OK ? 1 : 0;
 }
 
@@ -1353,22 +1144,16 @@ int jaf_convlstm_step_grouped(const float* x, const float* h, const float* c, co
   int threads;
   size_t smem;
   long grid;
-  if (grouped_swapped(Ch)) {
-    static jaf::PerDeviceOnce attr_once_t;
-    if (!attr_once_t.done(dev)) {
-      JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kHalfSmem));
+  if (grouped_swapped(Cin, Ch)) {
+    static jaf::PerDeviceOnce attr_once_p;
+    if (!attr_once_p.done(dev)) {
       JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_p, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      attr_once_t.mark(dev);
+      attr_once_p.mark(dev);
     }
-    bool persistent;
-    const int stt = plan_grouped_t(G, B, Cin, Ch, H, W, sm_count, a, smem, grid, persistent);
+    const int stt = plan_grouped_p(G, B, Cin, Ch, H, W, sm_count, a, smem, grid);
     if (stt != JAF_OK) return stt;
-    if (persistent) {
-      k_convlstm_grouped_p<<<(unsigned)grid, kThreadsP, smem, jaf::as_stream(stream)>>>(a);
-      return jaf::finish_launch("k_convlstm_grouped_p");
-    }
-    k_convlstm_grouped_t<<<(unsigned)grid, kThreadsT, smem, jaf::as_stream(stream)>>>(a);
-    return jaf::finish_launch("k_convlstm_grouped_t");
+    k_convlstm_grouped_p<<<(unsigned)grid, kThreadsP, smem, jaf::as_stream(stream)>>>(a);
+    return jaf::finish_launch("k_convlstm_grouped_p");
   }
   const int st = plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, threads, smem, grid);
   if (st != JAF_OK) return st;
@@ -1394,20 +1179,18 @@ int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const flo
   }
   GArgs a;
   a.bias = bias; a.wpack = static_cast<const uint8_t*>(wpack);
-  int threads = kThreadsT;
+  int threads = kThreadsP;
   size_t smem;
   long grid;
-  const bool swapped = grouped_swapped(Ch);
+  const bool swapped = grouped_swapped(Cin, Ch);
   if (swapped) {
-    static jaf::PerDeviceOnce attr_once_t;
-    if (!attr_once_t.done(dev)) {
-      JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kHalfSmem));
+    static jaf::PerDeviceOnce attr_once_p;
+    if (!attr_once_p.done(dev)) {
       JAF_CUDA(cudaFuncSetAttribute(k_convlstm_grouped_p, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      attr_once_t.mark(dev);
+      attr_once_p.mark(dev);
     }
   }
-  bool persistent = false;
-  const int st = swapped ? plan_grouped_t(G, B, Cin, Ch, H, W, sm_count, a, smem, grid, persistent)
+  const int st = swapped ? plan_grouped_p(G, B, Cin, Ch, H, W, sm_count, a, smem, grid)
                          : plan_grouped(G, B, Cin, Ch, H, W, sm_count, a, threads, smem, grid);
   if (st != JAF_OK) return st;
   const long HW = (long)H * W;
@@ -1424,8 +1207,7 @@ int jaf_convlstm_sequence_grouped(const float* x_seq, const float* h0, const flo
     a.h_out = h_seq + (long)t * Ch * HW;
     a.hos = (long)T * Ch * HW;
     a.c_out = cbuf[t & 1];
-    if (swapped && persistent) k_convlstm_grouped_p<<<(unsigned)grid, kThreadsP, smem, jaf::as_stream(stream)>>>(a);
-    else if (swapped) k_convlstm_grouped_t<<<(unsigned)grid, kThreadsT, smem, jaf::as_stream(stream)>>>(a);
+    if (swapped) k_convlstm_grouped_p<<<(unsigned)grid, kThreadsP, smem, jaf::as_stream(stream)>>>(a);
     else k_convlstm_grouped<<<(unsigned)grid, threads, smem, jaf::as_stream(stream)>>>(a);
   }
   return jaf::finish_launch("k_convlstm_grouped (sequence)", T);

@@ -130,13 +130,17 @@ __device__ __forceinline__ HotTap make_hot_tap(float gx, float gy, int Ws, int H
 // allocation, measured, so the fused kernel keeps the plain version below.)
 // One output pixel of the RGB planes (planar fp32, the reference layout): softmax in the reference's
 // sequential order, ATen's tap order, acc += w_k * warped_k — bit-identical to k_warp_fuse_generic.
-template <int KT, bool SKIP>
+// XSHARE (whole warp converged, lanes = x-adjacent pixels; `live` = this lane owns a real pixel): the ne / se taps of a
+// pixel are the nw / sw taps of its right-hand neighbour whenever the neighbour's corner is one column further (true for
+// most pixels of a locally translation-like flow) — they come from the neighbour lane by shuffle instead of a second,
+// line-straddling gather (same address, same bits).  Lanes whose neighbour samples elsewhere load the taps themselves.
+template <int KT, bool SKIP, bool XSHARE = false>
 __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __restrict__ rgb_base,
                                           const float2* __restrict__ b_grid, const float* __restrict__ b_logit,
                                           const float* __restrict__ b_vis, const int* __restrict__ b_fim,
                                           const float* __restrict__ b_mask, const float* __restrict__ b_fake,
                                           const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
-                                          unsigned HW, unsigned HWs, unsigned Ws) {
+                                          unsigned HW, unsigned HWs, unsigned Ws, bool live = true) {
   // every load that does not depend on another one is issued first: sample positions, logits, target mask
   float2 gxy0[KT];
   if constexpr (!SKIP && KT <= 4) {
@@ -191,15 +195,30 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
       ok[k] = (unsigned)(k * 3) * HWs + (unsigned)((int)fy * (int)Ws + (int)fx);
     }
     float vbuf[2][12];
+    bool coh[KT];  // XSHARE: the right-hand neighbour lane's nw / sw taps are this pixel's ne / se taps
+    if constexpr (XSHARE) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        coh[k] = (__shfl_down_sync(0xffffffffu, ok[k], 1) == ok[k] + 1u) && ((threadIdx.x & 31u) != 31u);
+    }
     auto gather = [&](int k, float* v) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* p0 = reinterpret_cast<const float*>(rgb_bytes + (size_t)(ok[k] + (unsigned)c * HWs) * 4u);
         const float* p1 = reinterpret_cast<const float*>(rgb_bytes + (size_t)(ok[k] + (unsigned)c * HWs + Ws) * 4u);
         v[4 * c + 0] = __ldg(p0);
-        v[4 * c + 1] = __ldg(p0 + 1);
         v[4 * c + 2] = __ldg(p1);
-        v[4 * c + 3] = __ldg(p1 + 1);
+        if constexpr (XSHARE) {
+          v[4 * c + 1] = 0.f;
+          v[4 * c + 3] = 0.f;
+          if (!coh[k]) {
+            v[4 * c + 1] = __ldg(p0 + 1);
+            v[4 * c + 3] = __ldg(p1 + 1);
+          }
+        } else {
+          v[4 * c + 1] = __ldg(p0 + 1);
+          v[4 * c + 3] = __ldg(p1 + 1);
+        }
       }
     };
     gather(0, vbuf[0]);
@@ -209,10 +228,18 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
       const float* v = vbuf[k & 1];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
+        float ne = v[4 * c + 1], se = v[4 * c + 3];
+        if constexpr (XSHARE) {
+          const float ne_s = __shfl_down_sync(0xffffffffu, v[4 * c + 0], 1), se_s = __shfl_down_sync(0xffffffffu, v[4 * c + 2], 1);
+          if (coh[k]) {
+            ne = ne_s;
+            se = se_s;
+          }
+        }
         float sacc = fmaf(v[4 * c + 0], tw[k][0], 0.f);
-        sacc = fmaf(v[4 * c + 1], tw[k][1], sacc);
+        sacc = fmaf(ne, tw[k][1], sacc);
         sacc = fmaf(v[4 * c + 2], tw[k][2], sacc);
-        sacc = fmaf(v[4 * c + 3], tw[k][3], sacc);
+        sacc = fmaf(se, tw[k][3], sacc);
         acc[c] = fmaf(wk[k], sacc, acc[c]);
       }
     }

@@ -645,7 +645,8 @@ def test_cal_flow_multi_equals_per_pair_cal_flow_and_feeds_warp_fuse():
 # ------------------------------------------------------------------ a13: G reference-sized cells per launch (tcgen05, split-bf16)
 @pytest.mark.parametrize("G,B,Cin,Ch,H,W", [(1, 1, 12, 12, 20, 20), (3, 2, 12, 12, 50, 37), (2, 1, 24, 24, 100, 100),
                                             (24, 1, 48, 48, 25, 25), (2, 3, 96, 96, 13, 13), (2, 1, 3, 12, 200, 200),
-                                            (1, 2, 20, 8, 9, 140)])
+                                            (1, 2, 20, 8, 9, 140), (2, 2, 8, 32, 30, 41), (1, 1, 4, 4, 7, 5),
+                                            (2, 1, 16, 32, 38, 37), (160, 1, 12, 12, 16, 16)])
 def test_convlstm_grouped_cells_vs_fp64(G, B, Cin, Ch, H, W):
     """Accumulate_LSTM_no_loss' per-part cells (src/networks.py:1304-1313: 12@200^2, 24@100^2, 24@50^2, 48@25^2,
     96@13^2; 24 parts with their own weights) in one launch.  Tolerance: the fp32 bound of the north star, 1e-4."""
