@@ -653,6 +653,20 @@ def run_aux(args):
         gseq = ops.FrameGraph(sequence)
         ts_g, pg, _ = timed(gseq.replay, steps * 3, 3)
         seq_ok = all(torch.equal(a, b) for a, b in zip(eager_out, outs)) and all(torch.equal(a, b) for a, b in zip(eager_out, two_call_out))
+        # the 30 frames are independent (the reference never feeds frame t-1 into frame t): the same calls captured on
+        # 4 parallel graph branches, frame t on branch t % 4 (per-stream workspaces)
+        def one_frame(t):
+            ops.warp_fuse_from_poses(src_cam1, src_verts1, cam[t:t + 1], verts[t:t + 1], f_idx, 256, rgb=rgb, fake=fake,
+                                     conf=conf, out_rgb=outs[t])
+            return outs[t]
+        lane_us = {}
+        for nl in (2, 4, 8):
+            for o in outs:
+                o.zero_()
+            gl = ops.FrameGraph(one_frame, frames=30, lanes=nl)
+            _, pl, _ = timed(gl.replay, steps * 3, 3)
+            lane_us[nl] = round(pl[len(pl) // 2] * 1e3 / 30, 2)
+            seq_ok = seq_ok and all(torch.equal(a, b) for a, b in zip(eager_out, outs))
         src_img, g1 = rgb[:, 0].contiguous(), grid[:, 0].contiguous()
 
         def torch_ref():
@@ -677,6 +691,7 @@ def run_aux(args):
                                         "us_per_frame_cuda_graph": round(pg[len(pg) // 2] * 1e3 / 30, 2),
                                         "us_per_frame_two_calls_eager": round(p2[len(p2) // 2] * 1e3 / 30, 2),
                                         "us_per_frame_two_calls_cuda_graph": round(pg2[len(pg2) // 2] * 1e3 / 30, 2),
+                                        "us_per_frame_cuda_graph_parallel_lanes": lane_us,
                                         "kernels_per_frame": seq_launches // 30, "graph_matches_eager_bits": bool(seq_ok),
                                         "note": "per frame, batch 1, 256^2: jaf_warp_fuse_from_poses (one clear + scatter + deferred "
                                                 "boxes + ONE fused resolve / compose / warp / visibility / blend kernel); two_calls = "

@@ -130,17 +130,13 @@ __device__ __forceinline__ HotTap make_hot_tap(float gx, float gy, int Ws, int H
 // allocation, measured, so the fused kernel keeps the plain version below.)
 // One output pixel of the RGB planes (planar fp32, the reference layout): softmax in the reference's
 // sequential order, ATen's tap order, acc += w_k * warped_k — bit-identical to k_warp_fuse_generic.
-// XSHARE (whole warp converged, lanes = x-adjacent pixels; `live` = this lane owns a real pixel): the ne / se taps of a
-// pixel are the nw / sw taps of its right-hand neighbour whenever the neighbour's corner is one column further (true for
-// most pixels of a locally translation-like flow) — they come from the neighbour lane by shuffle instead of a second,
-// line-straddling gather (same address, same bits).  Lanes whose neighbour samples elsewhere load the taps themselves.
-template <int KT, bool SKIP, bool XSHARE = false>
+template <int KT, bool SKIP>
 __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __restrict__ rgb_base,
                                           const float2* __restrict__ b_grid, const float* __restrict__ b_logit,
                                           const float* __restrict__ b_vis, const int* __restrict__ b_fim,
                                           const float* __restrict__ b_mask, const float* __restrict__ b_fake,
                                           const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
-                                          unsigned HW, unsigned HWs, unsigned Ws, bool live = true) {
+                                          unsigned HW, unsigned HWs, unsigned Ws) {
   // every load that does not depend on another one is issued first: sample positions, logits, target mask
   float2 gxy0[KT];
   if constexpr (!SKIP && KT <= 4) {
@@ -195,30 +191,15 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
       ok[k] = (unsigned)(k * 3) * HWs + (unsigned)((int)fy * (int)Ws + (int)fx);
     }
     float vbuf[2][12];
-    bool coh[KT];  // XSHARE: the right-hand neighbour lane's nw / sw taps are this pixel's ne / se taps
-    if constexpr (XSHARE) {
-#pragma unroll
-      for (int k = 0; k < KT; ++k)
-        coh[k] = (__shfl_down_sync(0xffffffffu, ok[k], 1) == ok[k] + 1u) && ((threadIdx.x & 31u) != 31u);
-    }
     auto gather = [&](int k, float* v) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* p0 = reinterpret_cast<const float*>(rgb_bytes + (size_t)(ok[k] + (unsigned)c * HWs) * 4u);
         const float* p1 = reinterpret_cast<const float*>(rgb_bytes + (size_t)(ok[k] + (unsigned)c * HWs + Ws) * 4u);
         v[4 * c + 0] = __ldg(p0);
+        v[4 * c + 1] = __ldg(p0 + 1);
         v[4 * c + 2] = __ldg(p1);
-        if constexpr (XSHARE) {
-          v[4 * c + 1] = 0.f;
-          v[4 * c + 3] = 0.f;
-          if (!coh[k]) {
-            v[4 * c + 1] = __ldg(p0 + 1);
-            v[4 * c + 3] = __ldg(p1 + 1);
-          }
-        } else {
-          v[4 * c + 1] = __ldg(p0 + 1);
-          v[4 * c + 3] = __ldg(p1 + 1);
-        }
+        v[4 * c + 3] = __ldg(p1 + 1);
       }
     };
     gather(0, vbuf[0]);
@@ -228,18 +209,10 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
       const float* v = vbuf[k & 1];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float ne = v[4 * c + 1], se = v[4 * c + 3];
-        if constexpr (XSHARE) {
-          const float ne_s = __shfl_down_sync(0xffffffffu, v[4 * c + 0], 1), se_s = __shfl_down_sync(0xffffffffu, v[4 * c + 2], 1);
-          if (coh[k]) {
-            ne = ne_s;
-            se = se_s;
-          }
-        }
         float sacc = fmaf(v[4 * c + 0], tw[k][0], 0.f);
-        sacc = fmaf(ne, tw[k][1], sacc);
+        sacc = fmaf(v[4 * c + 1], tw[k][1], sacc);
         sacc = fmaf(v[4 * c + 2], tw[k][2], sacc);
-        sacc = fmaf(se, tw[k][3], sacc);
+        sacc = fmaf(v[4 * c + 3], tw[k][3], sacc);
         acc[c] = fmaf(wk[k], sacc, acc[c]);
       }
     }
@@ -282,7 +255,7 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
       const float fkv = __ldg(b_fake + ((unsigned)c * HW + pix));
       ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
     }
-    if (live) st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
+    st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
   }
 }
 
@@ -291,19 +264,14 @@ __device__ __forceinline__ void rgb_pixel_lean(const WFArgs& a, const float* __r
 // k_warp_fuse_generic; the pipelined one replaces the K softmax divisions by one reciprocal, <= 1 ulp).
 // s_grid != nullptr: the flows of this tile live in shared memory (s_grid[k * s_kstride + s_pix], composed from the
 // poses by the kernel itself) and the pixel's visibility is known (s_vis 0 / 1) instead of coming from fim / vis.
-// Measured (same box, profiles/r02_bench_ab.jsonl): sharing helps the stand-alone RGB kernel (451 k -> 477 k frames/s dense,
-// 424 k -> 440 k hard) and costs the fused kernels 2-4 % (their phase B competes with phase A of the co-resident CTAs for
-// issue slots, and the shuffles + selects add ~36 instructions per pixel) — so the fused kernels keep their own gathers.
-constexpr bool kShareRgbTaps = false;
-// XSHARE / live: see rgb_pixel_lean (only the !SKIP pipelined flavour shares taps; the caller keeps the warp converged).
-template <int KT, bool SKIP, bool PIPE = (KT <= 4), bool XSHARE = false>  // PIPE: hand-pipelined flavour (needs ~2*KT + 45 registers)
+template <int KT, bool SKIP, bool PIPE = (KT <= 4)>  // PIPE: hand-pipelined flavour (needs ~2*KT + 45 registers)
 __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restrict__ rgb_base,
                                           const float2* __restrict__ b_grid, const float* __restrict__ b_logit,
                                           const float* __restrict__ b_vis, const int* __restrict__ b_fim,
                                           const float* __restrict__ b_mask, const float* __restrict__ b_fake,
                                           const float* __restrict__ b_conf, float* __restrict__ b_orgb, unsigned pix,
                                           unsigned HW, unsigned HWs, unsigned Ws, const float2* s_grid = nullptr,
-                                          unsigned s_kstride = 0, unsigned s_pix = 0, int s_vis = 1, bool live = true) {
+                                          unsigned s_kstride = 0, unsigned s_pix = 0, int s_vis = 1) {
   auto grid_at = [&](int k) -> float2 {
     if (s_grid != nullptr) return s_grid[(unsigned)k * s_kstride + s_pix];
     return __ldg(b_grid + ((unsigned)k * HW + pix));
@@ -362,53 +330,34 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
       t.off += k * 3 * (int)HWs;
       return t;
     };
-    bool coh[2] = {false, false};  // XSHARE: the right-hand neighbour lane's nw / sw taps are this pixel's ne / se taps
-    auto gather = [&](const HotTap& t, float* v, bool& co) {
-      if constexpr (XSHARE) co = (__shfl_down_sync(0xffffffffu, t.off, 1) == t.off + 1) && ((threadIdx.x & 31u) != 31u);
+    auto gather = [&](const HotTap& t, float* v) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* p0 = rgb_base + ((unsigned)t.off + (unsigned)c * HWs);
         v[4 * c + 0] = __ldg(p0);
+        v[4 * c + 1] = __ldg(p0 + 1);
         v[4 * c + 2] = __ldg(p0 + Ws);
-        if constexpr (XSHARE) {
-          v[4 * c + 1] = 0.f;
-          v[4 * c + 3] = 0.f;
-          if (!co) {
-            v[4 * c + 1] = __ldg(p0 + 1);
-            v[4 * c + 3] = __ldg(p0 + Ws + 1);
-          }
-        } else {
-          v[4 * c + 1] = __ldg(p0 + 1);
-          v[4 * c + 3] = __ldg(p0 + Ws + 1);
-        }
+        v[4 * c + 3] = __ldg(p0 + Ws + 1);
       }
     };
     const float inv = (KT == 1) ? 1.0f : __frcp_rn(ssum);  // one correctly-rounded reciprocal instead of K divisions
     HotTap tn = tap_of(0);
-    gather(tn, vbuf[0], coh[0]);
+    gather(tn, vbuf[0]);
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
       const HotTap tc = tn;
       if (k + 1 < KT) {
         tn = tap_of(k + 1);
-        gather(tn, vbuf[(k + 1) & 1], coh[(k + 1) & 1]);
+        gather(tn, vbuf[(k + 1) & 1]);
       }
       const float* v = vbuf[k & 1];
       const float w = (KT == 1) ? aw[k] : (aw[k] * inv);  // vf == 1 here (no visibility input)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float ne = v[4 * c + 1], se = v[4 * c + 3];
-        if constexpr (XSHARE) {
-          const float ne_s = __shfl_down_sync(0xffffffffu, v[4 * c + 0], 1), se_s = __shfl_down_sync(0xffffffffu, v[4 * c + 2], 1);
-          if (coh[k & 1]) {
-            ne = ne_s;
-            se = se_s;
-          }
-        }
         float sacc = fmaf(v[4 * c + 0], tc.nw, 0.f);
-        sacc = fmaf(ne, tc.ne, sacc);
+        sacc = fmaf(v[4 * c + 1], tc.ne, sacc);
         sacc = fmaf(v[4 * c + 2], tc.sw, sacc);
-        sacc = fmaf(se, tc.se, sacc);
+        sacc = fmaf(v[4 * c + 3], tc.se, sacc);
         acc[c] = fmaf(w, sacc, acc[c]);
       }
     }
@@ -444,7 +393,7 @@ __device__ __forceinline__ void rgb_pixel(const WFArgs& a, const float* __restri
       const float fkv = __ldg(b_fake + ((unsigned)c * HW + pix));
       ov = fkv * wc + ov * (1.0f - wc);  // src/flow_net.py:98
     }
-    if (live) st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
+    st_stream_f32(b_orgb + ((unsigned)c * HW + pix), ov);
   }
 }
 
@@ -924,19 +873,12 @@ k_warp_fuse_nhwc(const WFArgs a) {
     const int npx = TW * (y_end - y_begin);
     for (int p = threadIdx.x; p < npx; p += 256) {
       const int x = tx * TW + p % TW, y = y_begin + p / TW;
-      if constexpr (POSES) {
-        if (x >= (int)W) continue;
+      if (x >= (int)W) continue;
+      if constexpr (POSES)
         rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws,
                             s_T, tile_px, (unsigned)p, (int)s_vis[p]);
-      } else if constexpr (SKIP) {
-        if (x >= (int)W) continue;
+      else
         rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
-      } else {  // TW >= 32: a warp is one row segment and stays converged (tap sharing by shuffle)
-        const int xc = min(x, (int)W - 1);
-        // (narrower strips end the loop with partial warps: no sharing there)
-        rgb_pixel<KT, SKIP, (KT <= 4), (kShareRgbTaps && TW % 32 == 0)>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb,
-                                                       (unsigned)y * W + (unsigned)xc, HW, HWs, Ws, nullptr, 0, 0, 1, x < (int)W);
-      }
     }
   }
 }
@@ -1124,17 +1066,9 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
     float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
     const int npx = TW * (y_end - y_begin);
     for (int p = threadIdx.x; p < npx; p += 256) {
-      // TW is a multiple of 32: a warp is 32 x-adjacent pixels of one row and stays converged (tap sharing by shuffle);
-      // lanes beyond the right edge repeat the last column and store nothing
       const int x = tx * TW + p % TW, y = y_begin + p / TW;
-      if constexpr (SKIP) {
-        if (x >= (int)W) continue;
-        rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
-      } else {
-        const int xc = min(x, (int)W - 1);
-        rgb_pixel<KT, SKIP, (KT <= 4), kShareRgbTaps>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb,
-                                             (unsigned)y * W + (unsigned)xc, HW, HWs, Ws, nullptr, 0, 0, 1, x < (int)W);
-      }
+      if (x >= (int)W) continue;
+      rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
     }
   }
 }
@@ -1301,15 +1235,9 @@ k_warp_fuse_nhwc_wide2(const WFArgs a) {
     float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
     const int npx = TW * (y_end - y_begin);
     for (int p = threadIdx.x; p < npx; p += 256) {
-      const int x = tx * TW + p % TW, y = y_begin + p / TW;  // converged warp, see k_warp_fuse_nhwc_wide
-      if constexpr (SKIP) {
-        if (x >= (int)W) continue;
-        rgb_pixel<KT, SKIP, true>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
-      } else {
-        const int xc = min(x, (int)W - 1);
-        rgb_pixel<KT, SKIP, true, kShareRgbTaps>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb,
-                                        (unsigned)y * W + (unsigned)xc, HW, HWs, Ws, nullptr, 0, 0, 1, x < (int)W);
-      }
+      const int x = tx * TW + p % TW, y = y_begin + p / TW;
+      if (x >= (int)W) continue;
+      rgb_pixel<KT, SKIP, true>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
     }
   }
 }
@@ -1479,15 +1407,9 @@ k_warp_fuse_nhwc_wide2r(const WFArgs a) {
     float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
     const int npx = TW * (y_end - y_begin);
     for (int p = threadIdx.x; p < npx; p += 256) {
-      const int x = tx * TW + p % TW, y = y_begin + p / TW;  // converged warp, see k_warp_fuse_nhwc_wide
-      if constexpr (SKIP) {
-        if (x >= (int)W) continue;
-        rgb_pixel<KT, SKIP, true>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
-      } else {
-        const int xc = min(x, (int)W - 1);
-        rgb_pixel<KT, SKIP, true, kShareRgbTaps>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb,
-                                        (unsigned)y * W + (unsigned)xc, HW, HWs, Ws, nullptr, 0, 0, 1, x < (int)W);
-      }
+      const int x = tx * TW + p % TW, y = y_begin + p / TW;
+      if (x >= (int)W) continue;
+      rgb_pixel<KT, SKIP, true>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
     }
   }
 }
@@ -1503,22 +1425,17 @@ k_warp_fuse_rgb(const WFArgs a) {
   const int b = blockIdx.x / (a.tiles_x * a.tiles_y);
   const unsigned x = (unsigned)(tile % a.tiles_x) * 32u + (threadIdx.x & 31u);
   const unsigned y = (unsigned)(tile / a.tiles_x) * 8u + (threadIdx.x >> 5);
-  if (y >= (unsigned)a.H) return;  // warp-uniform
-  bool live = x < W;
-  if constexpr (SKIP) {
-    if (!live) return;
-  }
-  // !SKIP: the warp stays converged (tap sharing by shuffle); lanes beyond the right edge repeat the last column
-  const unsigned pix = y * W + (live ? x : W - 1u);
+  if (x >= W || y >= (unsigned)a.H) return;
+  const unsigned pix = y * W + x;
   const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
   const size_t bK = (size_t)b * KT * HW;
-  rgb_pixel_lean<KT, SKIP, !SKIP>(a, a.rgb + r * KT * 3 * (size_t)HWs, reinterpret_cast<const float2*>(a.grid) + bK,
+  rgb_pixel_lean<KT, SKIP>(a, a.rgb + r * KT * 3 * (size_t)HWs, reinterpret_cast<const float2*>(a.grid) + bK,
                       a.logits ? a.logits + bK : nullptr, a.vis ? a.vis + bK : nullptr,
                       (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr,
                       a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr,
                       (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr,
                       (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr, a.out_rgb + (size_t)b * 3 * HW, pix, HW,
-                      HWs, Ws, live);
+                      HWs, Ws);
 }
 
 template <int KT>

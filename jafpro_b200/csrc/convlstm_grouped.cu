@@ -38,7 +38,8 @@ constexpr int kThreadsHalf = 512;  // two CTAs per SM (64 registers per thread e
 constexpr int kHalfSmem = 112 * 1024;
 constexpr int kThreadsQuarter = 256;  // four CTAs per SM: more staging / MMA / epilogue phases of different tiles overlap
 constexpr int kQuarterSmem = 55 * 1024;
-constexpr int kRing = 3;        // weight stages in flight
+constexpr int kRing = 3;        // weight stages in flight the plan guarantees (it then deepens the ring into the free shared memory)
+constexpr int kMaxRing = 16;
 constexpr int kMaxSmem = 232448 - 1024;
 
 struct FastDiv {
@@ -67,7 +68,7 @@ struct GArgs {
   int tiles_per_group;
   FastDiv d_hpwp, d_wp, d_nb;  // persistent kernel: position -> (image, band, row, column) without divisions
   int C8, U;         // persistent kernel: 8-channel chunks of the staged window, K units (9 * C8)
-  int ring;          // persistent kernel: weight k-steps in flight
+  int ring;          // weight stages (k_convlstm_grouped) / k-steps (persistent kernel) in flight
   long ntiles;       // persistent kernel: G * tiles_per_group
   uint32_t idesc, a_half, stage_bytes, tmem_cols;
 };
@@ -163,21 +164,22 @@ __device__ __forceinline__ unsigned long long gtime() {
   { __VA_ARGS__; }
 #endif
 
-// Warp 0: weight stream + MMA issue (one thread).  Warps 1..31: activation staging, then the gate epilogue
-// (warps 1..28: seven warps per TMEM lane quarter).
+// Warp 0: MMA issue (one thread).  Last warp: weight stream (one thread).  The warps between: activation staging, then
+// the gate epilogue (warps 1..28 of 32: seven warps per TMEM lane quarter).
 __global__ void __launch_bounds__(kThreads, 1)
 k_convlstm_grouped(const GArgs a) {
   PROF_STAMP(t_start);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   uint8_t* sA = smem;                       // [hi | lo] x [Ctp/8 chunks][R rows][16 B]
-  uint8_t* sB = smem + 2 * a.a_half;        // kRing x stage_bytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kRing * a.stage_bytes);
-  uint64_t* full_bar = bars;                // [kRing]  bulk copy -> MMA
-  uint64_t* empty_bar = bars + kRing;       // [kRing]  MMA -> bulk copy
-  uint64_t* aready_bar = bars + 2 * kRing;  // staging -> MMA
-  uint64_t* tfull_bar = bars + 2 * kRing + 1;  // MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRing + 2);
+  uint8_t* sB = smem + 2 * a.a_half;        // ring x stage_bytes
+  const int ring = a.ring;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)ring * a.stage_bytes);
+  uint64_t* full_bar = bars;                      // [ring]  bulk copy -> MMA
+  uint64_t* empty_bar = bars + kMaxRing;          // [ring]  MMA -> bulk copy
+  uint64_t* aready_bar = bars + 2 * kMaxRing;     // staging -> MMA
+  uint64_t* tfull_bar = bars + 2 * kMaxRing + 1;  // MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxRing + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x % a.tiles_per_group;
@@ -188,11 +190,11 @@ k_convlstm_grouped(const GArgs a) {
   const int mt_here = (int)min((long)a.MT, (p_end - p0 + 127) / 128);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRing; ++s) {
+    for (int s = 0; s < ring; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(aready_bar, blockDim.x - 32);
+    mbar_init(aready_bar, blockDim.x - 64);
     mbar_init(tfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -206,18 +208,22 @@ k_convlstm_grouped(const GArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);  // warp-uniform by construction
 
-  if (warp == 0) {
-    // ===================== weight stream + MMA issue (warp-uniform; lane 0 is the leader) =====================
-    // The issue rate of this single thread bounds the small-N MMAs, so everything is kept in descriptor
-    // units (16 B) and advanced with adds: a descriptor's low 14 bits are the start address >> 4.
-    {
-      const bool leader = lane == 0;  // == the lane elect.sync picks (lowest active), so commits track these MMAs
+  const int last_warp = (int)(blockDim.x >> 5) - 1;  // weight stream (never an epilogue warp, see nsets below)
+  if (warp == last_warp) {
+    // ===================== weight stream: bulk copies through the ring, decoupled from the MMA issue =====================
+    // (Issued from the MMA warp the refill of a slot had to wait for that slot's MMAs to COMPLETE before the next
+    // stage's MMAs could be issued; per-role timers put the MMA warp of the 48- and 96-channel levels at 250-320 cycles
+    // per MMA against the 128-cycle floor.)
+    if (lane == 0) {
       const uint8_t* wg = a.wpack + (size_t)g * a.S * 64 * a.N;
       const uint32_t stage_bytes = a.stage_bytes;
       const int nstages = a.nstages, KS = a.KS;
-      // one stage = KS k-steps of this slice's rows.  A k-step of the pack is [hi | lo][2 chunks][N rows][16 B]; a slice
-      // is a contiguous run of Ns rows in each of the four blocks (one copy when the cell is not sliced)
-      auto load_stage = [&](int st, int slot) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int st = 0; st < nstages; ++st) {
+        if (st >= ring) mbar_wait(&empty_bar[slot], phase ^ 1u);  // the MMAs that read the slot's previous stage are done
+        // one stage = KS k-steps of this slice's rows.  A k-step of the pack is [hi | lo][2 chunks][N rows][16 B]; a
+        // slice is a contiguous run of Ns rows in each of the four blocks (one copy when the cell is not sliced)
         uint8_t* dst = sB + (size_t)slot * stage_bytes;
         mbar_expect_tx(&full_bar[slot], stage_bytes);
         if (a.CS == 1) {
@@ -231,11 +237,20 @@ k_convlstm_grouped(const GArgs a) {
               bulk_g2s(dst + (size_t)(j * 4 + blk) * run, src + (size_t)blk * 16 * a.N, run, &full_bar[slot]);
           }
         }
-      };
-      const int pre = min(kRing, nstages);
-      if (leader) {
-        for (int st = 0; st < pre; ++st) load_stage(st, st);
+        if (++slot == ring) {
+          slot = 0;
+          phase ^= 1u;
+        }
       }
+    }
+  } else if (warp == 0) {
+    // ===================== MMA issue (warp-uniform; lane 0 is the leader) =====================
+    // The issue rate of this single thread bounds the small-N MMAs, so everything is kept in descriptor
+    // units (16 B) and advanced with adds: a descriptor's low 14 bits are the start address >> 4.
+    {
+      const bool leader = lane == 0;  // == the lane elect.sync picks (lowest active), so commits track these MMAs
+      const uint32_t stage_bytes = a.stage_bytes;
+      const int nstages = a.nstages, KS = a.KS;
       const uint32_t N = (uint32_t)a.Ns, Nsub = (uint32_t)a.Nsub, R = (uint32_t)a.R, Wp = (uint32_t)a.Wp;  // N: rows of this slice
       const uint32_t idesc = a.idesc;
       const int nsplit = a.nsplit, spt = a.Ctp / 16;
@@ -248,9 +263,10 @@ k_convlstm_grouped(const GArgs a) {
       PROF_STAMP(t_aready);
       int kc = 0, kx = 0, ky = 0;
       uint32_t accf = 0;
+      int slot = 0;
+      uint32_t phase = 0;
       for (int st = 0; st < nstages; ++st) {
-        const int slot = st % kRing;
-        mbar_wait(&full_bar[slot], (uint32_t)(st / kRing) & 1u);
+        mbar_wait(&full_bar[slot], phase);
         tc_fence_after();
         uint32_t bh = b0 + (uint32_t)slot * stage_u;
         for (int j = 0; j < KS; ++j, bh += 4 * N) {
@@ -272,11 +288,9 @@ k_convlstm_grouped(const GArgs a) {
           }
         }
         if (leader) umma_commit(&empty_bar[slot]);
-        // refill the slot of the PREVIOUS stage (its MMAs were issued a stage ago) with stage st-1+kRing
-        if (st >= 1 && st - 1 + kRing < nstages) {
-          const int ps = (st - 1) % kRing;
-          mbar_wait(&empty_bar[ps], (uint32_t)((st - 1) / kRing) & 1u);
-          if (leader) load_stage(st - 1 + kRing, ps);
+        if (++slot == ring) {
+          slot = 0;
+          phase ^= 1u;
         }
       }
       if (leader) umma_commit(tfull_bar);
@@ -290,14 +304,14 @@ k_convlstm_grouped(const GArgs a) {
 #endif
     }
   } else {
-    // ===================== stage the activation rows (31 warps) =====================
+    // ===================== stage the activation rows (all warps but the first and the last) =====================
     const size_t HW = (size_t)a.H * a.W;
     {
       const int wid = threadIdx.x - 32;
       const long q0 = p0 - a.Wp - 1;
       const int npairs = a.Ctp / 16;
       const int items = a.R * npairs;  // (row, pair of 8-channel chunks): 16 independent loads in flight per thread
-      const int nworkers = (int)blockDim.x - 32;
+      const int nworkers = (int)blockDim.x - 64;
       for (int it = wid; it < items; it += nworkers) {
         const int cp = it / a.R, i = it - cp * a.R;
         const long q = q0 + i;
@@ -990,19 +1004,32 @@ static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_coun
   // Two launch shapes.  "Half": 512 threads, <= 112 KB and <= 256 TMEM columns per CTA, so two CTAs share an SM and
   // one stages / runs its epilogue while the other's MMAs execute.  "Full": 1024 threads, the whole SM, the largest
   // MT (smallest halo overhead).  Half is used when it fits and the grid is more than one wave of it.
+  constexpr long kBarBytes = (2 * kMaxRing + 2) * 8 + 16 + 128;  // barriers + TMEM slot + alignment slack
+  // the largest stage (KS k-steps, a divisor of S, at most stage_cap bytes) with which at least one accumulator tile and
+  // a ring of kRing stages fit; then the largest MT
   auto plan = [&](long smem_cap, int col_cap, long stage_cap, int& KS, int& MT) {
     KS = 1;
-    for (int ks = 1; ks <= a.S; ++ks)
-      if (a.S % ks == 0 && (long)ks * 64 * a.Ns <= stage_cap) KS = ks;
     MT = 0;
-    for (int m = 1; m <= 8; ++m) {
-      const long R = (long)m * 128 + 2L * a.Wp + 2;
-      const long sm = 4L * a.Ctp * R + (long)kRing * KS * 64 * a.Ns + 256 + 128;
-      if ((long)m * a.Ns <= col_cap && sm <= smem_cap && m <= tiles_total) MT = m;
+    for (int ks = a.S; ks >= 1 && MT == 0; --ks) {
+      if (a.S % ks != 0 || (ks > 1 && (long)ks * 64 * a.Ns > stage_cap)) continue;
+      for (int m = 1; m <= 8; ++m) {
+        const long R = (long)m * 128 + 2L * a.Wp + 2;
+        const long sm = 4L * a.Ctp * R + (long)kRing * ks * 64 * a.Ns + kBarBytes;
+        if ((long)m * a.Ns <= col_cap && sm <= smem_cap && m <= tiles_total) MT = m;
+      }
+      if (MT > 0) KS = ks;
     }
   };
   int ks_full, mt_full, ks_half, mt_half, ks_q, mt_q;
-  plan(kMaxSmem, 512, 28 * 1024, ks_full, mt_full);
+  // small stages: what counts for the weight stream is the bytes in flight, and a slot is refilled only when all its
+  // k-steps have been consumed (per-role timers on the 48- and 96-channel levels: the MMA warp spent half its time
+  // waiting for weights with three 24 KB stages)
+  static const long stage_cap_full = [] {
+    const char* e = getenv("JAF_CG_STAGE_KB");
+    const int v = e ? atoi(e) : 28;
+    return (long)(v >= 1 ? v : 28) * 1024;
+  }();
+  plan(kMaxSmem, 512, stage_cap_full, ks_full, mt_full);
   plan(kHalfSmem, 256, 10 * 1024, ks_half, mt_half);
   plan(kQuarterSmem, 128, 6 * 1024, ks_q, mt_q);
   if (mt_full < 1) {
@@ -1041,7 +1068,19 @@ static int plan_grouped(int G, int B, int Cin, int Ch, int H, int W, int sm_coun
   while (cols < (uint32_t)(MT * a.Ns)) cols <<= 1;
   a.tmem_cols = cols;
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Nsub >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  smem = 2 * (size_t)a.a_half + (size_t)kRing * a.stage_bytes + 256 + 128;
+  // the ring takes the shared memory the shape leaves free (the whole SM for the full shape)
+  const long cap = quarter ? kQuarterSmem : (half ? kHalfSmem : kMaxSmem);
+  long ring = (cap - 2L * a.a_half - kBarBytes) / (long)a.stage_bytes;
+  static const int ring_cap = [] {
+    const char* e = getenv("JAF_CG_RING");
+    const int v = e ? atoi(e) : kMaxRing;
+    return v >= kRing && v <= kMaxRing ? v : kMaxRing;
+  }();
+  if (ring > ring_cap) ring = ring_cap;
+  if (ring > a.nstages) ring = a.nstages;
+  if (ring < 1) ring = 1;
+  a.ring = (int)ring;
+  smem = 2 * (size_t)a.a_half + (size_t)ring * a.stage_bytes + kBarBytes;
   grid = (long)G * CS * a.tiles_per_group;
   if (grid >= (1L << 31)) {
     jaf::set_error("jaf_convlstm_step_grouped: too many tiles");

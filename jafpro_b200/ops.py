@@ -393,18 +393,42 @@ class FrameGraph:
     into those tensors with copy_ before `replay`); every kernel behind the C ABI is capture-safe (no allocation,
     synchronisation or host round trip inside a call)."""
 
-    def __init__(self, fn, warmup: int = 3):
+    def __init__(self, fn, warmup: int = 3, *, frames: int | None = None, lanes: int = 1):
+        """`fn()` is captured as it is.  With ``frames=n`` the callable is ``fn(t)`` for t in range(n) — n INDEPENDENT
+        frames (the reference's loop does not feed frame t-1 into frame t, conv_pro_test.py:255-278) — and frame t is
+        captured on lane ``t % lanes``: the graph gets `lanes` parallel branches, so the few-microsecond kernels of
+        several batch-1 frames overlap on the GPU instead of queueing behind each other.  Workspaces are per stream
+        (ops._workspace), so the branches do not share scratch."""
+        self.frames, self.lanes = frames, max(1, int(lanes))
+        self._fn = fn
+        self._lane_streams = [torch.cuda.Stream() for _ in range(self.lanes)] if (frames is not None and self.lanes > 1) else []
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):  # warm-up off the capture: one-time initialisation (workspaces, attributes)
             for _ in range(warmup):
-                fn()
+                self._run()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = fn()
+            self.out = self._run()
+
+    def _run(self):
+        if self.frames is None:
+            return self._fn()
+        if not self._lane_streams:
+            return [self._fn(t) for t in range(self.frames)]
+        cur = torch.cuda.current_stream()
+        outs = [None] * self.frames
+        for s in self._lane_streams:   # fork
+            s.wait_stream(cur)
+        for t in range(self.frames):
+            with torch.cuda.stream(self._lane_streams[t % self.lanes]):
+                outs[t] = self._fn(t)
+        for s in self._lane_streams:   # join
+            cur.wait_stream(s)
+        return outs
 
     def replay(self):
         self.graph.replay()

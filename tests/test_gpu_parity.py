@@ -842,6 +842,35 @@ def test_frame_graph_replays_the_batch_1_sequence_bit_identically():
     assert all(torch.equal(a, b) for a, b in zip(e2, outs)) and not torch.equal(e2[0], eager[0])
 
 
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_frame_graph_with_parallel_lanes_matches_eager(lanes):
+    """The frames of the reference's loop are independent (conv_pro_test.py:255-278 never feeds frame t-1 into frame t):
+    captured on `lanes` parallel graph branches (per-stream workspaces) they give the same bits as the eager loop."""
+    S, T = 64, 9
+    _, faces_idx = load_smpl_template()
+    f_idx = _cu(faces_idx)
+    cam, verts = synth.smpl_poses(T + 1, seed=37, device=DEV)
+    src = torch.randn(1, 1, 3, S, S, device=DEV)
+    fake, conf = torch.randn(T, 3, S, S, device=DEV), torch.rand(T, 1, S, S, device=DEV)
+    outs = [torch.empty(1, 3, S, S, device=DEV) for _ in range(T)]
+    sc, sv = cam[T:].reshape(1, 1, 3).contiguous(), verts[T:].reshape(1, 1, -1, 3).contiguous()
+
+    def frame(t):
+        ops.warp_fuse_from_poses(sc, sv, cam[t:t + 1], verts[t:t + 1], f_idx, S, rgb=src, fake=fake[t:t + 1],
+                                 conf=conf[t:t + 1], out_rgb=outs[t])
+        return outs[t]
+
+    eager = [frame(t).clone() for t in range(T)]
+    g = ops.FrameGraph(frame, frames=T, lanes=lanes)
+    for rep in range(3):
+        for o in outs:
+            o.zero_()
+        res = g.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(eager, res):
+            assert torch.equal(a, b), (lanes, rep)
+
+
 @pytest.mark.parametrize("K", [1, 3])
 def test_warp_fuse_from_poses_rgb_only(K):
     """The reference's per-frame chain at its own shapes (cal_flow -> warp_image -> mask -> confidence blend,
@@ -941,16 +970,18 @@ def test_convlstm_sequence_grouped_is_T_steps_in_one_call():
         assert torch.equal(hs[:, :, -1], h) and torch.equal(cl, c)
 
 
-def test_convlstm_cell_falls_back_when_the_tensor_core_plan_does_not_fit():
-    """Cin = Ch = 128 passes the channel-count rule of the grouped kernel but its row window + weight ring exceed the
-    SM's shared memory: the cell must take the exact-fp32 kernel instead of raising (the reference constructor accepts
-    any cell)."""
+@pytest.mark.parametrize("S,grouped", [(16, True), (100, False)])
+def test_convlstm_cell_falls_back_when_the_tensor_core_plan_does_not_fit(S, grouped):
+    """Cin = Ch = 128 passes the channel-count rule of the grouped kernel.  On a small map the planner slices the hidden
+    channels over CTAs and shrinks the weight stages until the cell fits; on a 100 x 100 map (too many tiles to slice)
+    the row window + weight ring exceed the SM's shared memory and the cell must take the exact-fp32 kernel instead of
+    raising (the reference constructor accepts any cell)."""
     from jafpro_b200.convLSTM import ConvLSTMCell
-    assert not ops.convlstm_grouped_supported(1, 1, 128, 128, 16, 16)
+    assert bool(ops.convlstm_grouped_supported(1, 1, 128, 128, S, S)) == grouped
     assert ops.convlstm_grouped_supported(24, 1, 24, 24, 100, 100)
     torch.manual_seed(3)
-    cell = ConvLSTMCell((16, 16), 128, 128, (3, 3), True).to(DEV)
-    x, h, c = (torch.randn(1, 128, 16, 16, device=DEV) for _ in range(3))
+    cell = ConvLSTMCell((S, S), 128, 128, (3, 3), True).to(DEV)
+    x, h, c = (torch.randn(1, 128, S, S, device=DEV) for _ in range(3))
     h2, c2 = cell(x, (h, c))
     cc = F.conv2d(torch.cat((x, h), 1).double(), cell.conv.weight.double(), cell.conv.bias.double(), padding=1)
     i, f, o, g = torch.split(cc, 128, dim=1)
