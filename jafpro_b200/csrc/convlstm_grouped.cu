@@ -67,6 +67,7 @@ struct GArgs {
   int S, KS, nstages;
   int tiles_per_group;
   FastDiv d_hpwp, d_wp, d_nb;  // persistent kernel: position -> (image, band, row, column) without divisions
+  FastDiv d_tpg;               // persistent kernel: tile -> cell (ntiles < 2^31)
   int C8, U;         // persistent kernel: 8-channel chunks of the staged window, K units (9 * C8)
   int ring;          // weight stages (k_convlstm_grouped) / k-steps (persistent kernel) in flight
   long ntiles;       // persistent kernel: G * tiles_per_group
@@ -221,7 +222,7 @@ k_convlstm_grouped(const GArgs a) {
       int slot = 0;
       uint32_t phase = 0;
       for (int st = 0; st < nstages; ++st) {
-        if (st >= ring) mbar_wait(&empty_bar[slot], phase ^ 1u);  // the MMAs that read the slot's previous stage are done
+        if (st >= ring) mbar_wait_relaxed(&empty_bar[slot], phase ^ 1u);  // the MMAs that read the slot's previous stage are done
         // one stage = KS k-steps of this slice's rows.  A k-step of the pack is [hi | lo][2 chunks][N rows][16 B]; a
         // slice is a contiguous run of Ns rows in each of the four blocks (one copy when the cell is not sliced)
         uint8_t* dst = sB + (size_t)slot * stage_bytes;
@@ -359,7 +360,7 @@ k_convlstm_grouped(const GArgs a) {
       const int nblk = a.Chs / 4;
       const int nitems = mt_here * nblk;  // (accumulator tile, block of 4 hidden channels)
       const float* bp = a.bias ? a.bias + (size_t)g * a.N : nullptr;
-      mbar_wait(tfull_bar, 0);
+      mbar_wait_relaxed(tfull_bar, 0);
       tc_fence_after();
       for (int it0 = set; it0 < nitems; it0 += 2 * nsets) {
         // two items per pass so that two sets of TMEM / global loads overlap.  The packed row order puts the four
@@ -561,8 +562,9 @@ __device__ __forceinline__ void epilogue_role_p(const GArgs& a, float* sX, uint6
   auto prep = [&](int it) {
     const long tile = first + it / kChunksPerSet;
     const int chunk = set + kEpiSets * (it % kChunksPerSet);
-    g_n = (int)(tile / a.tiles_per_group);
-    const long p0 = (long)a.Wp + 1 + (tile - (long)g_n * a.tiles_per_group) * kTileT + (long)chunk * 32;
+    uint32_t t_in_g;
+    g_n = (int)fdiv((uint32_t)tile, a.d_tpg, t_in_g);
+    const long p0 = (long)a.Wp + 1 + (long)t_in_g * kTileT + (long)chunk * 32;
     act_n = p0 < p_end;  // uniform over the set
 #ifdef JAF_PROBE_SKIP_EPI
     act_n = false;
@@ -607,7 +609,7 @@ __device__ __forceinline__ void epilogue_role_p(const GArgs& a, float* sX, uint6
         const int t4 = q * 32 + lane;
         if (t4 < rows) sbias[t4] = a.bias != nullptr ? __ldg(a.bias + (size_t)g_c * rows + t4) : 0.f;
       }
-      PROF_ACC(w_f, mbar_wait(&tfull[buf], ph));
+      PROF_ACC(w_f, mbar_wait_relaxed(&tfull[buf], ph));
       tc_fence_after();
     }
     // (1) dump this warp's raw gate rows of the chunk (TMEM lane = row gate*Ch + channel, column = pixel)
@@ -763,10 +765,11 @@ k_convlstm_grouped_p(const GArgs a) {
       int slot = 0;
       uint32_t wph = 0;
       for (int i = 0; i < n_here; ++i) {
-        const int g = (int)((first + i) / a.tiles_per_group);
+        uint32_t t_in_g_unused;
+        const int g = (int)fdiv((uint32_t)(first + i), a.d_tpg, t_in_g_unused);
         const uint8_t* wg = a.wpack + (size_t)g * a.S * a.stage_bytes;
         for (int ks = 0; ks < a.S; ++ks) {
-          mbar_wait(&wempty[slot], wph ^ 1u);
+          mbar_wait_relaxed(&wempty[slot], wph ^ 1u);
           mbar_expect_tx(&wfull[slot], a.stage_bytes);
           bulk_g2s(sW + (size_t)slot * a.stage_bytes, wg + (size_t)ks * a.stage_bytes, a.stage_bytes, &wfull[slot]);
           if (++slot == a.ring) {
@@ -787,11 +790,12 @@ k_convlstm_grouped_p(const GArgs a) {
       const int buf = i & 1;
       const uint32_t ph = (uint32_t)(i >> 1) & 1u;
       const long tile = first + i;
-      const int g = (int)(tile / a.tiles_per_group);
-      const long p0 = (long)a.Wp + 1 + (tile - (long)g * a.tiles_per_group) * kTileT;
+      uint32_t t_in_g;
+      const int g = (int)fdiv((uint32_t)tile, a.d_tpg, t_in_g);
+      const long p0 = (long)a.Wp + 1 + (long)t_in_g * kTileT;
       const long q0 = p0 - a.Wp - 1;
       uint8_t* dstb = sP + (size_t)buf * pbuf_bytes;
-      PROF_ACC(w_e, mbar_wait(&pempty[buf], ph ^ 1u));
+      PROF_ACC(w_e, mbar_wait_relaxed(&pempty[buf], ph ^ 1u));
 #ifdef JAF_PROBE_SKIP_STAGE
       for (int r = wid + (1 << 30); r < a.R; r += kStagerWarps * 32) {
 #else
@@ -1134,6 +1138,7 @@ static int plan_grouped_p(int G, int B, int Cin, int Ch, int H, int W, int sm_co
   a.d_hpwp = mk(a.HpWp);
   a.d_wp = mk(a.Wp);
   a.d_nb = mk(a.nb);
+  a.d_tpg = mk(a.tiles_per_group);
   const size_t pbuf = ((size_t)2 * a.a_half + 127) & ~(size_t)127;
   const size_t xb = ((size_t)kEpiSets * 4 * Ch * (kXPitch + 1) * 4 + 127) & ~(size_t)127;
   const size_t fixed = 2 * pbuf + xb + kRingPad + (2 * kMaxRingP + 9) * 8 + 128;
