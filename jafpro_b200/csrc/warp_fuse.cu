@@ -1314,6 +1314,149 @@ k_warp_fuse_nhwc_wide2(const WFArgs a) {
   }
 }
 
+// 5..8 references with the K <= 4 kernel's register budget: an EIGHT-lane group owns a pixel column.  Lane j prepares
+// reference j (one reference per lane, like the K <= 4 kernel).  Lanes j and j + 4 own the same 16 channels (32 bytes
+// per tap, one 256-bit load) and split the REFERENCES: the lower half of the group reduces references 0..3, the upper
+// half 4..K-1, each exactly like a 4-lane group of k_warp_fuse_nhwc_wide; the two partial sums are added across the
+// halves with 16 shuffles per row (x + y == y + x: both halves hold the same bits) and each half stores 8 of the 16
+// channels.  A lane holds one reference's taps at a time: 64 registers, 4 CTAs/SM, instead of the 80 registers / 3
+// CTAs of k_warp_fuse_nhwc_wide2 — and unlike the rounds flavour below nothing is serialised.  The sum over the
+// references is associated as (0..3) + (4..K-1) instead of left to right: same value within fp32 rounding.
+template <int KT, int MINB, bool SKIP>
+__global__ void __launch_bounds__(256, MINB)
+k_warp_fuse_nhwc_widesk(const WFArgs a) {
+  static_assert(KT >= 5 && KT <= 8, "two halves of four lanes, one reference per lane");
+  constexpr int LPP = 8, PPW = 4, TW = 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned PIXB = 128;  // bytes of one channels-last pixel (64 bf16)
+  int bid = blockIdx.x;
+  const int tx = bid % a.tiles_x;
+  bid /= a.tiles_x;
+  const int ty = bid % a.tiles_y;
+  const int b = bid / a.tiles_y;
+  const int y_begin = ty * a.rows_per_cta;
+  const int y_end = min(a.H, y_begin + a.rows_per_cta);
+  const unsigned W = (unsigned)a.W, Ws = (unsigned)a.Ws;
+  const unsigned HW = (unsigned)a.H * W, HWs = (unsigned)a.Hs * Ws;
+  const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
+  const size_t bK = (size_t)b * KT * HW;
+  const float* __restrict__ b_logit = a.logits ? a.logits + bK : nullptr;
+  const float* __restrict__ b_vis = a.vis ? a.vis + bK : nullptr;
+  const int* __restrict__ b_fim = (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr;
+  const float2* __restrict__ b_grid = reinterpret_cast<const float2*>(a.grid) + bK;
+  const float* __restrict__ b_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
+
+  // =========================== phase A: features ===========================
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPP, j = lane % LPP, gl = g * LPP;
+    const int half = j >> 2, jc = j & 3;  // which references this lane reduces; which 16 channels it owns
+    const bool mine = j < KT;             // lane j prepares reference j
+    const int x = tx * TW + warp * PPW + g;
+    const bool xin = x < (int)W;
+    const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + jc * 32;
+    char* __restrict__ o_lane = reinterpret_cast<char*>(a.out_feat) + (size_t)b * HW * PIXB + jc * 32 + half * 16;
+    const unsigned lane_in = (unsigned)(mine ? j : 0) * HW;
+    const uint64_t keep = l2_policy_evict_last();
+    unsigned pix = (unsigned)y_begin * W + (unsigned)x;
+#pragma unroll 1
+    for (int y = y_begin; y < y_end; ++y, pix += W) {
+      float lg = 0.f, v = 1.f;
+      float2 gxy = make_float2(0.f, 0.f);
+      if (xin) {
+        if (mine) {
+          gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pix)), keep);
+          if (b_logit) lg = ld_stream_keep_f32(b_logit + (lane_in + pix), keep);
+          if (b_vis) v = ld_stream_f32(b_vis + (lane_in + pix));
+        }
+        if (b_fim) v = (ld_stream_s32(b_fim + pix) != -1) ? 1.f : 0.f;
+        if (b_mask) v *= ld_stream_f32(b_mask + pix);
+      }
+      float m = mine ? lg : -CUDART_INF_F;
+#pragma unroll
+      for (int s = 4; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
+      const float e = mine ? expf(lg - m) : 0.f;
+      float ssum = e;
+#pragma unroll
+      for (int s = 1; s < 8; s <<= 1) ssum += __shfl_xor_sync(FULL, ssum, s);
+      const float aw = (xin && mine) ? __fdividef(e, ssum) * v : 0.f;
+      HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
+      t.nw *= aw;
+      t.ne *= aw;
+      t.sw *= aw;
+      t.se *= aw;
+      const unsigned off = (aw != 0.f) ? (unsigned)t.off : 0u;
+      const bool any = SKIP ? (__ballot_sync(FULL, aw != 0.f) != 0u) : true;
+
+      float2 acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
+      if (any) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int kidx = half * 4 + k;  // the reference this half reduces in step k
+          const int src = gl + kidx;
+          const unsigned osh = __shfl_sync(FULL, off, src);
+          float wt[4];
+          wt[0] = __shfl_sync(FULL, t.nw, src);
+          wt[1] = __shfl_sync(FULL, t.ne, src);
+          wt[2] = __shfl_sync(FULL, t.sw, src);
+          wt[3] = __shfl_sync(FULL, t.se, src);
+          if (KT == 8 || kidx < KT) {  // the upper half has fewer than four references when K < 8
+            const unsigned o0 = osh + (unsigned)kidx * HWs;
+            const char* p0 = f_lane + (size_t)o0 * PIXB;
+            const char* p1 = f_lane + (size_t)(o0 + Ws) * PIXB;
+            U256 q[4];
+            q[0] = ld_gather_u256(p0);
+            q[1] = ld_gather_u256(p0 + PIXB);
+            q[2] = ld_gather_u256(p1);
+            q[3] = ld_gather_u256(p1 + PIXB);
+#pragma unroll
+            for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+              const float2 w2 = make_float2(wt[tp], wt[tp]);
+              const uint32_t wd[8] = {q[tp].lo.x, q[tp].lo.y, q[tp].lo.z, q[tp].lo.w,
+                                      q[tp].hi.x, q[tp].hi.y, q[tp].hi.z, q[tp].hi.w};
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
+            }
+          }
+        }
+        // (references 0..3) + (references 4..K-1): both halves end up with the same bits
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          acc[c].x += __shfl_xor_sync(FULL, acc[c].x, 4);
+          acc[c].y += __shfl_xor_sync(FULL, acc[c].y, 4);
+        }
+      }
+      if (xin) {  // lower half: channels 0..7 of its 16, upper half: channels 8..15
+        const float2 s0 = half ? acc[4] : acc[0], s1 = half ? acc[5] : acc[1];
+        const float2 s2 = half ? acc[6] : acc[2], s3 = half ? acc[7] : acc[3];
+        uint4 ov;
+        ov.x = pack_bf16x2(s0.x, s0.y);
+        ov.y = pack_bf16x2(s1.x, s1.y);
+        ov.z = pack_bf16x2(s2.x, s2.y);
+        ov.w = pack_bf16x2(s3.x, s3.y);
+        st_stream_u128(reinterpret_cast<uint4*>(o_lane + (size_t)pix * PIXB), ov);
+      }
+    }
+  }
+
+  // =========================== phase B: RGB ===========================
+  if (a.rgb != nullptr && a.out_rgb != nullptr) {
+    const float* __restrict__ rgb_base = a.rgb + r * KT * 3 * (size_t)HWs;
+    const float* __restrict__ b_fake = (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr;
+    const float* __restrict__ b_conf = (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr;
+    float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
+    const int npx = TW * (y_end - y_begin);
+    for (int p = threadIdx.x; p < npx; p += 256) {
+      const int x = tx * TW + p % TW, y = y_begin + p / TW;
+      if (x >= (int)W) continue;
+      rgb_pixel<KT, SKIP, true>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
+    }
+  }
+}
+
 // (A/B flavour, JAF_WF_WIDE8_ROUNDS=1; measured slower than k_warp_fuse_nhwc_wide2, see wf_tune().)
 // 5..8 references in ROUNDS of four: the softmax terms of all K references are formed first (two logits per lane), but
 // the sample positions / bilinear weights of references 4..7 are built only after references 0..3 have been reduced
@@ -1747,6 +1890,8 @@ struct WFTune {
   int wide_rows;    // JAF_WF_WIDE_ROWS_PER_CTA: rows of a wide tile (64 columns)
   int rgb_merge;    // JAF_WF_RGB_MERGE: RGB planes inside the feature row loop (1) or as a second pass (0)
   int minb_poses;   // JAF_WF_MINB_POSES: CTAs/SM of the pose-driven kernel, K <= 4 (4 or 5)
+  int wide8_splitk; // JAF_WF_WIDE8_SPLITK: K = 5..8 on 8-lane groups whose halves split the references (64 registers, 4 CTAs/SM)
+  int splitk_rows;  // JAF_WF_SPLITK_ROWS: rows of a split-K tile (32 columns)
   int wide8_rounds; // JAF_WF_WIDE8_ROUNDS: K = 5..8 in rounds of four references (64 registers, 4 CTAs/SM) instead of
                     // two references per lane (80 registers, 3 CTAs/SM)
 };
@@ -1777,6 +1922,12 @@ const WFTune& wf_tune() {
     // 11.1 k (0.605): the second round's sample positions serialise behind the first round's reduction, which costs more
     // than the fourth resident CTA brings
     v.wide8_rounds = wf_env("JAF_WF_WIDE8_ROUNDS", 0);
+    // measured (profiles/r02_bench_ab.jsonl, 512^2 K=8, same box): split-K 11.0 k frames/s (0.600) dense / 10.4 k (0.565) hard
+    // vs two references per lane 11.2 k (0.612) / 10.6 k (0.580) — the fourth resident CTA buys nothing at this shape
+    // (SM clock 1.7-1.8 GHz under sw_power_cap for the whole 21 ms launch), so the flavour stays an A/B knob
+    v.wide8_splitk = wf_env("JAF_WF_WIDE8_SPLITK", 0);
+    v.splitk_rows = wf_env("JAF_WF_SPLITK_ROWS", 16);
+    if (v.splitk_rows < 1) v.splitk_rows = 16;
     return v;
   }();
   return t;
@@ -1864,6 +2015,21 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
       if (a.K <= 3) {
         const int wide_minb = 4;  // K < 4 carries one occupancy variant
         JAF_W(1, 4) JAF_W(2, 4) JAF_W(3, 4)
+      }
+      if (a.K >= 5 && tn.wide8_splitk != 0 && tn.wide8_rounds == 0) {
+        WFArgs s = a;
+        s.tiles_x = (s.W + 31) / 32;
+        s.rows_per_cta = s.H < tn.splitk_rows ? s.H : tn.splitk_rows;
+        s.tiles_y = (s.H + s.rows_per_cta - 1) / s.rows_per_cta;
+        const long grids = (long)s.tiles_x * s.tiles_y * s.B;
+        if (grids <= 0x7fffffffL) {
+#define JAF_WSK(KV) if (s.K == KV) { \
+          jaf::note_kernel("k_warp_fuse_nhwc_widesk<K=%d,MINB=4,SKIP=%d>", KV, (int)skip); \
+          if (skip) k_warp_fuse_nhwc_widesk<KV, 4, true><<<(unsigned)grids, 256, 0, st>>>(s); else k_warp_fuse_nhwc_widesk<KV, 4, false><<<(unsigned)grids, 256, 0, st>>>(s); \
+          return true; }
+          JAF_WSK(5) JAF_WSK(6) JAF_WSK(7) JAF_WSK(8)
+#undef JAF_WSK
+        }
       }
 #define JAF_W8R(KV) if (a.K == KV && tn.wide8_rounds != 0) { \
         jaf::note_kernel("k_warp_fuse_nhwc_wide2r<K=%d,MINB=4,SKIP=%d>", KV, (int)skip); \
@@ -2085,9 +2251,9 @@ extern "C" int jaf_tuning_info(char* buf, int n) {
   const int len = snprintf(tmp, sizeof(tmp),
                            "JAF_WF_WIDE=%d JAF_WF_WIDE_MINB=%d JAF_WF_WIDE_MINB8=%d JAF_WF_WIDE_ROWS_PER_CTA=%d "
                            "JAF_WF_RGB_MERGE=%d JAF_WF_MINB=%d JAF_WF_MINB_SKIP=%d JAF_WF_MINB_POSES=%d JAF_WF_ROWS=%d "
-                           "JAF_WF_ROWS_PER_CTA=%d JAF_WF_WIDE8_ROUNDS=%d",
+                           "JAF_WF_ROWS_PER_CTA=%d JAF_WF_WIDE8_ROUNDS=%d JAF_WF_WIDE8_SPLITK=%d JAF_WF_SPLITK_ROWS=%d",
                            t.wide, t.wide_minb, t.wide_minb8, t.wide_rows, t.rgb_merge, t.minb_dense, t.minb_skip,
-                           t.minb_poses, t.rows, t.rows_per_cta, t.wide8_rounds);
+                           t.minb_poses, t.rows, t.rows_per_cta, t.wide8_rounds, t.wide8_splitk, t.splitk_rows);
   if (buf != nullptr && n > 0) snprintf(buf, (size_t)n, "%s", tmp);
   return len + 1;
 }

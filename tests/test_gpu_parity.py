@@ -269,7 +269,7 @@ def test_warp_fuse_hot_kernel_matches_oracle(K, C):
     assert float((out_feat.float() - ref).abs().max()) <= 2e-2
 
 
-@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_warp_fuse_wide_lane_kernel_matches_oracle(K):
     """C = 64 without a visibility input takes the wide-lane kernel (4 lanes x 32 B per pixel, 256-bit gathers;
     two references per lane beyond K = 4).  Ragged sizes: W is not a multiple of the 64-column tile, H is odd."""
@@ -295,6 +295,38 @@ def test_warp_fuse_wide_lane_kernel_matches_oracle(K):
     assert float((rgb2 - out_rgb).abs().max()) <= 1e-5
     ok2, frac2 = _bf16_close(_bf16_bits(feat2.permute(0, 2, 3, 1).contiguous()), _bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()))
     assert ok2 and frac2 < 2e-3
+
+
+def test_split_k_flavour_matches_the_default_kernel_in_a_subprocess():
+    """JAF_WF_WIDE8_SPLITK=1 (A/B flavour for K = 5..8: 8-lane groups whose halves split the references) is read once per
+    process, so it is exercised in a child process: ragged sizes, K = 5..8, against the oracle with the same bounds as
+    the default kernel."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np, torch
+root = %r
+sys.path[:0] = [root, root + "/tests"]
+import oracle
+from test_gpu_parity import _rand_case, _cu, _np, _bf16_bits, _bf16_close
+from jafpro_b200 import ops, _lib
+torch.set_grad_enabled(False)
+for K in (5, 6, 7, 8):
+    B, H, W, C = 2, 37, 75, 64
+    c = _rand_case(B, K, C, H, W, seed=700 + K, Hs=29, Ws=58)
+    fb = oracle.f32_to_bf16_bits(c["feat"].transpose(0, 1, 3, 4, 2))
+    o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=fb, feat_layout="nhwc", feat_bf16=True, logits=c["logits"], tgt_mask=c["mask"])
+    feat = _cu(fb.view(np.int16)).view(torch.bfloat16).permute(0, 1, 4, 2, 3)
+    out_rgb, out_feat = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, logits=_cu(c["logits"]), tgt_mask=_cu(c["mask"]))
+    assert "widesk<K=%%d" %% K in _lib.last_kernel(), _lib.last_kernel()
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 1e-5
+    ok, frac = _bf16_close(_bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
+    assert ok and frac < 2e-3, (K, frac)
+print("split-k ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JAF_WF_WIDE8_SPLITK="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "split-k ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_warp_fuse_k1_is_exactly_warp_image_times_mask():
