@@ -344,9 +344,13 @@ def run_wf(args):
     # (A) the application's layout: K references per VIDEO held once in host memory, target frames index them
     #     through ref_index (what test/conv_pro_test.py keeps per video) -> headline e2e;
     # (B) the device benchmark's layout (every frame carries its own K references) for comparison.
-    Be = min(B, args.e2e_frames)
+    # e2e step = the workload's own step (all B frames of this GPU) unless --e2e-frames says otherwise; capped so that the
+    # pinned result buffers stay under ~3 GB per rank (512^2 frames are 37 MB each)
+    out_frame_bytes = S * S * (12 + 2 * C)
+    Be = min(B, args.e2e_frames) if args.e2e_frames > 0 else min(B, max(Fv, (3 << 30) // out_frame_bytes))
     nvid = max(1, Be // Fv)
     Be = min(Be, nvid * Fv)
+    Bb = min(Be, 60)  # the per-frame-references comparison keeps the short step (every frame uploads K references)
     pin = lambda t: t.cpu().contiguous().pin_memory()
     h = dict(grid=pin(inp["grid"][:Be]), logits=pin(inp["logits"][:Be]), mask=pin(inp["mask"][:Be]))
     h_fim = pin(inp["fim"][:Be]) if inp["fim"] is not None else None
@@ -354,8 +358,8 @@ def run_wf(args):
     hv_rgb = pin(inp["rgb"][vid_first])
     hv_feat = pin(feat[vid_first].permute(0, 1, 3, 4, 2)) if feat is not None else None
     ref_index = torch.tensor([i // Fv for i in range(Be)], dtype=torch.int32)
-    hf_rgb = pin(inp["rgb"][:Be])
-    hf_feat = pin(feat[:Be].permute(0, 1, 3, 4, 2)) if feat is not None else None
+    hf_rgb = pin(inp["rgb"][:Bb])
+    hf_feat = pin(feat[:Bb].permute(0, 1, 3, 4, 2)) if feat is not None else None
     o_rgb = torch.empty((Be, 3, S, S), dtype=torch.float32).pin_memory()
     o_feat = torch.empty((Be, S, S, C), dtype=torch.bfloat16).pin_memory() if feat is not None else None
 
@@ -364,8 +368,9 @@ def run_wf(args):
             ops.warp_fuse_host(h["grid"], rgb=hv_rgb, feat=hv_feat, feat_channels_last=True, logits=h["logits"],
                                fim=h_fim, tgt_mask=h["mask"], ref_index=ref_index, out_rgb=o_rgb, out_feat=o_feat)
         else:
-            ops.warp_fuse_host(h["grid"], rgb=hf_rgb, feat=hf_feat, feat_channels_last=True, logits=h["logits"],
-                               fim=h_fim, tgt_mask=h["mask"], out_rgb=o_rgb, out_feat=o_feat)
+            ops.warp_fuse_host(h["grid"][:Bb], rgb=hf_rgb, feat=hf_feat, feat_channels_last=True, logits=h["logits"][:Bb],
+                               fim=h_fim[:Bb] if h_fim is not None else None, tgt_mask=h["mask"][:Bb], out_rgb=o_rgb[:Bb],
+                               out_feat=o_feat[:Bb] if o_feat is not None else None)
 
     def time_e2e(per_video):
         for _ in range(3):
@@ -378,12 +383,12 @@ def run_wf(args):
             e2e_step(per_video)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1000.0
-        mx, fr = jd.reduce_max_sum(ms, float(Be * n), device=dev)
+        mx, fr = jd.reduce_max_sum(ms, float((Be if per_video else Bb) * n), device=dev)
         return fr / (mx / 1000.0)
 
     nbytes = lambda ts: sum(t.numel() * t.element_size() for t in ts if t is not None)
     e2e_frame_refs = time_e2e(False)
-    ok_b = bool(torch.equal(out[0][:Be].cpu(), o_rgb))
+    ok_b = bool(torch.equal(out[0][:Bb].cpu(), o_rgb[:Bb]))
     e2e_video_refs = time_e2e(True)
     chk_rgb, _ = ops.warp_fuse(inp["grid"][:Be].contiguous(), rgb=inp["rgb"][vid_first].contiguous(),
                                feat=feat[vid_first] if feat is not None else None, logits=inp["logits"][:Be].contiguous(),
@@ -392,7 +397,7 @@ def run_wf(args):
     e2e_ok = ok_b and bool(torch.equal(chk_rgb.cpu(), o_rgb))
     common = list(h.values()) + [h_fim]
     h2d = nbytes(common + [hv_rgb, hv_feat, ref_index])
-    h2d_b = nbytes(common + [hf_rgb, hf_feat])
+    h2d_b = nbytes([t[:Bb] for t in common if t is not None] + [hf_rgb, hf_feat])
     d2h = nbytes([o_rgb, o_feat])
     del hf_rgb, hf_feat
 
@@ -471,7 +476,7 @@ def run_wf(args):
         "e2e": {"value": round(e2e_video_refs, 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "frames_per_step": Be,
                 "refs": "K references per video, uploaded every step, frames index them via ref_index",
-                "per_frame_refs": {"value": round(e2e_frame_refs, 1), "h2d_bytes_per_step": int(h2d_b),
+                "per_frame_refs": {"value": round(e2e_frame_refs, 1), "h2d_bytes_per_step": int(h2d_b), "frames_per_step": Bb,
                                    "note": "every frame carries its own K references (the device benchmark's layout)"},
                 "api": "jafpro_b200.fusion.warp_fuse_host -> jaf_warp_fuse_host (pinned host buffers)",
                 "matches_device_path": e2e_ok, "cpu_affinity_bound_to_gpu": bool(numa_bound),
@@ -998,7 +1003,7 @@ def main():
     ap.add_argument("--flow", default="dense", choices=FLOWS,
                     help="dense: every pixel visible, smooth <= 8 px displacement (headline); smpl: real transfer flows, ~12%% "
                          "foreground; hard: full coverage, piecewise-affine with rotation / scale / +-64 px; perm: random permutation")
-    ap.add_argument("--e2e-frames", type=int, default=60)
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step (0 = the workload's whole per-GPU step)")
     ap.add_argument("--videos-per-gpu", type=int, default=0, help="override the workload's videos per GPU (profiling)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

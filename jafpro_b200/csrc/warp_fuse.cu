@@ -1060,9 +1060,17 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
           const char* p1 = f_lane + (size_t)(o0 + Ws) * PIXB;
           U256 q[4];
           q[0] = ld_gather_u256(p0);
-          q[1] = ld_gather_u256(p0 + PIXB);
           q[2] = ld_gather_u256(p1);
+#if defined(JAF_PROBE_TAPS) && JAF_PROBE_TAPS == 2   // what-if probes (WRONG results): upper bound of any tap-sharing scheme
+          q[1] = q[0];
+          q[3] = q[2];
+#elif defined(JAF_PROBE_TAPS) && JAF_PROBE_TAPS == 3
+          q[1] = ld_gather_u256(p0 + PIXB);
+          q[3] = q[2];
+#else
+          q[1] = ld_gather_u256(p0 + PIXB);
           q[3] = ld_gather_u256(p1 + PIXB);
+#endif
           float rv[4];
           if constexpr (RGBM) {
             const float* r0 = rgb_cta + (osh + (unsigned)(3 * k) * HWs + rgb_c);
