@@ -959,6 +959,20 @@ __device__ __forceinline__ U256 ld_gather_u256(const void* p) {
   return v;
 }
 
+// The same gather issued only by the lanes whose `take` is set (the others get unspecified registers).
+__device__ __forceinline__ U256 ld_gather_u256_if(const void* p, bool take) {
+  U256 v;
+  asm("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %9, 0;\n\t@pp ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+      : "=r"(v.lo.x), "=r"(v.lo.y), "=r"(v.lo.z), "=r"(v.lo.w), "=r"(v.hi.x), "=r"(v.hi.y), "=r"(v.hi.z), "=r"(v.hi.w)
+      : "l"(p), "r"((uint32_t)take));
+  return v;
+}
+// coh ? (the same word of the pixel group one to the right: lane + 4) : own
+__device__ __forceinline__ uint32_t right_word(uint32_t left, uint32_t own, bool coh) {
+  const uint32_t t = __shfl_down_sync(0xffffffffu, left, 4);
+  return coh ? t : own;
+}
+
 // RGBM ("RGB merged"): the RGB planes are produced inside the feature row loop instead of a second pass over the
 // tile.  In the reduction over the references every lane of the pixel group already receives reference k's corner
 // offset and its four bilinear weights (pre-multiplied by softmax * visibility * mask) by shuffle; lane c < 3 of the
@@ -1008,6 +1022,9 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
     // merged RGB: CTA-uniform 64-bit base + 32-bit per-lane offsets (lane 3 shadows plane 0 and stores nothing)
     const float* __restrict__ rgb_cta = RGBM ? a.rgb + r * KT * 3 * (size_t)HWs : nullptr;
     const unsigned rgb_c = (j < 3 ? (unsigned)j : 0u) * HWs;
+#if defined(JAF_PROBE_TAPS) && JAF_PROBE_TAPS == 5
+    uint32_t probe_sink = 0;
+#endif
 #pragma unroll 1
     for (int y = y_begin; y < y_end; ++y, pix += W) {
       float lg = 0.f, v = 1.f;
@@ -1051,7 +1068,11 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
       if (any) {
+#if defined(JAF_WF_XTAP_UNROLL1)
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int k = 0; k < KT; ++k) {
           const int src = gl + k;
           const unsigned osh = __shfl_sync(FULL, off, src);
@@ -1067,6 +1088,28 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
 #elif defined(JAF_PROBE_TAPS) && JAF_PROBE_TAPS == 3
           q[1] = ld_gather_u256(p0 + PIXB);
           q[3] = q[2];
+#elif defined(JAF_PROBE_TAPS) && JAF_PROBE_TAPS == 4   // the se gather dropped, its unpack kept (runtime-zero xor defeats CSE)
+          q[1] = ld_gather_u256(p0 + PIXB);
+          {
+            const uint32_t z = blockIdx.x >> 31;
+            q[3].lo = make_uint4(q[2].lo.x ^ z, q[2].lo.y ^ z, q[2].lo.z ^ z, q[2].lo.w ^ z);
+            q[3].hi = make_uint4(q[2].hi.x ^ z, q[2].hi.y ^ z, q[2].hi.z ^ z, q[2].hi.w ^ z);
+          }
+#elif defined(JAF_WF_XTAP)
+          // the ne / se taps of this pixel are the nw / sw taps of the pixel group to the right whenever that group's
+          // corner is one column further: take them from its registers (8 shuffles per tap) instead of gathering the
+          // same line a second time; groups whose neighbour samples elsewhere (and the last group of the warp) gather
+          const unsigned osh_r = __shfl_down_sync(FULL, osh, 4);
+          const bool coh = lane < 28 && osh_r == osh + 1u;
+          q[1] = ld_gather_u256_if(p0 + PIXB, !coh);
+          q[3] = ld_gather_u256_if(p1 + PIXB, !coh);
+#elif defined(JAF_PROBE_TAPS) && JAF_PROBE_TAPS == 5   // the se gather kept (folded into a sink), its unpack shared with sw
+          q[1] = ld_gather_u256(p0 + PIXB);
+          {
+            const U256 t3 = ld_gather_u256(p1 + PIXB);
+            probe_sink ^= t3.lo.x ^ t3.lo.y ^ t3.lo.z ^ t3.lo.w ^ t3.hi.x ^ t3.hi.y ^ t3.hi.z ^ t3.hi.w;
+            q[3] = q[2];
+          }
 #else
           q[1] = ld_gather_u256(p0 + PIXB);
           q[3] = ld_gather_u256(p1 + PIXB);
@@ -1091,8 +1134,18 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
 #pragma unroll
           for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
             const float2 w2 = make_float2(wt[tp], wt[tp]);
+#if defined(JAF_WF_XTAP)
+            // odd taps (ne, se): the words come from the right-hand group's even tap when its corner is adjacent
+            const int te = tp & ~1;
+            const uint32_t wd[8] = {
+                (tp & 1) ? right_word(q[te].lo.x, q[tp].lo.x, coh) : q[tp].lo.x, (tp & 1) ? right_word(q[te].lo.y, q[tp].lo.y, coh) : q[tp].lo.y,
+                (tp & 1) ? right_word(q[te].lo.z, q[tp].lo.z, coh) : q[tp].lo.z, (tp & 1) ? right_word(q[te].lo.w, q[tp].lo.w, coh) : q[tp].lo.w,
+                (tp & 1) ? right_word(q[te].hi.x, q[tp].hi.x, coh) : q[tp].hi.x, (tp & 1) ? right_word(q[te].hi.y, q[tp].hi.y, coh) : q[tp].hi.y,
+                (tp & 1) ? right_word(q[te].hi.z, q[tp].hi.z, coh) : q[tp].hi.z, (tp & 1) ? right_word(q[te].hi.w, q[tp].hi.w, coh) : q[tp].hi.w};
+#else
             const uint32_t wd[8] = {q[tp].lo.x, q[tp].lo.y, q[tp].lo.z, q[tp].lo.w,
                                     q[tp].hi.x, q[tp].hi.y, q[tp].hi.z, q[tp].hi.w};
+#endif
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
@@ -1122,6 +1175,9 @@ k_warp_fuse_nhwc_wide(const WFArgs a) {
         }
       }
     }
+#if defined(JAF_PROBE_TAPS) && JAF_PROBE_TAPS == 5
+    if (probe_sink == 0x9e3779b9u && a.out_rgb != nullptr) a.out_rgb[0] = 0.f;  // keeps the probe's loads alive
+#endif
   }
 
   // =========================== phase B: RGB (two-pass flavour) ===========================
