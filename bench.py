@@ -996,7 +996,7 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)  # the driver's own call uses --steps 20 --warmup 5
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dancevideo_256_k4_c64", choices=sorted(WF_WORKLOADS) + list(AUX_WORKLOADS))
