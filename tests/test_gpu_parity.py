@@ -297,6 +297,47 @@ def test_warp_fuse_wide_lane_kernel_matches_oracle(K):
     assert ok2 and frac2 < 2e-3
 
 
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_warp_fuse_random_configurations_match_the_oracle(seed):
+    """Randomised sweep over the argument space of row F: batch, K = 1..8, channel count / layout / dtype of the features,
+    ragged target and source sizes, reference sets shared through ref_index, and every optional input (logits, per-reference
+    visibility or a face-index map, 1- or 3-channel target mask, confidence blend, align_corners) — whichever kernel the
+    dispatcher picks must agree with the CPU oracle within the north star's bounds."""
+    rng = np.random.default_rng(4242 + seed)
+    B, K = int(rng.integers(1, 4)), int(rng.integers(1, 9))
+    H, W = int(rng.integers(3, 70)), int(rng.integers(3, 90))
+    Hs, Ws = int(rng.integers(2, 60)), int(rng.integers(2, 75))
+    nhwc = bool(rng.integers(0, 2))
+    C = int(rng.choice([32, 64, 128])) if nhwc else int(rng.integers(1, 20))
+    R = int(rng.integers(1, B + 1))
+    c = _rand_case(B, K, C, H, W, seed=9000 + seed, Hs=Hs, Ws=Ws, R=R)
+    ref_index = rng.integers(0, R, size=B).astype(np.int32) if (R != B or rng.integers(0, 2)) else None
+    use_logits, use_mask, use_blend = bool(rng.integers(0, 2)), int(rng.integers(0, 3)), bool(rng.integers(0, 2))
+    vis_kind = int(rng.integers(0, 3))  # 0 none, 1 per-reference visibility, 2 face-index map
+    ac = bool(rng.integers(0, 2))
+    mask = None if use_mask == 0 else (c["mask"] if use_mask == 1 else np.repeat(c["mask"], 3, axis=1) * (rng.random((B, 3, H, W)) > 0.1))
+    mask = None if mask is None else np.ascontiguousarray(mask, np.float32)
+    kw_o = dict(logits=c["logits"] if use_logits else None, vis=c["vis"] if vis_kind == 1 else None,
+                fim=c["fim"] if vis_kind == 2 else None, tgt_mask=mask, fake=c["fake"] if use_blend else None,
+                conf=c["conf"] if use_blend else None, ref_index=ref_index, align_corners=ac)
+    kw_g = {k: (None if v is None else (v if isinstance(v, bool) else _cu(v))) for k, v in kw_o.items()}
+    if nhwc:
+        fb = oracle.f32_to_bf16_bits(c["feat"].transpose(0, 1, 3, 4, 2))
+        o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=fb, feat_layout="nhwc", feat_bf16=True, **kw_o)
+        feat = _cu(fb.view(np.int16)).view(torch.bfloat16).permute(0, 1, 4, 2, 3)
+    else:
+        o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=c["feat"], **kw_o)
+        feat = _cu(c["feat"])
+    out_rgb, out_feat = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, **kw_g)
+    what = (seed, B, K, C, H, W, Hs, Ws, nhwc, R, use_logits, use_mask, use_blend, vis_kind, ac, _lib.last_kernel())
+    assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 1e-5, what
+    if nhwc:
+        ok, frac = _bf16_close(_bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
+        assert ok and frac < 5e-3, (what, frac)
+    else:
+        assert float(np.abs(_np(out_feat) - o["out_feat"]).max()) <= 1e-4, what
+
+
 def test_split_k_flavour_matches_the_default_kernel_in_a_subprocess():
     """JAF_WF_WIDE8_SPLITK=1 (A/B flavour for K = 5..8: 8-lane groups whose halves split the references) is read once per
     process, so it is exercised in a child process: ragged sizes, K = 5..8, against the oracle with the same bounds as
@@ -699,6 +740,37 @@ def test_convlstm_grouped_cells_vs_fp64(G, B, Cin, Ch, H, W):
     # the exact-fp32 CUDA-core cell agrees as well (same interface, G = 1 per call)
     h3, c3 = ops.convlstm_step(x[0], h[0], c[0], wgt[0], None)
     assert float((c3 - c2[0]).abs().max()) <= 1e-4 and float((h3 - h2[0]).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_convlstm_grouped_random_shapes_vs_fp64(seed):
+    """Randomised sweep over what the planner has to place: narrow cells (operand-swapped persistent kernel), wide ones
+    (un-swapped kernel: full / half launch shapes, hidden-channel slices, weight-ring depths), odd map sizes, several
+    bands, batch > 1, Cin != Ch.  Unsupported combinations must say so; supported ones meet 1e-4 against fp64."""
+    rng = np.random.default_rng(77 + seed)
+    G, B = int(rng.integers(1, 7)), int(rng.integers(1, 4))
+    Ch = int(rng.choice([4, 8, 12, 16, 24, 32, 40, 48, 64, 96, 128]))
+    Cin = int(rng.integers(1, 2 * Ch + 1))
+    H, W = int(rng.integers(3, 64)), int(rng.integers(3, 110))
+    if not ops.convlstm_grouped_supported(G, B, Cin, Ch, H, W):
+        with pytest.raises(RuntimeError):
+            ops.convlstm_step_grouped(torch.zeros(G, B, Cin, H, W, device=DEV), torch.zeros(G, B, Ch, H, W, device=DEV),
+                                      torch.zeros(G, B, Ch, H, W, device=DEV),
+                                      ops.convlstm_gpack_weight(torch.zeros(G, 4 * Ch, Cin + Ch, 3, 3, device=DEV), Cin, Ch),
+                                      None, Cin, Ch)
+        return
+    torch.manual_seed(seed)
+    x, h, c = (torch.randn(G, B, n, H, W, device=DEV) for n in (Cin, Ch, Ch))
+    wgt = torch.randn(G, 4 * Ch, Cin + Ch, 3, 3, device=DEV) * (1.5 / (9 * (Cin + Ch)) ** 0.5)
+    bias = torch.randn(G, 4 * Ch, device=DEV)
+    h2, c2 = ops.convlstm_step_grouped(x, h, c, ops.convlstm_gpack_weight(wgt, Cin, Ch), bias, Cin, Ch)
+    for g in range(G):
+        cc = F.conv2d(torch.cat((x[g], h[g]), 1).double(), wgt[g].double(), bias[g].double(), padding=1)
+        i, f, o, gg = torch.split(cc, Ch, dim=1)
+        c_r = torch.sigmoid(f) * c[g].double() + torch.sigmoid(i) * torch.tanh(gg)
+        h_r = torch.sigmoid(o) * torch.tanh(c_r)
+        ec, eh = float((c2[g].double() - c_r).abs().max()), float((h2[g].double() - h_r).abs().max())
+        assert ec <= 1e-4 and eh <= 1e-4, (seed, G, B, Cin, Ch, H, W, g, ec, eh)
 
 
 def test_convlstm_grouped_rejects_unsupported_shapes():
