@@ -773,6 +773,29 @@ def test_convlstm_grouped_random_shapes_vs_fp64(seed):
         assert ec <= 1e-4 and eh <= 1e-4, (seed, G, B, Cin, Ch, H, W, g, ec, eh)
 
 
+def test_run_concurrently_gives_the_serial_results():
+    """The pyramid levels of a recurrent step are independent: one side stream per level (fork / join by events), eager
+    and captured in a CUDA graph, gives the bits of the serial loop."""
+    levels = []
+    for Ch, S in [(12, 40), (24, 20), (48, 9)]:
+        torch.manual_seed(Ch)
+        x, h, c = (torch.randn(3, 1, Ch, S, S, device=DEV) for _ in range(3))
+        w = torch.randn(3, 4 * Ch, 2 * Ch, 3, 3, device=DEV) * 0.05
+        levels.append((x, h, c, ops.convlstm_gpack_weight(w, Ch, Ch), Ch))
+    step = lambda lv: ops.convlstm_step_grouped(lv[0], lv[1], lv[2], lv[3], None, lv[4], lv[4])
+    serial = [step(lv) for lv in levels]
+    fns = [(lambda lv=lv: step(lv)) for lv in levels]
+    forked = ops.run_concurrently(fns)
+    torch.cuda.synchronize()
+    for (h1, c1), (h2, c2) in zip(serial, forked):
+        assert torch.equal(h1, h2) and torch.equal(c1, c2)
+    g = ops.FrameGraph(lambda: ops.run_concurrently(fns))
+    res = g.replay()
+    torch.cuda.synchronize()
+    for (h1, c1), (h2, c2) in zip(serial, res):
+        assert torch.equal(h1, h2) and torch.equal(c1, c2)
+
+
 def test_convlstm_grouped_rejects_unsupported_shapes():
     assert _lib.lib().jaf_convlstm_gpack_bytes(1, 12, 10) == 0   # Ch % 4
     assert _lib.lib().jaf_convlstm_gpack_bytes(1, 12, 256) == 0  # 4*Ch > 512 TMEM columns

@@ -55,6 +55,35 @@ def main():
                           "max_abs_err_vs_fp64": err, "TFLOPs_useful": round(flop / t_g / 1e9, 1),
                           "GBps_compulsory": round(byts / t_g / 1e6, 1)}))
     print(json.dumps({"config": "a13 whole pyramid (5 levels x 24 parts), one step", **{k + "_ms": round(v, 4) for k, v in tot.items()}}))
+    # the five levels of a step are independent (src/networks.py:1346-1355 runs five separate ConvLSTMs): the whole pyramid
+    # step (a) back to back on one stream, (b) one stream per level (fork / join by events), (c) = (b) as a CUDA graph
+    lv = []
+    for Ch, S in LEVELS:
+        torch.manual_seed(Ch + S)
+        x, h, c = (torch.randn(G, B, Ch, S, S, device=DEV) for _ in range(3))
+        w = torch.randn(G, 4 * Ch, 2 * Ch, 3, 3, device=DEV) * (1.5 / (18 * Ch) ** 0.5)
+        b = torch.randn(G, 4 * Ch, device=DEV)
+        ho, co = torch.empty_like(h), torch.empty_like(c)
+        lv.append((x, h, c, ops.convlstm_gpack_weight(w, Ch, Ch), b, Ch, ho, co))
+
+    def serial():
+        for x, h, c, wp, b, Ch, ho, co in lv:
+            ops.convlstm_step_grouped(x, h, c, wp, b, Ch, Ch)
+
+    def forked(order=(0, 1, 2, 3, 4)):
+        return ops.run_concurrently([(lambda t=lv[i]: ops.convlstm_step_grouped(t[0], t[1], t[2], t[3], t[4], t[5], t[5]))
+                                     for i in order])
+
+    res = {"config": "a13 whole pyramid step as ONE unit of work"}
+    res["serial_one_stream_ms"] = round(timeit(serial, n=30)[0], 4)
+    # (eager: the results are handed to the current stream with record_stream, so the caching allocator needs a long
+    # warm-up before its per-stream pools stop growing; the graph flavour below is the intended use)
+    res["one_stream_per_level_ms"] = round(timeit(forked, n=30, warm=60)[0], 4)
+    g = ops.FrameGraph(serial)
+    res["serial_cuda_graph_ms"] = round(timeit(g.replay, n=30)[0], 4)
+    g2 = ops.FrameGraph(forked)
+    res["one_stream_per_level_cuda_graph_ms"] = round(timeit(g2.replay, n=30)[0], 4)
+    print(json.dumps(res))
 
 
 if __name__ == "__main__":
