@@ -1378,6 +1378,298 @@ k_warp_fuse_nhwc_wide2(const WFArgs a) {
   }
 }
 
+// NO-SHUFFLE flavour of k_warp_fuse_nhwc_wide (A/B, JAF_WF_WIDE_NOSHFL=1; K <= 4, no visibility input): every lane of the
+// 4-lane pixel group loads the flow samples / logits of ALL K references of its pixel (the four lanes read the same
+// addresses: one line per load instruction, broadcast) and builds every reference's taps itself, instead of lane k
+// preparing reference k and broadcasting corner + weights with 5 shuffles per reference.  Shuffles are LSU / L1TEX
+// instructions — the resource that bounds this kernel — while the redundant arithmetic runs on
+// pipes that have slack.  Same operations in the same order per channel: bit-identical to the shuffle flavour.
+template <int KT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_warp_fuse_nhwc_wide_ns(const WFArgs a) {
+  static_assert(KT <= 4, "register budget");
+  constexpr int LPP = 4, PPW = 8, TW = 64;
+  constexpr unsigned PIXB = 128;  // bytes of one channels-last pixel (64 bf16)
+  int bid = blockIdx.x;
+  const int tx = bid % a.tiles_x;
+  bid /= a.tiles_x;
+  const int ty = bid % a.tiles_y;
+  const int b = bid / a.tiles_y;
+  const int y_begin = ty * a.rows_per_cta;
+  const int y_end = min(a.H, y_begin + a.rows_per_cta);
+  const unsigned W = (unsigned)a.W, Ws = (unsigned)a.Ws;
+  const unsigned HW = (unsigned)a.H * W, HWs = (unsigned)a.Hs * Ws;
+  const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
+  const size_t bK = (size_t)b * KT * HW;
+  const float* __restrict__ b_logit = a.logits ? a.logits + bK : nullptr;
+  const float2* __restrict__ b_grid = reinterpret_cast<const float2*>(a.grid) + bK;
+  const float* __restrict__ b_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
+
+  // =========================== phase A: features ===========================
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPP, j = lane % LPP;
+    const int x = tx * TW + warp * PPW + g;
+    const bool xin = x < (int)W;
+    const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + j * 32;
+    char* __restrict__ o_lane = reinterpret_cast<char*>(a.out_feat) + (size_t)b * HW * PIXB + j * 32;
+    const uint64_t keep = l2_policy_evict_last();
+    unsigned pix = (unsigned)y_begin * W + (unsigned)x;
+#pragma unroll 1
+    for (int y = y_begin; y < y_end; ++y, pix += W) {
+      float lg[KT];
+      float2 gxy[KT];
+      float v = 1.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        gxy[k] = make_float2(0.f, 0.f);
+        lg[k] = 0.f;
+        if (xin) {
+          gxy[k] = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + ((unsigned)k * HW + pix)), keep);
+          if (b_logit) lg[k] = ld_stream_keep_f32(b_logit + ((unsigned)k * HW + pix), keep);
+        }
+      }
+      if (xin && b_mask) v = ld_stream_f32(b_mask + pix);
+      // softmax over the K references, in the association of the shuffle flavour: (e0 + e1) + (e2 + e3) for K = 4
+      float m = lg[0];
+#pragma unroll
+      for (int k = 1; k < KT; ++k) m = fmaxf(m, lg[k]);
+#pragma unroll
+      for (int k = 0; k < KT; ++k) lg[k] = expf(lg[k] - m);
+      float ssum;
+      if constexpr (KT == 4) ssum = (lg[0] + lg[1]) + (lg[2] + lg[3]);
+      else if constexpr (KT == 3) ssum = ((0.f + lg[0]) + lg[1]) + lg[2];
+      else if constexpr (KT == 2) ssum = lg[0] + lg[1];
+      else ssum = lg[0];
+
+      float2 acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const float aw = xin ? __fdividef(lg[k], ssum) * v : 0.f;
+        HotTap t = make_hot_tap(gxy[k].x, gxy[k].y, (int)Ws, a.Hs, a.align_corners);
+        const float wt[4] = {t.nw * aw, t.ne * aw, t.sw * aw, t.se * aw};
+        const unsigned o0 = ((aw != 0.f) ? (unsigned)t.off : 0u) + (unsigned)k * HWs;
+        const char* p0 = f_lane + (size_t)o0 * PIXB;
+        const char* p1 = f_lane + (size_t)(o0 + Ws) * PIXB;
+        U256 q[4];
+        q[0] = ld_gather_u256(p0);
+        q[1] = ld_gather_u256(p0 + PIXB);
+        q[2] = ld_gather_u256(p1);
+        q[3] = ld_gather_u256(p1 + PIXB);
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+          const float2 w2 = make_float2(wt[tp], wt[tp]);
+          const uint32_t wd[8] = {q[tp].lo.x, q[tp].lo.y, q[tp].lo.z, q[tp].lo.w,
+                                  q[tp].hi.x, q[tp].hi.y, q[tp].hi.z, q[tp].hi.w};
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            acc[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acc[c]);
+        }
+      }
+      if (xin) {
+        uint4 o0v, o1v;
+        o0v.x = pack_bf16x2(acc[0].x, acc[0].y); o0v.y = pack_bf16x2(acc[1].x, acc[1].y);
+        o0v.z = pack_bf16x2(acc[2].x, acc[2].y); o0v.w = pack_bf16x2(acc[3].x, acc[3].y);
+        o1v.x = pack_bf16x2(acc[4].x, acc[4].y); o1v.y = pack_bf16x2(acc[5].x, acc[5].y);
+        o1v.z = pack_bf16x2(acc[6].x, acc[6].y); o1v.w = pack_bf16x2(acc[7].x, acc[7].y);
+        uint4* op = reinterpret_cast<uint4*>(o_lane + (size_t)pix * PIXB);
+        st_stream_u128(op, o0v);
+        st_stream_u128(op + 1, o1v);
+      }
+    }
+  }
+
+  // =========================== phase B: RGB ===========================
+  if (a.rgb != nullptr && a.out_rgb != nullptr) {
+    const float* __restrict__ rgb_base = a.rgb + r * KT * 3 * (size_t)HWs;
+    const float* __restrict__ b_fake = (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr;
+    const float* __restrict__ b_conf = (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr;
+    float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
+    const int npx = TW * (y_end - y_begin);
+    for (int p = threadIdx.x; p < npx; p += 256) {
+      const int x = tx * TW + p % TW, y = y_begin + p / TW;
+      if (x >= (int)W) continue;
+      rgb_pixel<KT, false>(a, rgb_base, b_grid, b_logit, nullptr, nullptr, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
+    }
+  }
+}
+
+// The gather issued only by the lanes whose `take` is set (the others keep unspecified registers).
+__device__ __forceinline__ uint4 ld_gather_u128_if(const void* p, bool take) {
+  uint4 v;
+  asm("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %5, 0;\n\t@pp ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];\n\t}"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(p), "r"((uint32_t)take));
+  return v;
+}
+
+// PAIR flavour (A/B, JAF_WF_PAIR=1): an eight-lane group owns TWO x-adjacent pixels and 8 channels per lane (16 bytes per
+// tap).  The ne / se taps of the left pixel ARE the nw / sw taps of the right pixel whenever the right pixel's corner is one
+// column further (per reference; true for most pixels of a locally translation-like flow): the group then gathers 3 columns
+// x 2 rows = 6 taps for its 8 tap uses and the shared column never leaves the registers (no shuffle: the what-if probes put
+// a tap that is not gathered at +10 %, and data shuffles cost more L1TEX time than the gather they replace).
+// Pairs whose corners are not adjacent gather the right pixel's own nw / sw (predicated) and select.  Lanes 0..3 of a
+// group prepare references 0..3 of the left pixel, lanes 4..7 those of the right pixel; per channel the arithmetic and its
+// order are those of k_warp_fuse_nhwc_wide (bit-identical results).
+template <int KT, int MINB, bool SKIP>
+__global__ void __launch_bounds__(256, MINB)
+k_warp_fuse_nhwc_pair(const WFArgs a) {
+  static_assert(KT <= 4, "four lanes of a half group, one reference per lane");
+  constexpr int TW = 64;         // 8 warps x 4 groups x 2 pixels
+  constexpr bool KPOW2 = (KT & (KT - 1)) == 0;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned PIXB = 128;  // bytes of one channels-last pixel (64 bf16)
+  int bid = blockIdx.x;
+  const int tx = bid % a.tiles_x;
+  bid /= a.tiles_x;
+  const int ty = bid % a.tiles_y;
+  const int b = bid / a.tiles_y;
+  const int y_begin = ty * a.rows_per_cta;
+  const int y_end = min(a.H, y_begin + a.rows_per_cta);
+  const unsigned W = (unsigned)a.W, Ws = (unsigned)a.Ws;
+  const unsigned HW = (unsigned)a.H * W, HWs = (unsigned)a.Hs * Ws;
+  const size_t r = a.ref_index ? (size_t)a.ref_index[b] : (size_t)b;
+  const size_t bK = (size_t)b * KT * HW;
+  const float* __restrict__ b_logit = a.logits ? a.logits + bK : nullptr;
+  const float* __restrict__ b_vis = a.vis ? a.vis + bK : nullptr;
+  const int* __restrict__ b_fim = (!a.vis && a.fim) ? a.fim + (size_t)b * HW : nullptr;
+  const float2* __restrict__ b_grid = reinterpret_cast<const float2*>(a.grid) + bK;
+  const float* __restrict__ b_mask = a.tgt_mask ? a.tgt_mask + (size_t)b * a.mask_c * HW : nullptr;
+
+  // =========================== phase A: features ===========================
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, j = lane & 7, gl = g * 8;
+    const int half = j >> 2, kk = (j & 3) % KT;  // which pixel of the pair / which reference this lane prepares
+    const int xa = tx * TW + warp * 8 + g * 2;   // left pixel of the pair
+    const int xm = xa + half;                    // the pixel this lane prepares
+    const bool xin_m = xm < (int)W, xin_a = xa < (int)W, xin_b = xa + 1 < (int)W;
+    const char* __restrict__ f_lane = reinterpret_cast<const char*>(a.feat) + r * KT * (size_t)HWs * PIXB + j * 16;
+    char* __restrict__ o_lane = reinterpret_cast<char*>(a.out_feat) + (size_t)b * HW * PIXB + j * 16;
+    const unsigned lane_in = (unsigned)kk * HW;
+    const uint64_t keep = l2_policy_evict_last();
+    unsigned pix = (unsigned)y_begin * W + (unsigned)xa;
+#pragma unroll 1
+    for (int y = y_begin; y < y_end; ++y, pix += W) {
+      float lg = 0.f, v = 1.f;
+      float2 gxy = make_float2(0.f, 0.f);
+      if (xin_m) {
+        const unsigned pm = pix + (unsigned)half;
+        gxy = ld_stream_keep_f32x2(reinterpret_cast<const float*>(b_grid + (lane_in + pm)), keep);
+        if (b_logit) lg = ld_stream_keep_f32(b_logit + (lane_in + pm), keep);
+        if (b_vis) v = ld_stream_f32(b_vis + (lane_in + pm));
+        if (b_fim) v = (ld_stream_s32(b_fim + pm) != -1) ? 1.f : 0.f;
+        if (b_mask) v *= ld_stream_f32(b_mask + pm);
+      }
+      float m = lg, ssum;
+      if constexpr (KPOW2) {
+#pragma unroll
+        for (int s2 = KT / 2; s2 > 0; s2 >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s2));
+      } else {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) m = fmaxf(m, __shfl_sync(FULL, lg, gl + half * 4 + k));
+      }
+      const float e = expf(lg - m);
+      if constexpr (KPOW2) {
+        ssum = e;
+#pragma unroll
+        for (int s2 = 1; s2 < KT; s2 <<= 1) ssum += __shfl_xor_sync(FULL, ssum, s2);
+      } else {
+        ssum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) ssum += __shfl_sync(FULL, e, gl + half * 4 + k);
+      }
+      const float aw = xin_m ? __fdividef(e, ssum) * v : 0.f;
+      HotTap t = make_hot_tap(gxy.x, gxy.y, (int)Ws, a.Hs, a.align_corners);
+      t.nw *= aw;
+      t.ne *= aw;
+      t.sw *= aw;
+      t.se *= aw;
+      const unsigned off = (aw != 0.f) ? (unsigned)t.off : 0u;
+      const bool any = SKIP ? (__ballot_sync(FULL, aw != 0.f) != 0u) : true;
+
+      float2 acca[4], accb[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acca[c] = accb[c] = make_float2(0.f, 0.f);
+      if (any) {
+#pragma unroll 1  // unrolled, the fallback registers of several references are live at once and spill (148 B at 64 registers)
+        for (int k = 0; k < KT; ++k) {
+          const unsigned oa = __shfl_sync(FULL, off, gl + k) + (unsigned)k * HWs;
+          const unsigned ob = __shfl_sync(FULL, off, gl + 4 + k) + (unsigned)k * HWs;
+          const bool coh = ob == oa + 1u;  // uniform over the group
+          const char* pa = f_lane + (size_t)oa * PIXB;
+          const char* pb = f_lane + (size_t)ob * PIXB;
+          uint4 qa[4], qb[4];
+          qa[0] = ld_gather_u128(reinterpret_cast<const uint4*>(pa));
+          qa[1] = ld_gather_u128(reinterpret_cast<const uint4*>(pa + PIXB));
+          qa[2] = ld_gather_u128(reinterpret_cast<const uint4*>(pa + (size_t)Ws * PIXB));
+          qa[3] = ld_gather_u128(reinterpret_cast<const uint4*>(pa + (size_t)Ws * PIXB + PIXB));
+          qb[1] = ld_gather_u128(reinterpret_cast<const uint4*>(pb + PIXB));
+          qb[3] = ld_gather_u128(reinterpret_cast<const uint4*>(pb + (size_t)Ws * PIXB + PIXB));
+          qb[0] = ld_gather_u128_if(pb, !coh);
+          qb[2] = ld_gather_u128_if(pb + (size_t)Ws * PIXB, !coh);
+          float wa[4], wb[4];
+          wa[0] = __shfl_sync(FULL, t.nw, gl + k);
+          wa[1] = __shfl_sync(FULL, t.ne, gl + k);
+          wa[2] = __shfl_sync(FULL, t.sw, gl + k);
+          wa[3] = __shfl_sync(FULL, t.se, gl + k);
+#pragma unroll
+          for (int tp = 0; tp < 4; ++tp) {  // nw, ne, sw, se: ATen's accumulation order
+            const float2 w2 = make_float2(wa[tp], wa[tp]);
+            const uint32_t wd[4] = {qa[tp].x, qa[tp].y, qa[tp].z, qa[tp].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acca[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, acca[c]);
+          }
+          // the right pixel: its nw / sw taps are the left pixel's ne / se when the corners are adjacent
+          qb[0].x = coh ? qa[1].x : qb[0].x; qb[0].y = coh ? qa[1].y : qb[0].y;
+          qb[0].z = coh ? qa[1].z : qb[0].z; qb[0].w = coh ? qa[1].w : qb[0].w;
+          qb[2].x = coh ? qa[3].x : qb[2].x; qb[2].y = coh ? qa[3].y : qb[2].y;
+          qb[2].z = coh ? qa[3].z : qb[2].z; qb[2].w = coh ? qa[3].w : qb[2].w;
+          wb[0] = __shfl_sync(FULL, t.nw, gl + 4 + k);
+          wb[1] = __shfl_sync(FULL, t.ne, gl + 4 + k);
+          wb[2] = __shfl_sync(FULL, t.sw, gl + 4 + k);
+          wb[3] = __shfl_sync(FULL, t.se, gl + 4 + k);
+#pragma unroll
+          for (int tp = 0; tp < 4; ++tp) {
+            const float2 w2 = make_float2(wb[tp], wb[tp]);
+            const uint32_t wd[4] = {qb[tp].x, qb[tp].y, qb[tp].z, qb[tp].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) accb[c] = __ffma2_rn(make_float2(bf16_lo(wd[c]), bf16_hi(wd[c])), w2, accb[c]);
+          }
+        }
+      }
+      if (xin_a) {
+        uint4 o;
+        o.x = pack_bf16x2(acca[0].x, acca[0].y); o.y = pack_bf16x2(acca[1].x, acca[1].y);
+        o.z = pack_bf16x2(acca[2].x, acca[2].y); o.w = pack_bf16x2(acca[3].x, acca[3].y);
+        st_stream_u128(reinterpret_cast<uint4*>(o_lane + (size_t)pix * PIXB), o);
+      }
+      if (xin_b) {
+        uint4 o;
+        o.x = pack_bf16x2(accb[0].x, accb[0].y); o.y = pack_bf16x2(accb[1].x, accb[1].y);
+        o.z = pack_bf16x2(accb[2].x, accb[2].y); o.w = pack_bf16x2(accb[3].x, accb[3].y);
+        st_stream_u128(reinterpret_cast<uint4*>(o_lane + (size_t)(pix + 1u) * PIXB), o);
+      }
+    }
+  }
+
+  // =========================== phase B: RGB ===========================
+  if (a.rgb != nullptr && a.out_rgb != nullptr) {
+    const float* __restrict__ rgb_base = a.rgb + r * KT * 3 * (size_t)HWs;
+    const float* __restrict__ b_fake = (a.fake && a.conf) ? a.fake + (size_t)b * 3 * HW : nullptr;
+    const float* __restrict__ b_conf = (a.fake && a.conf) ? a.conf + (size_t)b * HW : nullptr;
+    float* __restrict__ b_orgb = a.out_rgb + (size_t)b * 3 * HW;
+    const int npx = TW * (y_end - y_begin);
+    for (int p = threadIdx.x; p < npx; p += 256) {
+      const int x = tx * TW + p % TW, y = y_begin + p / TW;
+      if (x >= (int)W) continue;
+      rgb_pixel<KT, SKIP>(a, rgb_base, b_grid, b_logit, b_vis, b_fim, b_mask, b_fake, b_conf, b_orgb, (unsigned)y * W + (unsigned)x, HW, HWs, Ws);
+    }
+  }
+}
+
 // 5..8 references with the K <= 4 kernel's register budget: an EIGHT-lane group owns a pixel column.  Lane j prepares
 // reference j (one reference per lane, like the K <= 4 kernel).  Lanes j and j + 4 own the same 16 channels (32 bytes
 // per tap, one 256-bit load) and split the REFERENCES: the lower half of the group reduces references 0..3, the upper
@@ -1954,6 +2246,8 @@ struct WFTune {
   int wide_rows;    // JAF_WF_WIDE_ROWS_PER_CTA: rows of a wide tile (64 columns)
   int rgb_merge;    // JAF_WF_RGB_MERGE: RGB planes inside the feature row loop (1) or as a second pass (0)
   int minb_poses;   // JAF_WF_MINB_POSES: CTAs/SM of the pose-driven kernel, K <= 4 (4 or 5)
+  int noshfl;       // JAF_WF_WIDE_NOSHFL: K <= 4 wide kernel in which every lane prepares all K references (no shuffles)
+  int pair;         // JAF_WF_PAIR: K <= 4, C = 64 on 8-lane groups that own a PAIR of adjacent pixels (shared tap column in registers)
   int wide8_splitk; // JAF_WF_WIDE8_SPLITK: K = 5..8 on 8-lane groups whose halves split the references (64 registers, 4 CTAs/SM)
   int splitk_rows;  // JAF_WF_SPLITK_ROWS: rows of a split-K tile (32 columns)
   int wide8_rounds; // JAF_WF_WIDE8_ROUNDS: K = 5..8 in rounds of four references (64 registers, 4 CTAs/SM) instead of
@@ -1990,6 +2284,8 @@ const WFTune& wf_tune() {
     // vs two references per lane 11.2 k (0.612) / 10.6 k (0.580) — the fourth resident CTA buys nothing at this shape
     // (SM clock 1.7-1.8 GHz under sw_power_cap for the whole 21 ms launch), so the flavour stays an A/B knob
     v.wide8_splitk = wf_env("JAF_WF_WIDE8_SPLITK", 0);
+    v.pair = wf_env("JAF_WF_PAIR", 0);
+    v.noshfl = wf_env("JAF_WF_WIDE_NOSHFL", 0);
     v.splitk_rows = wf_env("JAF_WF_SPLITK_ROWS", 16);
     if (v.splitk_rows < 1) v.splitk_rows = 16;
     return v;
@@ -2070,6 +2366,24 @@ bool launch_nhwc(WFArgs a, cudaStream_t st) {
     if (gridw <= 0x7fffffffL) {
       const bool skip = a.vis != nullptr || a.fim != nullptr;
       const bool rgbm = tn.rgb_merge != 0 && a.rgb != nullptr && a.out_rgb != nullptr && a.mask_c == 1;
+      if (tn.noshfl != 0 && a.K <= 4 && !skip) {
+#define JAF_WN(KV) if (a.K == KV) { \
+        jaf::note_kernel("k_warp_fuse_nhwc_wide_ns<K=%d,MINB=%d>", KV, tn.noshfl == 3 ? 3 : 4); \
+        if (tn.noshfl == 3) k_warp_fuse_nhwc_wide_ns<KV, 3><<<(unsigned)gridw, 256, 0, st>>>(a); \
+        else k_warp_fuse_nhwc_wide_ns<KV, 4><<<(unsigned)gridw, 256, 0, st>>>(a); \
+        return true; }
+        JAF_WN(1) JAF_WN(2) JAF_WN(3) JAF_WN(4)
+#undef JAF_WN
+      }
+      if (tn.pair != 0 && a.K <= 4 && !skip) {
+#define JAF_WP(KV) if (a.K == KV) { \
+        jaf::note_kernel("k_warp_fuse_nhwc_pair<K=%d,MINB=%d,SKIP=0>", KV, tn.pair == 3 ? 3 : 4); \
+        if (tn.pair == 3) k_warp_fuse_nhwc_pair<KV, 3, false><<<(unsigned)gridw, 256, 0, st>>>(a); \
+        else k_warp_fuse_nhwc_pair<KV, 4, false><<<(unsigned)gridw, 256, 0, st>>>(a); \
+        return true; }
+        JAF_WP(1) JAF_WP(2) JAF_WP(3) JAF_WP(4)
+#undef JAF_WP
+      }
 #define JAF_W(KV, MB) if (a.K == KV && wide_minb == MB) { \
         jaf::note_kernel("k_warp_fuse_nhwc_wide<K=%d,MINB=%d,SKIP=%d,RGBM=%d>", KV, MB, (int)skip, (int)rgbm); \
         if (skip) { if (rgbm) k_warp_fuse_nhwc_wide<KV, MB, true, true><<<(unsigned)gridw, 256, 0, st>>>(a); else k_warp_fuse_nhwc_wide<KV, MB, true, false><<<(unsigned)gridw, 256, 0, st>>>(a); } \
@@ -2315,9 +2629,9 @@ extern "C" int jaf_tuning_info(char* buf, int n) {
   const int len = snprintf(tmp, sizeof(tmp),
                            "JAF_WF_WIDE=%d JAF_WF_WIDE_MINB=%d JAF_WF_WIDE_MINB8=%d JAF_WF_WIDE_ROWS_PER_CTA=%d "
                            "JAF_WF_RGB_MERGE=%d JAF_WF_MINB=%d JAF_WF_MINB_SKIP=%d JAF_WF_MINB_POSES=%d JAF_WF_ROWS=%d "
-                           "JAF_WF_ROWS_PER_CTA=%d JAF_WF_WIDE8_ROUNDS=%d JAF_WF_WIDE8_SPLITK=%d JAF_WF_SPLITK_ROWS=%d",
+                           "JAF_WF_ROWS_PER_CTA=%d JAF_WF_WIDE8_ROUNDS=%d JAF_WF_WIDE8_SPLITK=%d JAF_WF_SPLITK_ROWS=%d JAF_WF_PAIR=%d JAF_WF_WIDE_NOSHFL=%d",
                            t.wide, t.wide_minb, t.wide_minb8, t.wide_rows, t.rgb_merge, t.minb_dense, t.minb_skip,
-                           t.minb_poses, t.rows, t.rows_per_cta, t.wide8_rounds, t.wide8_splitk, t.splitk_rows);
+                           t.minb_poses, t.rows, t.rows_per_cta, t.wide8_rounds, t.wide8_splitk, t.splitk_rows, t.pair, t.noshfl);
   if (buf != nullptr && n > 0) snprintf(buf, (size_t)n, "%s", tmp);
   return len + 1;
 }

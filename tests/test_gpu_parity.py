@@ -338,10 +338,14 @@ def test_warp_fuse_random_configurations_match_the_oracle(seed):
         assert float(np.abs(_np(out_feat) - o["out_feat"]).max()) <= 1e-4, what
 
 
-def test_split_k_flavour_matches_the_default_kernel_in_a_subprocess():
-    """JAF_WF_WIDE8_SPLITK=1 (A/B flavour for K = 5..8: 8-lane groups whose halves split the references) is read once per
-    process, so it is exercised in a child process: ragged sizes, K = 5..8, against the oracle with the same bounds as
-    the default kernel."""
+@pytest.mark.parametrize("knob,ks,label", [("JAF_WF_WIDE8_SPLITK", (5, 6, 7, 8), "widesk<K=%d"),
+                                           ("JAF_WF_PAIR", (1, 2, 3, 4), "pair<K=%d"),
+                                           ("JAF_WF_WIDE_NOSHFL", (1, 2, 3, 4), "wide_ns<K=%d")])
+def test_ab_flavours_of_the_wide_kernel_match_the_oracle_in_a_subprocess(knob, ks, label):
+    """The A/B flavours kept behind environment knobs (read once per process, so each runs in a child process): K = 5..8 on
+    8-lane groups whose halves split the references; 8-lane groups that own a PAIR of adjacent pixels (shared tap column in
+    registers); the no-shuffle kernel in which every lane prepares all K references.  Ragged sizes, against the oracle with
+    the bounds of the default kernel."""
     import subprocess
     import sys
     code = r"""
@@ -352,22 +356,23 @@ import oracle
 from test_gpu_parity import _rand_case, _cu, _np, _bf16_bits, _bf16_close
 from jafpro_b200 import ops, _lib
 torch.set_grad_enabled(False)
-for K in (5, 6, 7, 8):
+for K in %r:
     B, H, W, C = 2, 37, 75, 64
     c = _rand_case(B, K, C, H, W, seed=700 + K, Hs=29, Ws=58)
     fb = oracle.f32_to_bf16_bits(c["feat"].transpose(0, 1, 3, 4, 2))
     o = oracle.warp_fuse(c["grid"], rgb=c["rgb"], feat=fb, feat_layout="nhwc", feat_bf16=True, logits=c["logits"], tgt_mask=c["mask"])
     feat = _cu(fb.view(np.int16)).view(torch.bfloat16).permute(0, 1, 4, 2, 3)
     out_rgb, out_feat = ops.warp_fuse(_cu(c["grid"]), rgb=_cu(c["rgb"]), feat=feat, logits=_cu(c["logits"]), tgt_mask=_cu(c["mask"]))
-    assert "widesk<K=%%d" %% K in _lib.last_kernel(), _lib.last_kernel()
+    assert (%r %% K) in _lib.last_kernel(), _lib.last_kernel()
     assert float(np.abs(_np(out_rgb) - o["out_rgb"]).max()) <= 1e-5
     ok, frac = _bf16_close(_bf16_bits(out_feat.permute(0, 2, 3, 1).contiguous()), o["out_feat"])
     assert ok and frac < 2e-3, (K, frac)
-print("split-k ok")
-""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, JAF_WF_WIDE8_SPLITK="1")
+print("flavour ok")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), tuple(ks), label)
+    env = dict(os.environ)
+    env[knob] = "1"
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "split-k ok" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "flavour ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_warp_fuse_k1_is_exactly_warp_image_times_mask():
